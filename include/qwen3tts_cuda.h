@@ -1,0 +1,187 @@
+/*
+ * libqwen3tts_cuda -- C ABI of the B200-native (sm_100a) 12 Hz speech-tokenizer DECODER
+ * (codec token grids [B,16,T] int32 -> 24 kHz float PCM).
+ *
+ * Drop-in boundary for ONE path of AtomGradient/swift-qwen3-tts.  Every entry point names
+ * the reference interface it replaces (paths relative to the reference repo;
+ * ST.swift = Sources/Qwen3TTS/Models/SpeechTokenizer.swift,
+ * Q3.swift = Sources/Qwen3TTS/Models/Qwen3.swift, Cfg.swift = Sources/Qwen3TTS/Models/Config.swift).
+ *
+ * Plain C: pointers and sizes only.  No PyTorch / MLX types, no CPU fallback: every compute
+ * entry point fails with Q3TTS_ECUDA when no sm_100 device is usable.
+ * Buffers are caller-owned; the library owns device weights and a grow-only workspace per model.
+ * Calls on the same handle are serialised internally; use one handle per GPU.
+ */
+#ifndef QWEN3TTS_CUDA_H
+#define QWEN3TTS_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define Q3TTS_ABI_VERSION 1
+
+/* ---- status codes (returned by every function that returns int) ------------------------ */
+enum {
+  Q3TTS_OK = 0,
+  Q3TTS_EINVAL = 1,   /* bad argument / shape / code id >= codebook size (checked on device)  */
+  Q3TTS_EIO = 2,      /* file missing / unreadable                                            */
+  Q3TTS_EFORMAT = 3,  /* malformed config.json / safetensors, missing tensor, wrong shape     */
+  Q3TTS_ECUDA = 4,    /* CUDA error, or no sm_100 device                                      */
+  Q3TTS_ENOMEM = 5,   /* host or device allocation failed                                     */
+  Q3TTS_ESTATE = 6    /* call not valid in this state (e.g. push on a closed stream)          */
+};
+
+/* ---- options ----------------------------------------------------------------------------- */
+enum { Q3TTS_PREC_FP32 = 0,   /* CUDA-core fp32 everywhere: the parity anchor (PCM max-abs <= 1e-4) */
+       Q3TTS_PREC_FP16 = 1,   /* tcgen05 fp16 operands, fp32 accumulate (SNR >= 40 dB)               */
+       Q3TTS_PREC_BF16 = 2 }; /* tcgen05 bf16 operands, fp32 accumulate                              */
+
+enum { Q3TTS_ATTN_REFERENCE = 0, /* full, unmasked, no RoPE: what ST.swift:512-528,763 does        */
+       Q3TTS_ATTN_CAUSAL_SW = 1 }; /* causal, window = sliding_window (Cfg.swift:401): streaming    */
+
+enum { Q3TTS_CODES_BQT = 0,   /* [B,16,T]  -- Qwen3TTSSpeechTokenizerDecoder.callAsFunction, ST.swift:754 */
+       Q3TTS_CODES_BTQ = 1 }; /* [B,T,16]  -- Qwen3TTSSpeechTokenizer.decode, ST.swift:823               */
+
+typedef struct q3tts_options {
+  uint32_t struct_size;       /* = sizeof(q3tts_options)                                       */
+  int32_t device;             /* CUDA device ordinal; -1 = current device                      */
+  int32_t precision;          /* Q3TTS_PREC_*                                                  */
+  int32_t attn_mode;          /* Q3TTS_ATTN_*                                                  */
+  uint64_t workspace_bytes;   /* activation workspace cap per model; 0 = default (24 GiB)      */
+  int32_t max_frames_per_launch; /* micro-batch cap in codec frames; 0 = derive from workspace */
+  int32_t reserved;
+} q3tts_options;
+
+/* Decoder hyper-parameters as parsed from config.json (Cfg.swift:361-408 keys and defaults). */
+typedef struct q3tts_config {
+  int32_t latent_dim, codebook_dim, codebook_size, decoder_dim, hidden_size, intermediate_size;
+  int32_t num_hidden_layers, num_attention_heads, num_key_value_heads, head_dim;
+  int32_t sliding_window, num_quantizers, num_semantic_quantizers, semantic_codebook_size;
+  int32_t num_upsample_rates, upsample_rates[8];
+  int32_t num_upsampling_ratios, upsampling_ratios[8];
+  int32_t total_upsample;     /* Cfg.swift:411-414 (1920)                                      */
+  int32_t decode_upsample_rate; /* Cfg.swift:590 (1920): factor used for audioLengths         */
+  int32_t output_sample_rate; /* Cfg.swift:589 (24000)                                         */
+  int32_t has_encoder_config; /* ST.swift:816 hasEncoder (the encoder itself is out of scope)  */
+  float rms_norm_eps, rope_theta, layer_scale_initial_scale;
+  int64_t num_decoder_tensors;/* on-disk decoder.* tensors consumed (271 for the full model)   */
+  int64_t num_parameters;     /* decoder parameters after codebook folding                     */
+} q3tts_config;
+
+typedef struct q3tts_model q3tts_model;
+typedef struct q3tts_stream q3tts_stream;
+
+/* ---- library ------------------------------------------------------------------------------ */
+int q3tts_abi_version(void);
+/* Thread-local message for the last non-OK status on this thread. */
+const char* q3tts_last_error(void);
+/* Number of usable sm_100 devices (0 when there is none: every compute call then fails).     */
+int q3tts_device_count(void);
+void q3tts_options_default(q3tts_options* opts);
+
+/* ---- load / free ---------------------------------------------------------------------------
+ * Replaces the speech-tokenizer half of Qwen3TTSModel.postLoadHook (Q3.swift:1461-1494):
+ * reads <dir>/config.json (Qwen3TTSTokenizerConfig, Cfg.swift:565-595) and every
+ * <dir>/ *.safetensors, applies sanitizeSpeechTokenizerWeights' decoder rules
+ * (Q3.swift:1498-1512, 1530-1543, 1581-1588, 1687-1724 incl. the layout heuristic 1246-1260),
+ * folds codebooks (embedding_sum / clip(cluster_usage, 1e-5)), packs and uploads the weights.
+ * encoder.* tensors are ignored.  Unlike `update(verify: [])` (Q3.swift:1486) a missing or
+ * mis-shaped decoder tensor is an error (Q3TTS_EFORMAT).  A config without decoder_config is
+ * Q3TTS_EFORMAT (the reference calls fatalError, ST.swift:801-805).  F32 / F16 / BF16 files.   */
+int q3tts_model_load(const char* speech_tokenizer_dir, const q3tts_options* opts, q3tts_model** out);
+void q3tts_model_free(q3tts_model* m);
+int q3tts_model_config(const q3tts_model* m, q3tts_config* out);
+/* Host-only: parse + validate a checkpoint without touching CUDA (config, tensor inventory,
+ * shapes, layout rules).  Fills *cfg when non-NULL.                                           */
+int q3tts_checkpoint_inspect(const char* speech_tokenizer_dir, q3tts_config* cfg);
+
+/* samples produced for T frames = T * total_upsample (ST.swift:752-753; Cfg.swift:411-414).   */
+int64_t q3tts_output_samples(const q3tts_model* m, int64_t frames);
+
+/* ---- decode: host buffers -------------------------------------------------------------------
+ * Replaces Qwen3TTSSpeechTokenizer.decode (ST.swift:823-836) when layout = Q3TTS_CODES_BTQ and
+ * Qwen3TTSSpeechTokenizerDecoder.callAsFunction (ST.swift:754-784) when Q3TTS_CODES_BQT.
+ * codes: int32 [B,T,16] or [B,16,T].  pcm_out: float [B, T*total_upsample], clipped to [-1,1].
+ * lengths_out (may be NULL): int32 [B] = count(code[b,t,0] > 0) * decode_upsample_rate
+ * (ST.swift:831-833).  Synchronous: returns when PCM is in the caller's buffer.
+ * A code id outside its codebook is Q3TTS_EINVAL (the reference leaves it unchecked).          */
+int q3tts_decode(q3tts_model* m, const int32_t* codes, int32_t B, int32_t T, int32_t layout,
+                 float* pcm_out, int32_t* lengths_out);
+
+/* Mixed-length batch: utterance i has frame_offsets[i+1]-frame_offsets[i] frames.
+ * codes_packed: int32 [sum_T, 16] (frame-major, = the [T,16] rows `generate` stacks, Q3.swift:736-741).
+ * pcm_out: float [sum_T * total_upsample], utterance i at sample offset frame_offsets[i]*total_upsample.
+ * Every utterance equals its own B=1 q3tts_decode (no cross-utterance leakage).                */
+int q3tts_decode_varlen(q3tts_model* m, const int32_t* codes_packed, const int64_t* frame_offsets,
+                        int32_t n_utterances, float* pcm_out, int32_t* lengths_out);
+
+/* ---- decode: device buffers (codes and PCM already in HBM), asynchronous on `stream` ---------
+ * Same semantics as q3tts_decode; `stream` is a cudaStream_t (NULL = legacy default stream).
+ * Returns after enqueueing; errors detected on device (bad code ids) surface at
+ * q3tts_sync().                                                                                */
+int q3tts_decode_device(q3tts_model* m, const int32_t* d_codes, int32_t B, int32_t T, int32_t layout,
+                        float* d_pcm_out, int32_t* d_lengths_out, void* stream);
+int q3tts_sync(q3tts_model* m, void* stream);
+
+/* ---- stage taps (debug / parity) --------------------------------------------------------------
+ * The reference's test walks the decoder stage by stage (Tests.swift:57-257).  After a decode
+ * with taps enabled, q3tts_stage_tap copies stage `name` as float32 NCT [B, C, L] (the
+ * reference's inter-module layout) into `out`.  Names: "rvq_sum_first", "rvq_sum_rest",
+ * "quantized", "pre_conv", "pre_transformer", "upsample0", "upsample1", "init_conv",
+ * "block0".."block3", "out_conv".  Taps force single-launch decode (B*T bounded by workspace). */
+int q3tts_set_taps(q3tts_model* m, int32_t enable);
+int q3tts_stage_tap_shape(q3tts_model* m, const char* name, int32_t* B, int32_t* C, int64_t* L);
+int q3tts_stage_tap(q3tts_model* m, const char* name, float* out, int64_t out_elems);
+/* Packed weight probe, MLX layout of the reference module tree, e.g.
+ * "decoder.decoder.initConv.conv.weight" -> [1536,7,1024] (Tests.swift:131-132).               */
+int q3tts_weight_shape(const q3tts_model* m, const char* swift_key, int32_t* ndim, int64_t dims[4]);
+
+/* ---- streaming (chunked decode with causal state carry; Q3TTS_ATTN_CAUSAL_SW only) ------------
+ * The reference has no chunked PCM streaming (Qwen3+Streaming.swift:19-120 emits one final
+ * .audio); correctness here is chunk-invariance: concatenated chunk PCM == one-shot decode in
+ * the same mode.  A stream is pinned to the model's GPU for life.                              */
+int q3tts_stream_open(q3tts_model* m, q3tts_stream** out);
+/* codes: int32 [n_frames,16]; pcm_out: float [n_frames*total_upsample].                        */
+int q3tts_stream_push(q3tts_stream* s, const int32_t* codes, int32_t n_frames, float* pcm_out);
+/* Push one chunk for each of n streams in ONE batched launch chain (config 5).                 */
+int q3tts_stream_push_batch(q3tts_stream* const* streams, int32_t n_streams,
+                            const int32_t* const* codes, const int32_t* n_frames, float* const* pcm_out);
+void q3tts_stream_close(q3tts_stream* s);
+
+/* ---- batch scheduler (host-only, no CUDA) ------------------------------------------------------
+ * Longest-processing-time-first partition of utterances over `n_parts` GPUs by frame count;
+ * part_out[i] in [0,n_parts).  Deterministic (ties by index) so every rank computes the same map. */
+int q3tts_partition_lpt(const int64_t* frames, int32_t n_utterances, int32_t n_parts, int32_t* part_out);
+
+/* ---- PCM post-processing (caller-side semantics of the reference) ------------------------------
+ * q3tts_trim_length: Q3.swift:746-752 (valid_len in (0,n) trims, else keeps n).
+ * q3tts_voice_clone_cut: Q3.swift:1196-1199, Float arithmetic: first sample to keep.
+ * q3tts_pcm_to_int16: Sources/Qwen3TTSDemo/main.swift:134-165 (Int16(clamp(x,-1,1) * 32767)).   */
+int64_t q3tts_trim_length(int64_t n_samples, int64_t valid_len);
+int64_t q3tts_voice_clone_cut(int64_t ref_frames, int64_t total_frames, int64_t n_samples);
+int q3tts_pcm_to_int16(const float* pcm, int64_t n, int16_t* out);
+int q3tts_write_wav(const char* path, const float* pcm, int64_t n, int32_t sample_rate);
+
+/* ---- measurement -------------------------------------------------------------------------------
+ * Per-stage CUDA-event timing of the most recent decode (enable before decoding).
+ * q3tts_profile_get: fills up to `cap` entries; returns the number of stages recorded.          */
+typedef struct q3tts_stage_time {
+  char name[32];
+  float ms;            /* device time of the stage (sum over its kernels, events on the launch stream) */
+  int32_t launches;    /* kernels launched by this stage                                               */
+  double flops;        /* algorithmic FLOPs of the stage for this decode                               */
+  double bytes;        /* algorithmic HBM bytes (one read of inputs + one write of outputs + weights)   */
+} q3tts_stage_time;
+int q3tts_profile_enable(q3tts_model* m, int32_t enable);
+int q3tts_profile_get(q3tts_model* m, q3tts_stage_time* out, int32_t cap);
+/* Kernels launched by this model since load (all decodes).                                      */
+int64_t q3tts_launch_count(const q3tts_model* m);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QWEN3TTS_CUDA_H */

@@ -113,7 +113,7 @@ class OracleDecoder:
         s = torch.sin(x_nct * a)
         return x_nct + (1.0 / (b + 1e-9)) * (s * s)
 
-    def quantizer_decode(self, codes):
+    def quantizer_decode(self, codes, taps=None):
         """SplitResidualVectorQuantizer.decode, ST.swift:214-226 (+ 161-169, 81-96, 50-55)."""
         cfg = self.cfg
         ns = cfg.num_semantic_quantizers
@@ -125,6 +125,8 @@ class OracleDecoder:
                 e = emb[part_codes[:, i, :].long()]        # Embedding gather -> [B,T,D]
                 e = e.permute(0, 2, 1)                     # ST.swift:54
                 q = e if q is None else q + e
+            if taps is not None:   # pre-projection sum: the bit-exact part of the dequantiser
+                taps["rvq_sum_first" if part == "rvq_first" else "rvq_sum_rest"] = q.detach().clone()
             # Conv1dProjection, ST.swift:110-118 (1x1 conv, no bias)
             w = self.w[f"decoder.quantizer.{part}.output_proj.weight"]
             return self.conv1d_ntc(q.permute(0, 2, 1), w).permute(0, 2, 1)
@@ -232,7 +234,7 @@ class OracleDecoder:
             if taps is not None:
                 taps[name] = t.detach().clone()
 
-        hidden = self.quantizer_decode(codes); tap("quantized", hidden)
+        hidden = self.quantizer_decode(codes, taps); tap("quantized", hidden)
         hidden = self.causal_conv1d(hidden, "decoder.pre_conv", 3); tap("pre_conv", hidden)
         hidden = self.transformer(hidden.permute(0, 2, 1)).permute(0, 2, 1); tap("pre_transformer", hidden)
         for i, r in enumerate(cfg.upsampling_ratios):

@@ -1,185 +1,3 @@
-"""Seeded synthetic checkpoint generator for the speech-tokenizer decoder.
-
-Writes ``<dir>/speech_tokenizer/{config.json, model.safetensors}`` in the ON-DISK
-(PyTorch / HF) layout the reference loads (Qwen3.swift:1461-1494): numeric
-``decoder.decoder.N`` keys, ``[out,in,k]`` conv weights, ``[in,out,k]`` transposed-conv
-weights and ``_codebook.{cluster_usage,embedding_sum}`` pairs (SURVEY Appendix B,
-271 tensors).  The same file feeds the oracle and the CUDA engine.
-
-Swift's default initialisers give a degenerate decoder (zero projections,
-SpeechTokenizer.swift:107, 242-243, 382 -- SURVEY F6), so the "random-init weights of
-the named architecture" are drawn here.  Gains are chosen so that every stage keeps
-O(1) activations and the PCM is well inside [-1, 1] (clipping would hide errors).
-TEST INFRASTRUCTURE (see package docstring).
-"""
-from __future__ import annotations
-
-import json
-import os
-from typing import Dict, Optional
-
-import numpy as np
-import torch
-
-from .config import DecoderConfig, TokenizerConfig
-
-DEFAULT_SEED = 20261018
-# Global scale of outConv, calibrated once with tools in tests (PCM std ~0.15).
-OUT_CONV_GAIN = 0.045
-
-
-def _uniform(g, shape, bound):
-    return (torch.rand(shape, generator=g, dtype=torch.float32) * 2.0 - 1.0) * bound
-
-
-def _normal(g, shape, std, mean=0.0):
-    return torch.randn(shape, generator=g, dtype=torch.float32) * std + mean
-
-
-def decoder_tensor_specs(cfg: DecoderConfig):
-    """(on-disk key, shape, kind, fan_in) in a fixed order; kind selects the initialiser."""
-    specs = []
-    half = cfg.codebook_dim // 2
-    q = "decoder.quantizer"
-    # codebooks: Qwen3.swift:1716-1724, SpeechTokenizer.swift:139, 196-208
-    for i in range(cfg.num_semantic_quantizers):
-        specs.append((f"{q}.rvq_first.vq.layers.{i}._codebook.cluster_usage", (cfg.semantic_codebook_size,), "usage", 0))
-        specs.append((f"{q}.rvq_first.vq.layers.{i}._codebook.embedding_sum", (cfg.semantic_codebook_size, half), "embsum", 0))
-    for i in range(cfg.num_quantizers - cfg.num_semantic_quantizers):
-        specs.append((f"{q}.rvq_rest.vq.layers.{i}._codebook.cluster_usage", (cfg.codebook_size,), "usage", 0))
-        specs.append((f"{q}.rvq_rest.vq.layers.{i}._codebook.embedding_sum", (cfg.codebook_size, half), "embsum", 0))
-    for part in ("rvq_first", "rvq_rest"):
-        specs.append((f"{q}.{part}.input_proj.weight", (half, cfg.codebook_dim, 1), "w", cfg.codebook_dim))
-        specs.append((f"{q}.{part}.output_proj.weight", (cfg.codebook_dim, half, 1), "w", half))
-    specs.append(("decoder.pre_conv.conv.weight", (cfg.latent_dim, cfg.codebook_dim, 3), "w", cfg.codebook_dim * 3))
-    specs.append(("decoder.pre_conv.conv.bias", (cfg.latent_dim,), "b", 0))
-    H, L, I = cfg.hidden_size, cfg.latent_dim, cfg.intermediate_size
-    A = cfg.num_attention_heads * cfg.head_dim
-    KV = cfg.num_key_value_heads * cfg.head_dim
-    pt = "decoder.pre_transformer"
-    specs += [(f"{pt}.input_proj.weight", (H, L), "w", L), (f"{pt}.input_proj.bias", (H,), "b", 0),
-              (f"{pt}.output_proj.weight", (L, H), "w", H), (f"{pt}.output_proj.bias", (L,), "b", 0),
-              (f"{pt}.norm.weight", (H,), "norm", 0)]
-    for n in range(cfg.num_hidden_layers):
-        p = f"{pt}.layers.{n}"
-        specs += [(f"{p}.self_attn.q_proj.weight", (A, H), "w", H),
-                  (f"{p}.self_attn.k_proj.weight", (KV, H), "w", H),
-                  (f"{p}.self_attn.v_proj.weight", (KV, H), "w", H),
-                  (f"{p}.self_attn.o_proj.weight", (H, A), "w", A),
-                  (f"{p}.mlp.gate_proj.weight", (I, H), "w", H),
-                  (f"{p}.mlp.up_proj.weight", (I, H), "w", H),
-                  (f"{p}.mlp.down_proj.weight", (H, I), "w", I),
-                  (f"{p}.input_layernorm.weight", (H,), "norm", 0),
-                  (f"{p}.post_attention_layernorm.weight", (H,), "norm", 0),
-                  (f"{p}.self_attn_layer_scale.scale", (H,), "lscale", 0),
-                  (f"{p}.mlp_layer_scale.scale", (H,), "lscale", 0)]
-    for i, r in enumerate(cfg.upsampling_ratios):
-        u = f"decoder.upsample.{i}"
-        specs += [(f"{u}.0.conv.weight", (L, L, r), "wt", L), (f"{u}.0.conv.bias", (L,), "b", 0),
-                  (f"{u}.1.dwconv.conv.weight", (L, 1, 7), "w", 7), (f"{u}.1.dwconv.conv.bias", (L,), "b", 0),
-                  (f"{u}.1.norm.weight", (L,), "norm", 0), (f"{u}.1.norm.bias", (L,), "b", 0),
-                  (f"{u}.1.pwconv1.weight", (4 * L, L), "w", L), (f"{u}.1.pwconv1.bias", (4 * L,), "b", 0),
-                  (f"{u}.1.pwconv2.weight", (L, 4 * L), "w", 4 * L), (f"{u}.1.pwconv2.bias", (L,), "b", 0),
-                  (f"{u}.1.gamma", (L,), "lscale", 0)]
-    D = cfg.decoder_dim
-    dd = "decoder.decoder"
-    specs += [(f"{dd}.0.conv.weight", (D, L, 7), "w", L * 7), (f"{dd}.0.conv.bias", (D,), "b", 0)]
-    for i, r in enumerate(cfg.upsample_rates):
-        cin, cout = D >> i, D >> (i + 1)
-        b = f"{dd}.{i + 1}.block"
-        specs += [(f"{b}.0.alpha", (cin,), "snake", 0), (f"{b}.0.beta", (cin,), "snake", 0),
-                  # transposed conv: every output sample sees 2 taps x cin inputs
-                  (f"{b}.1.conv.weight", (cin, cout, 2 * r), "wt", 2 * cin), (f"{b}.1.conv.bias", (cout,), "b", 0)]
-        for j in (2, 3, 4):
-            specs += [(f"{b}.{j}.act1.alpha", (cout,), "snake", 0), (f"{b}.{j}.act1.beta", (cout,), "snake", 0),
-                      (f"{b}.{j}.conv1.conv.weight", (cout, cout, 7), "wres", cout * 7),
-                      (f"{b}.{j}.conv1.conv.bias", (cout,), "b", 0),
-                      (f"{b}.{j}.act2.alpha", (cout,), "snake", 0), (f"{b}.{j}.act2.beta", (cout,), "snake", 0),
-                      (f"{b}.{j}.conv2.conv.weight", (cout, cout, 1), "wres", cout),
-                      (f"{b}.{j}.conv2.conv.bias", (cout,), "b", 0)]
-    cl = D >> len(cfg.upsample_rates)
-    specs += [(f"{dd}.5.alpha", (cl,), "snake", 0), (f"{dd}.5.beta", (cl,), "snake", 0),
-              (f"{dd}.6.conv.weight", (1, cl, 7), "wout", cl * 7), (f"{dd}.6.conv.bias", (1,), "b0", 0)]
-    return specs
-
-
-def make_decoder_state(cfg: DecoderConfig, seed: int = DEFAULT_SEED) -> Dict[str, torch.Tensor]:
-    g = torch.Generator(device="cpu")
-    g.manual_seed(seed)
-    state: Dict[str, torch.Tensor] = {}
-    for key, shape, kind, fan_in in decoder_tensor_specs(cfg):
-        if kind == "usage":
-            t = torch.rand(shape, generator=g, dtype=torch.float32) * 99.0 + 1.0
-            state[key] = t
-        elif kind == "embsum":
-            usage = state[key.replace("embedding_sum", "cluster_usage")]
-            t = _normal(g, shape, 1.0) * usage[:, None]
-        elif kind == "w":      # main path: unit gain, var = 1/fan_in
-            t = _uniform(g, shape, (3.0 / fan_in) ** 0.5)
-        elif kind == "wt":     # transposed conv (on-disk [in,out,k]), unit gain
-            t = _uniform(g, shape, (3.0 / fan_in) ** 0.5)
-        elif kind == "wres":   # residual-branch convs: MLXNN's own U(-1/sqrt(fan_in), ..) family
-            t = _uniform(g, shape, (1.0 / fan_in) ** 0.5)
-        elif kind == "wout":
-            t = _uniform(g, shape, (3.0 / fan_in) ** 0.5) * OUT_CONV_GAIN
-        elif kind == "b":
-            t = _normal(g, shape, 0.02)
-        elif kind == "b0":
-            t = torch.zeros(shape, dtype=torch.float32)
-        elif kind == "snake":  # log-domain; e^a ~ 0.7..1.4 (pretrained means 0.82 / 0.96, Tests.swift:187)
-            t = _normal(g, shape, 0.3)
-        elif kind == "norm":
-            t = _normal(g, shape, 0.1, mean=1.0)
-        elif kind == "lscale":  # layer-scale / gamma: large enough that the branches matter
-            t = torch.rand(shape, generator=g, dtype=torch.float32) * 0.45 + 0.05
-        else:
-            raise AssertionError(kind)
-        state[key] = t.contiguous()
-    return state
-
-
-def write_checkpoint(model_dir: str, cfg: Optional[DecoderConfig] = None, seed: int = DEFAULT_SEED,
-                     dtype: str = "float32", with_encoder_stub: bool = False,
-                     mlx_layout: bool = False) -> str:
-    """Write ``<model_dir>/speech_tokenizer/`` and return that path.
-
-    dtype 'float16' + no encoder == the 'lite' variant's on-disk form.
-    ``with_encoder_stub`` adds a couple of ``encoder.*`` tensors + ``encoder_config`` that a
-    decoder-only loader must ignore.  ``mlx_layout`` stores conv / transposed-conv weights
-    pre-transposed to exercise the layout heuristic's "already MLX" branch.
-    """
-    from safetensors.torch import save_file
-    cfg = cfg or DecoderConfig()
-    st_dir = os.path.join(model_dir, "speech_tokenizer")
-    os.makedirs(st_dir, exist_ok=True)
-    state = make_decoder_state(cfg, seed)
-    if mlx_layout:
-        for k in list(state.keys()):
-            v = state[k]
-            if v.ndim != 3 or "quantizer" in k:
-                continue  # the quantizer projections are transposed unconditionally by the reference
-            is_t = (".0.conv.weight" in k and "upsample" in k) or (".block.1.conv.weight" in k)
-            state[k] = (v.permute(1, 2, 0) if is_t else v.permute(0, 2, 1)).contiguous()
-    tdtype = {"float32": torch.float32, "float16": torch.float16, "bfloat16": torch.bfloat16}[dtype]
-    out = {k: v.to(tdtype).contiguous() for k, v in state.items()}
-    tok = TokenizerConfig(decoder_config=cfg)
-    if with_encoder_stub:
-        out["encoder.encoder.layers.0.conv.weight"] = torch.zeros(4, 1, 7, dtype=tdtype)
-        out["encoder.quantizer.semantic_residual_vector_quantizer.layers.0.codebook.embed_sum"] = torch.zeros(8, 4, dtype=tdtype)
-        tok.encoder_config = {"num_filters": 4}
-    save_file(out, os.path.join(st_dir, "model.safetensors"))
-    with open(os.path.join(st_dir, "config.json"), "w") as f:
-        json.dump(tok.to_dict(), f, indent=1)
-    return st_dir
-
-
-def synth_codes(cfg: DecoderConfig, B: int, T: int, seed: int, zero_frac: float = 0.0) -> np.ndarray:
-    """Codes [B, 16, T] int32: codebook 0 ~ U{1..codebook_size-1} (what ``generate`` can emit,
-    Qwen3.swift:622-628), codebooks 1.. ~ U{0..codebook_size-1}."""
-    rng = np.random.default_rng(seed)
-    codes = rng.integers(0, cfg.codebook_size, size=(B, cfg.num_quantizers, T), dtype=np.int64)
-    codes[:, 0, :] = rng.integers(1, cfg.codebook_size, size=(B, T), dtype=np.int64)
-    if zero_frac > 0:
-        mask = rng.random((B, T)) < zero_frac
-        codes[:, 0, :][mask] = 0
-    return codes.astype(np.int32)
+"""Re-export of the synthetic checkpoint generator (tools/synth_checkpoint.py)."""
+from tools.synth_checkpoint import *  # noqa: F401,F403
+from tools.synth_checkpoint import DEFAULT_SEED, make_decoder_state, write_checkpoint, synth_codes, decoder_tensor_specs  # noqa: F401

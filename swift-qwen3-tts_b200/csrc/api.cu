@@ -1,0 +1,474 @@
+// extern "C" entry points of libqwen3tts_cuda (see include/qwen3tts_cuda.h for the reference
+// interface each one replaces).
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <numeric>
+
+#include "../../include/qwen3tts_cuda.h"
+#include "engine.hpp"
+
+using namespace q3;
+
+namespace {
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+
+template <typename F>
+int guarded(F&& f) {
+  try {
+    return f();
+  } catch (const Error& e) {
+    return fail(e.code, e.what());
+  } catch (const std::bad_alloc&) {
+    return fail(Q3TTS_ENOMEM, "host allocation failed");
+  } catch (const std::exception& e) {
+    return fail(Q3TTS_EINVAL, e.what());
+  }
+}
+
+#define CUDA_OK(expr)                                                                                   \
+  do {                                                                                                  \
+    cudaError_t _e = (expr);                                                                            \
+    if (_e != cudaSuccess)                                                                              \
+      throw Error(_e == cudaErrorMemoryAllocation ? Q3TTS_ENOMEM : Q3TTS_ECUDA,                         \
+                  std::string(#expr) + ": " + cudaGetErrorString(_e));                                  \
+  } while (0)
+
+template <typename Tp>
+void ensure_dev(Tp** p, size_t* cap, size_t bytes) {
+  if (bytes <= *cap && *p) return;
+  if (*p) cudaFree(*p);
+  *p = nullptr;
+  *cap = 0;
+  CUDA_OK(cudaMalloc(p, std::max<size_t>(bytes, 256)));
+  *cap = bytes;
+}
+
+struct Utt { int64_t code_base, pcm_base; int frames, orig; };
+
+int64_t frames_cap(const Model& m) {
+  const size_t per = (plan_bytes(m, 1, 256) + 255) / 256;
+  uint64_t ws = m.opts.workspace_bytes ? m.opts.workspace_bytes : (24ull << 30);
+  int64_t cap = (int64_t)(ws / per);
+  if (m.opts.max_frames_per_launch > 0) cap = std::min<int64_t>(cap, m.opts.max_frames_per_launch);
+  return std::max<int64_t>(cap, 1);
+}
+
+// Enqueue the decode of `utts` (any order).  d_codes / d_pcm / d_lengths are device pointers.
+// Metadata goes through a pinned staging buffer and is re-uploaded only when it changes.
+void decode_core(Model& m, const int32_t* d_codes, std::vector<Utt> utts, int64_t sq, int64_t st, float* d_pcm,
+                 int32_t* d_lengths, cudaStream_t s) {
+  const int n = (int)utts.size();
+  if (n == 0) return;
+  // lengths first, in the caller's order (ST.swift:831-833)
+  std::vector<Utt> orig = utts;
+  std::stable_sort(utts.begin(), utts.end(), [](const Utt& a, const Utt& b) { return a.frames > b.frames; });
+  while (!utts.empty() && utts.back().frames == 0) utts.pop_back();
+  const int nz = (int)utts.size();
+  const int64_t cap = frames_cap(m);
+  std::vector<MicroBatch> mbs;
+  for (int i = 0; i < nz;) {
+    MicroBatch mb;
+    mb.first = i;
+    mb.Tmax = utts[(size_t)i].frames;
+    if (mb.Tmax > cap)
+      throw Error(Q3TTS_ENOMEM, "an utterance of " + std::to_string(mb.Tmax) + " frames does not fit the workspace (" +
+                                    std::to_string(cap) + " frames); raise q3tts_options.workspace_bytes or use the streaming API");
+    int b = 0;
+    while (i + b < nz && (int64_t)(b + 1) * mb.Tmax <= cap) ++b;
+    mb.B = b;
+    mbs.push_back(mb);
+    i += b;
+  }
+  if (m.taps_enabled && mbs.size() > 1) throw Error(Q3TTS_EINVAL, "stage taps need the whole batch in one launch chain; reduce B*T");
+  // metadata block: [len_sorted int32 x nz][pad][code_base_sorted i64 x nz][pcm_base_sorted i64 x nz]
+  //                 [len_orig int32 x n][pad][code_base_orig i64 x n]
+  auto al8 = [](size_t v) { return (v + 7) & ~(size_t)7; };
+  const size_t o_len = 0, o_cb = al8((size_t)nz * 4), o_pb = o_cb + (size_t)nz * 8, o_lo = o_pb + (size_t)nz * 8,
+               o_cbo = o_lo + al8((size_t)n * 4), total = o_cbo + (size_t)n * 8;
+  std::vector<char> meta(total, 0);
+  for (int i = 0; i < nz; ++i) {
+    ((int32_t*)(meta.data() + o_len))[i] = utts[(size_t)i].frames;
+    ((int64_t*)(meta.data() + o_cb))[i] = utts[(size_t)i].code_base;
+    ((int64_t*)(meta.data() + o_pb))[i] = utts[(size_t)i].pcm_base;
+  }
+  for (int i = 0; i < n; ++i) {
+    ((int32_t*)(meta.data() + o_lo))[i] = orig[(size_t)i].frames;
+    ((int64_t*)(meta.data() + o_cbo))[i] = orig[(size_t)i].code_base;
+  }
+  if (meta != m.meta_key) {
+    CUDA_OK(cudaStreamSynchronize(s));   // the previous chain may still be reading the old metadata
+    if (total > m.h_meta_cap) {
+      if (m.h_meta) cudaFreeHost(m.h_meta);
+      m.h_meta = nullptr;
+      CUDA_OK(cudaMallocHost(&m.h_meta, total));
+      m.h_meta_cap = total;
+    }
+    ensure_dev(&m.d_meta, &m.d_meta_cap, total);
+    std::memcpy(m.h_meta, meta.data(), total);
+    CUDA_OK(cudaMemcpyAsync(m.d_meta, m.h_meta, total, cudaMemcpyHostToDevice, s));
+    m.meta_key = meta;
+  }
+  const int* d_len = (const int*)(m.d_meta + o_len);
+  const int64_t* d_cb = (const int64_t*)(m.d_meta + o_cb);
+  const int64_t* d_pb = (const int64_t*)(m.d_meta + o_pb);
+  if (m.profile_enabled)
+    for (auto& sp : m.prof) { sp.used = false; sp.ms_accum = 0; sp.flops = 0; sp.bytes = 0; sp.launches = 0; }
+  for (auto& mb : mbs) {
+    int64_t valid = 0;
+    for (int i = 0; i < mb.B; ++i) valid += utts[(size_t)(mb.first + i)].frames;
+    run_microbatch(m, d_codes, d_cb + mb.first, sq, st, d_len + mb.first, d_pb + mb.first, d_pcm, mb.B, mb.Tmax, valid, s);
+    if (m.profile_enabled) {
+      CUDA_OK(cudaStreamSynchronize(s));
+      for (auto& sp : m.prof)
+        if (sp.used) {
+          float ms = 0;
+          if (cudaEventElapsedTime(&ms, sp.ev0, sp.ev1) == cudaSuccess) sp.ms_accum += ms;
+        }
+    }
+  }
+  if (d_lengths) {
+    launch_lengths(d_codes, (const int64_t*)(m.d_meta + o_cbo), st, (const int*)(m.d_meta + o_lo), n,
+                   m.cfg.decode_upsample_rate, d_lengths, s);
+    m.launches += 1;
+  }
+}
+
+void check_device_errors(Model& m, cudaStream_t s) {
+  CUDA_OK(cudaMemcpyAsync(m.h_err, m.d_err, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CUDA_OK(cudaStreamSynchronize(s));
+  if (*m.h_err) {
+    *m.h_err = 0;
+    CUDA_OK(cudaMemsetAsync(m.d_err, 0, sizeof(int), s));
+    throw Error(Q3TTS_EINVAL, "a code id is outside its codebook (semantic ids must be < semantic_codebook_size, acoustic < codebook_size)");
+  }
+}
+
+}  // namespace
+
+struct q3tts_model { Model* m; };
+struct q3tts_stream { q3tts_model* owner; };
+
+extern "C" {
+
+int q3tts_abi_version(void) { return Q3TTS_ABI_VERSION; }
+const char* q3tts_last_error(void) { return g_last_error.c_str(); }
+
+int q3tts_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  int ok = 0;
+  for (int i = 0; i < n; ++i) {
+    cudaDeviceProp p{};
+    if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major == 10) ++ok;
+  }
+  return ok;
+}
+
+void q3tts_options_default(q3tts_options* o) {
+  if (!o) return;
+  std::memset(o, 0, sizeof(*o));
+  o->struct_size = sizeof(*o);
+  o->device = -1;
+  o->precision = Q3TTS_PREC_FP16;
+  o->attn_mode = Q3TTS_ATTN_REFERENCE;
+}
+
+int q3tts_checkpoint_inspect(const char* dir, q3tts_config* cfg) {
+  return guarded([&]() {
+    if (!dir) return fail(Q3TTS_EINVAL, "speech_tokenizer_dir is NULL");
+    Checkpoint ck;
+    load_checkpoint(dir, &ck);
+    if (cfg) *cfg = ck.cfg;
+    return (int)Q3TTS_OK;
+  });
+}
+
+int q3tts_model_load(const char* dir, const q3tts_options* opts, q3tts_model** out) {
+  return guarded([&]() {
+    if (!dir || !out) return fail(Q3TTS_EINVAL, "NULL argument");
+    *out = nullptr;
+    q3tts_options o;
+    q3tts_options_default(&o);
+    if (opts) {
+      if (opts->struct_size != sizeof(q3tts_options)) return fail(Q3TTS_EINVAL, "q3tts_options.struct_size mismatch");
+      o = *opts;
+    }
+    if (o.precision < Q3TTS_PREC_FP32 || o.precision > Q3TTS_PREC_BF16) return fail(Q3TTS_EINVAL, "bad precision");
+    if (o.attn_mode != Q3TTS_ATTN_REFERENCE && o.attn_mode != Q3TTS_ATTN_CAUSAL_SW) return fail(Q3TTS_EINVAL, "bad attn_mode");
+    Checkpoint ck;
+    load_checkpoint(dir, &ck);
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+      cudaGetLastError();
+      return fail(Q3TTS_ECUDA, "no CUDA device: libqwen3tts_cuda has no CPU fallback");
+    }
+    std::unique_ptr<q3tts_model> h(new q3tts_model{nullptr});
+    h->m = model_create(ck, o);
+    *out = h.release();
+    return (int)Q3TTS_OK;
+  });
+}
+
+void q3tts_model_free(q3tts_model* h) {
+  if (!h) return;
+  delete h->m;
+  delete h;
+}
+
+int q3tts_model_config(const q3tts_model* h, q3tts_config* out) {
+  if (!h || !out) return fail(Q3TTS_EINVAL, "NULL argument");
+  *out = h->m->cfg;
+  return Q3TTS_OK;
+}
+
+int64_t q3tts_output_samples(const q3tts_model* h, int64_t frames) {
+  if (!h || frames < 0) return -1;
+  return frames * h->m->cfg.total_upsample;
+}
+
+static int decode_common(q3tts_model* h, const int32_t* codes, int32_t B, int32_t T, int32_t layout, float* pcm,
+                         int32_t* lengths, bool device_ptrs, cudaStream_t user_stream) {
+  return guarded([&]() {
+    if (!h) return fail(Q3TTS_EINVAL, "model is NULL");
+    if (B < 0 || T < 0) return fail(Q3TTS_EINVAL, "negative B or T");
+    if (layout != Q3TTS_CODES_BQT && layout != Q3TTS_CODES_BTQ) return fail(Q3TTS_EINVAL, "bad codes layout");
+    if (B == 0 || T == 0) return (int)Q3TTS_OK;   // empty input: nothing to decode
+    if (!codes || !pcm) return fail(Q3TTS_EINVAL, "NULL buffer");
+    Model& m = *h->m;
+    std::lock_guard<std::mutex> lock(m.mu);
+    CUDA_OK(cudaSetDevice(m.device));
+    const int Q = m.cfg.num_quantizers;
+    const int64_t up = m.cfg.total_upsample;
+    const size_t n_codes = (size_t)B * T * Q, n_pcm = (size_t)B * T * up;
+    cudaStream_t s = device_ptrs ? user_stream : m.stream;
+    const int32_t* d_codes = codes;
+    float* d_pcm = pcm;
+    int32_t* d_len = lengths;
+    if (!device_ptrs) {
+      ensure_dev(&m.d_codes, &m.d_codes_cap, n_codes * 4);
+      ensure_dev(&m.d_pcm, &m.d_pcm_cap, n_pcm * 4);
+      ensure_dev(&m.d_lengths, &m.d_lengths_cap, (size_t)B * 4);
+      CUDA_OK(cudaMemcpyAsync(m.d_codes, codes, n_codes * 4, cudaMemcpyHostToDevice, s));
+      d_codes = m.d_codes;
+      d_pcm = m.d_pcm;
+      d_len = lengths ? m.d_lengths : nullptr;
+    }
+    std::vector<Utt> utts((size_t)B);
+    for (int b = 0; b < B; ++b) utts[(size_t)b] = Utt{(int64_t)b * T * Q, (int64_t)b * T * up, T, b};
+    const int64_t sq = layout == Q3TTS_CODES_BQT ? T : 1, st = layout == Q3TTS_CODES_BQT ? 1 : Q;
+    decode_core(m, d_codes, utts, sq, st, d_pcm, d_len, s);
+    if (!device_ptrs) {
+      CUDA_OK(cudaMemcpyAsync(pcm, m.d_pcm, n_pcm * 4, cudaMemcpyDeviceToHost, s));
+      if (lengths) CUDA_OK(cudaMemcpyAsync(lengths, m.d_lengths, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
+      check_device_errors(m, s);
+    }
+    return (int)Q3TTS_OK;
+  });
+}
+
+int q3tts_decode(q3tts_model* h, const int32_t* codes, int32_t B, int32_t T, int32_t layout, float* pcm_out,
+                 int32_t* lengths_out) {
+  return decode_common(h, codes, B, T, layout, pcm_out, lengths_out, false, nullptr);
+}
+
+int q3tts_decode_device(q3tts_model* h, const int32_t* d_codes, int32_t B, int32_t T, int32_t layout, float* d_pcm_out,
+                        int32_t* d_lengths_out, void* stream) {
+  return decode_common(h, d_codes, B, T, layout, d_pcm_out, d_lengths_out, true, (cudaStream_t)stream);
+}
+
+int q3tts_sync(q3tts_model* h, void* stream) {
+  return guarded([&]() {
+    if (!h) return fail(Q3TTS_EINVAL, "model is NULL");
+    Model& m = *h->m;
+    std::lock_guard<std::mutex> lock(m.mu);
+    CUDA_OK(cudaSetDevice(m.device));
+    check_device_errors(m, (cudaStream_t)stream);
+    return (int)Q3TTS_OK;
+  });
+}
+
+int q3tts_decode_varlen(q3tts_model* h, const int32_t* codes_packed, const int64_t* frame_offsets, int32_t n,
+                        float* pcm_out, int32_t* lengths_out) {
+  return guarded([&]() {
+    if (!h) return fail(Q3TTS_EINVAL, "model is NULL");
+    if (n < 0) return fail(Q3TTS_EINVAL, "negative utterance count");
+    if (n == 0) return (int)Q3TTS_OK;
+    if (!frame_offsets) return fail(Q3TTS_EINVAL, "frame_offsets is NULL");
+    for (int i = 0; i < n; ++i)
+      if (frame_offsets[i + 1] < frame_offsets[i] || frame_offsets[i + 1] - frame_offsets[i] > INT32_MAX)
+        return fail(Q3TTS_EINVAL, "frame_offsets must be non-decreasing");
+    if (frame_offsets[0] != 0) return fail(Q3TTS_EINVAL, "frame_offsets[0] must be 0");
+    const int64_t total = frame_offsets[n];
+    Model& m = *h->m;
+    std::lock_guard<std::mutex> lock(m.mu);
+    CUDA_OK(cudaSetDevice(m.device));
+    if (total == 0) {
+      if (lengths_out) std::memset(lengths_out, 0, (size_t)n * 4);
+      return (int)Q3TTS_OK;
+    }
+    if (!codes_packed || !pcm_out) return fail(Q3TTS_EINVAL, "NULL buffer");
+    const int Q = m.cfg.num_quantizers;
+    const int64_t up = m.cfg.total_upsample;
+    cudaStream_t s = m.stream;
+    ensure_dev(&m.d_codes, &m.d_codes_cap, (size_t)total * Q * 4);
+    ensure_dev(&m.d_pcm, &m.d_pcm_cap, (size_t)total * up * 4);
+    ensure_dev(&m.d_lengths, &m.d_lengths_cap, (size_t)n * 4);
+    CUDA_OK(cudaMemcpyAsync(m.d_codes, codes_packed, (size_t)total * Q * 4, cudaMemcpyHostToDevice, s));
+    std::vector<Utt> utts((size_t)n);
+    for (int i = 0; i < n; ++i)
+      utts[(size_t)i] = Utt{frame_offsets[i] * Q, frame_offsets[i] * up, (int)(frame_offsets[i + 1] - frame_offsets[i]), i};
+    decode_core(m, m.d_codes, utts, 1, Q, m.d_pcm, lengths_out ? m.d_lengths : nullptr, s);
+    CUDA_OK(cudaMemcpyAsync(pcm_out, m.d_pcm, (size_t)total * up * 4, cudaMemcpyDeviceToHost, s));
+    if (lengths_out) CUDA_OK(cudaMemcpyAsync(lengths_out, m.d_lengths, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+    check_device_errors(m, s);
+    return (int)Q3TTS_OK;
+  });
+}
+
+// ---- taps -------------------------------------------------------------------------------------------
+int q3tts_set_taps(q3tts_model* h, int32_t enable) {
+  if (!h) return fail(Q3TTS_EINVAL, "model is NULL");
+  std::lock_guard<std::mutex> lock(h->m->mu);
+  h->m->taps_enabled = enable != 0;
+  return Q3TTS_OK;
+}
+
+int q3tts_stage_tap_shape(q3tts_model* h, const char* name, int32_t* B, int32_t* C, int64_t* L) {
+  if (!h || !name) return fail(Q3TTS_EINVAL, "NULL argument");
+  std::lock_guard<std::mutex> lock(h->m->mu);
+  auto it = h->m->taps.find(name);
+  if (it == h->m->taps.end() || !it->second.d) return fail(Q3TTS_EINVAL, std::string("no tap named '") + name + "' (enable taps, then decode)");
+  if (B) *B = it->second.B;
+  if (C) *C = it->second.C;
+  if (L) *L = it->second.L;
+  return Q3TTS_OK;
+}
+
+int q3tts_stage_tap(q3tts_model* h, const char* name, float* out, int64_t out_elems) {
+  return guarded([&]() {
+    if (!h || !name || !out) return fail(Q3TTS_EINVAL, "NULL argument");
+    Model& m = *h->m;
+    std::lock_guard<std::mutex> lock(m.mu);
+    auto it = m.taps.find(name);
+    if (it == m.taps.end() || !it->second.d) return fail(Q3TTS_EINVAL, std::string("no tap named '") + name + "'");
+    const int64_t n = (int64_t)it->second.B * it->second.C * it->second.L;
+    if (out_elems < n) return fail(Q3TTS_EINVAL, "tap output buffer too small");
+    CUDA_OK(cudaSetDevice(m.device));
+    CUDA_OK(cudaStreamSynchronize(m.stream));
+    CUDA_OK(cudaMemcpy(out, it->second.d, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    return (int)Q3TTS_OK;
+  });
+}
+
+int q3tts_weight_shape(const q3tts_model* h, const char* key, int32_t* ndim, int64_t dims[4]) {
+  if (!h || !key || !ndim || !dims) return fail(Q3TTS_EINVAL, "NULL argument");
+  auto it = h->m->weight_shapes.find(key);
+  if (it == h->m->weight_shapes.end()) return fail(Q3TTS_EINVAL, std::string("no weight named '") + key + "'");
+  *ndim = (int32_t)it->second.size();
+  for (size_t i = 0; i < it->second.size() && i < 4; ++i) dims[i] = it->second[i];
+  return Q3TTS_OK;
+}
+
+// ---- streaming (implemented in a later milestone) ------------------------------------------------------
+int q3tts_stream_open(q3tts_model*, q3tts_stream** out) {
+  if (out) *out = nullptr;
+  return fail(Q3TTS_ESTATE, "chunked streaming is not available in this build");
+}
+int q3tts_stream_push(q3tts_stream*, const int32_t*, int32_t, float*) {
+  return fail(Q3TTS_ESTATE, "chunked streaming is not available in this build");
+}
+int q3tts_stream_push_batch(q3tts_stream* const*, int32_t, const int32_t* const*, const int32_t*, float* const*) {
+  return fail(Q3TTS_ESTATE, "chunked streaming is not available in this build");
+}
+void q3tts_stream_close(q3tts_stream*) {}
+
+// ---- scheduler ------------------------------------------------------------------------------------------
+int q3tts_partition_lpt(const int64_t* frames, int32_t n, int32_t parts, int32_t* part_out) {
+  if (n < 0 || parts <= 0 || (n > 0 && (!frames || !part_out))) return fail(Q3TTS_EINVAL, "bad partition arguments");
+  std::vector<int32_t> order((size_t)n);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return frames[a] > frames[b]; });
+  std::vector<int64_t> load((size_t)parts, 0);
+  for (int32_t idx : order) {
+    int best = 0;
+    for (int p = 1; p < parts; ++p)
+      if (load[(size_t)p] < load[(size_t)best]) best = p;
+    part_out[idx] = best;
+    load[(size_t)best] += std::max<int64_t>(frames[idx], 0);
+  }
+  return Q3TTS_OK;
+}
+
+// ---- PCM post-processing ----------------------------------------------------------------------------------
+int64_t q3tts_trim_length(int64_t n, int64_t valid) { return (valid > 0 && valid < n) ? valid : n; }
+
+int64_t q3tts_voice_clone_cut(int64_t ref_frames, int64_t total_frames, int64_t n) {
+  const float cutf = (float)ref_frames / (float)std::max<int64_t>(total_frames, 1) * (float)n;   // Q3.swift:1196
+  const int64_t cut = (int64_t)cutf;
+  return (cut > 0 && cut < n) ? cut : 0;
+}
+
+int q3tts_pcm_to_int16(const float* pcm, int64_t n, int16_t* out) {
+  if (n < 0 || (n > 0 && (!pcm || !out))) return fail(Q3TTS_EINVAL, "bad arguments");
+  for (int64_t i = 0; i < n; ++i) {
+    const float c = std::max(-1.0f, std::min(1.0f, pcm[i]));
+    out[i] = (int16_t)(c * 32767.0f);
+  }
+  return Q3TTS_OK;
+}
+
+int q3tts_write_wav(const char* path, const float* pcm, int64_t n, int32_t rate) {
+  if (!path || n < 0 || (n > 0 && !pcm) || rate <= 0) return fail(Q3TTS_EINVAL, "bad arguments");
+  FILE* f = std::fopen(path, "wb");
+  if (!f) return fail(Q3TTS_EIO, std::string("cannot open ") + path);
+  const uint32_t data = (uint32_t)(n * 2), riff = 36 + data, fmt = 16, byte_rate = (uint32_t)rate * 2, sr = (uint32_t)rate;
+  const uint16_t pcm_fmt = 1, ch = 1, align = 2, bits = 16;
+  std::fwrite("RIFF", 1, 4, f); std::fwrite(&riff, 4, 1, f); std::fwrite("WAVE", 1, 4, f);
+  std::fwrite("fmt ", 1, 4, f); std::fwrite(&fmt, 4, 1, f); std::fwrite(&pcm_fmt, 2, 1, f); std::fwrite(&ch, 2, 1, f);
+  std::fwrite(&sr, 4, 1, f); std::fwrite(&byte_rate, 4, 1, f); std::fwrite(&align, 2, 1, f); std::fwrite(&bits, 2, 1, f);
+  std::fwrite("data", 1, 4, f); std::fwrite(&data, 4, 1, f);
+  std::vector<int16_t> buf((size_t)n);
+  q3tts_pcm_to_int16(pcm, n, buf.data());
+  const size_t wrote = std::fwrite(buf.data(), 2, (size_t)n, f);
+  std::fclose(f);
+  return wrote == (size_t)n ? Q3TTS_OK : fail(Q3TTS_EIO, "short write");
+}
+
+// ---- measurement --------------------------------------------------------------------------------------------
+int q3tts_profile_enable(q3tts_model* h, int32_t enable) {
+  if (!h) return fail(Q3TTS_EINVAL, "model is NULL");
+  std::lock_guard<std::mutex> lock(h->m->mu);
+  h->m->profile_enabled = enable != 0;
+  return Q3TTS_OK;
+}
+
+int q3tts_profile_get(q3tts_model* h, q3tts_stage_time* out, int32_t cap) {
+  if (!h || (!out && cap > 0)) return 0;
+  std::lock_guard<std::mutex> lock(h->m->mu);
+  int n = 0;
+  for (auto& sp : h->m->prof) {
+    if (!sp.used) continue;
+    if (n < cap) {
+      std::memset(&out[n], 0, sizeof(out[n]));
+      std::snprintf(out[n].name, sizeof(out[n].name), "%s", sp.name.c_str());
+      out[n].ms = sp.ms_accum;
+      out[n].launches = sp.launches;
+      out[n].flops = sp.flops;
+      out[n].bytes = sp.bytes;
+    }
+    ++n;
+  }
+  return n;
+}
+
+int64_t q3tts_launch_count(const q3tts_model* h) { return h ? h->m->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,569 @@
+// See engine.hpp.  Weight packing + the per-micro-batch launch chain.
+#include "engine.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <memory>
+
+namespace q3 {
+
+#define CUDA_OK(expr)                                                                                   \
+  do {                                                                                                  \
+    cudaError_t _e = (expr);                                                                            \
+    if (_e != cudaSuccess)                                                                              \
+      throw Error(_e == cudaErrorMemoryAllocation ? Q3TTS_ENOMEM : Q3TTS_ECUDA,                         \
+                  std::string(#expr) + ": " + cudaGetErrorString(_e));                                  \
+  } while (0)
+
+static size_t dt_size(int dt) { return dt == DT_F32 ? 4 : 2; }
+
+Model::~Model() {
+  cudaSetDevice(device);
+  for (void* p : allocs) cudaFree(p);
+  if (arena) cudaFree(arena);
+  if (d_codes) cudaFree(d_codes);
+  if (d_pcm) cudaFree(d_pcm);
+  if (d_lengths) cudaFree(d_lengths);
+  if (d_meta) cudaFree(d_meta);
+  if (h_meta) cudaFreeHost(h_meta);
+  if (d_err) cudaFree(d_err);
+  if (h_err) cudaFreeHost(h_err);
+  for (auto& t : taps) if (t.second.d) cudaFree(t.second.d);
+  for (auto& p : prof) { if (p.ev0) cudaEventDestroy(p.ev0); if (p.ev1) cudaEventDestroy(p.ev1); }
+  if (stream) cudaStreamDestroy(stream);
+}
+
+// ---- upload helpers -----------------------------------------------------------------------------
+static float* upload(Model& m, const std::vector<float>& v) {
+  float* d = nullptr;
+  CUDA_OK(cudaMalloc(&d, std::max<size_t>(v.size(), 1) * sizeof(float)));
+  m.allocs.push_back(d);
+  CUDA_OK(cudaMemcpy(d, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));
+  return d;
+}
+
+static const HostTensor& T(const Checkpoint& ck, const std::string& k) {
+  auto it = ck.tensors.find(k);
+  if (it == ck.tensors.end()) throw Error(Q3TTS_EFORMAT, "missing decoder tensor " + k);
+  return it->second;
+}
+
+static void finish_gemm(Model& m, GemmW& g, const std::vector<float>& packed, const std::vector<float>* bias) {
+  if (g.Cin % 4) throw Error(Q3TTS_EFORMAT, "channel counts must be multiples of 4");
+  g.w32 = upload(m, packed);
+  if (m.op_dtype != DT_F32) {
+    void* d = nullptr;
+    CUDA_OK(cudaMalloc(&d, packed.size() * 2));
+    m.allocs.push_back(d);
+    launch_convert(g.w32, d, m.op_dtype, (int64_t)packed.size(), m.stream);
+    g.w16 = d;
+  }
+  g.bias = bias ? upload(m, *bias) : nullptr;
+}
+
+// conv weight, MLX layout [Cout, K, Cin] -> [K][Cout][Cin]
+static void pack_conv(Model& m, GemmW& g, const HostTensor& w, const HostTensor* bias, int dil) {
+  const int64_t Co = w.shape[0], K = w.shape[1], Ci = w.shape[2];
+  g.taps = (int)K; g.N = (int)Co; g.Cin = (int)Ci; g.dil = dil;
+  std::vector<float> p((size_t)(K * Co * Ci));
+  for (int64_t o = 0; o < Co; ++o)
+    for (int64_t k = 0; k < K; ++k)
+      std::memcpy(&p[(size_t)((k * Co + o) * Ci)], &w.data[(size_t)((o * K + k) * Ci)], (size_t)Ci * 4);
+  finish_gemm(m, g, p, bias ? &bias->data : nullptr);
+}
+
+// linear weight [N, Cin] (several stacked row-wise) -> taps=1
+static void pack_linear(Model& m, GemmW& g, const std::vector<const HostTensor*>& ws, const HostTensor* bias,
+                        bool interleave2 = false) {
+  const int64_t Ci = ws[0]->shape[1];
+  int64_t N = 0;
+  for (auto* w : ws) N += w->shape[0];
+  g.taps = 1; g.N = (int)N; g.Cin = (int)Ci; g.dil = 1;
+  std::vector<float> p((size_t)(N * Ci));
+  if (interleave2) {  // rows (2i, 2i+1) = (ws[0][i], ws[1][i]) so the SwiGLU epilogue sees gate/up side by side
+    const int64_t I = ws[0]->shape[0];
+    for (int64_t i = 0; i < I; ++i) {
+      std::memcpy(&p[(size_t)((2 * i) * Ci)], &ws[0]->data[(size_t)(i * Ci)], (size_t)Ci * 4);
+      std::memcpy(&p[(size_t)((2 * i + 1) * Ci)], &ws[1]->data[(size_t)(i * Ci)], (size_t)Ci * 4);
+    }
+  } else {
+    int64_t r = 0;
+    for (auto* w : ws) {
+      std::memcpy(&p[(size_t)(r * Ci)], w->data.data(), w->data.size() * 4);
+      r += w->shape[0];
+    }
+  }
+  finish_gemm(m, g, p, bias ? &bias->data : nullptr);
+}
+
+// transposed conv, MLX layout [Cout, K, Cin], stride r.  K == r: one tap; K == 2r: two taps
+// (ST.swift:339-353: y[t*r+p] = W[:,p,:] x[t] + W[:,p+r,:] x[t-1] + b).
+static void pack_tconv(Model& m, GemmW& g, const HostTensor& w, const HostTensor& bias, int r) {
+  const int64_t Co = w.shape[0], K = w.shape[1], Ci = w.shape[2];
+  if (K != r && K != 2 * r) throw Error(Q3TTS_EFORMAT, "transposed conv kernel must be stride or 2*stride");
+  const int taps = (K == r) ? 1 : 2;
+  g.taps = taps; g.N = (int)(r * Co); g.Cin = (int)Ci; g.dil = 1;
+  std::vector<float> p((size_t)(taps * r * Co * Ci));
+  for (int j = 0; j < taps; ++j)
+    for (int64_t ph = 0; ph < r; ++ph)
+      for (int64_t o = 0; o < Co; ++o) {
+        // last tap (j = taps-1) multiplies x[t] -> kernel index ph; the earlier one multiplies x[t-1] -> ph + r
+        const int64_t k = (j == taps - 1) ? ph : ph + r;
+        std::memcpy(&p[(size_t)(((int64_t)j * r * Co + ph * Co + o) * Ci)], &w.data[(size_t)((o * K + k) * Ci)], (size_t)Ci * 4);
+      }
+  std::vector<float> b((size_t)(r * Co));
+  for (int64_t ph = 0; ph < r; ++ph)
+    for (int64_t o = 0; o < Co; ++o) b[(size_t)(ph * Co + o)] = bias.data[(size_t)o];
+  finish_gemm(m, g, p, &b);
+}
+
+static SnakeW pack_snake(Model& m, const HostTensor& alpha, const HostTensor& beta, int rep) {
+  const int64_t C = alpha.shape[0];
+  std::vector<float> ea((size_t)(C * rep)), ib((size_t)(C * rep));
+  for (int r = 0; r < rep; ++r)
+    for (int64_t c = 0; c < C; ++c) {
+      ea[(size_t)(r * C + c)] = expf(alpha.data[(size_t)c]);
+      ib[(size_t)(r * C + c)] = 1.0f / (expf(beta.data[(size_t)c]) + 1e-9f);   // ST.swift:237, 252
+    }
+  SnakeW s;
+  s.ea = upload(m, ea);
+  s.ib = upload(m, ib);
+  s.n = (int)(C * rep);
+  return s;
+}
+
+Model* model_create(const Checkpoint& ck, const q3tts_options& opts) {
+  std::unique_ptr<Model> mp(new Model());
+  Model& m = *mp;
+  m.cfg = ck.cfg;
+  m.opts = opts;
+  int dev = opts.device;
+  if (dev < 0) CUDA_OK(cudaGetDevice(&dev));
+  m.device = dev;
+  CUDA_OK(cudaSetDevice(dev));
+  cudaDeviceProp prop{};
+  CUDA_OK(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10)
+    throw Error(Q3TTS_ECUDA, std::string("device ") + prop.name + " is not sm_100: libqwen3tts_cuda is built for sm_100a only and has no fallback");
+  m.op_dtype = opts.precision == Q3TTS_PREC_FP32 ? DT_F32 : (opts.precision == Q3TTS_PREC_FP16 ? DT_F16 : DT_BF16);
+  m.st_dtype = m.op_dtype;
+  CUDA_OK(cudaStreamCreateWithFlags(&m.stream, cudaStreamNonBlocking));
+  const q3tts_config& c = m.cfg;
+  if (c.latent_dim > 2048) throw Error(Q3TTS_EFORMAT, "latent_dim > 2048 is not supported");
+  if (c.head_dim != 32 && c.head_dim != 64 && c.head_dim != 128) throw Error(Q3TTS_EFORMAT, "head_dim must be 32, 64 or 128");
+  if ((c.codebook_dim / 2) % 4) throw Error(Q3TTS_EFORMAT, "codebook_dim/2 must be a multiple of 4");
+  for (auto& kv : ck.tensors) m.weight_shapes[kv.first] = kv.second.shape;
+
+  // --- codebooks (fp32 tables; Q3.swift:1716-1724 folding was done by the loader) ---
+  std::vector<const float*> tabs;
+  std::vector<int32_t> sizes;
+  for (int q = 0; q < c.num_quantizers; ++q) {
+    const bool sem = q < c.num_semantic_quantizers;
+    const std::string k = std::string("decoder.quantizer.") + (sem ? "rvq_first" : "rvq_rest") + ".vq.layers." +
+                          std::to_string(sem ? q : q - c.num_semantic_quantizers) + ".codebook.embed.weight";
+    const HostTensor& e = T(ck, k);
+    float* d = upload(m, e.data);
+    m.codebooks.push_back(d);
+    tabs.push_back(d);
+    sizes.push_back((int32_t)e.shape[0]);
+  }
+  CUDA_OK(cudaMalloc(&m.d_tables, tabs.size() * sizeof(float*)));
+  m.allocs.push_back((void*)m.d_tables);
+  CUDA_OK(cudaMemcpy((void*)m.d_tables, tabs.data(), tabs.size() * sizeof(float*), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMalloc(&m.d_table_sizes, sizes.size() * 4));
+  m.allocs.push_back(m.d_table_sizes);
+  CUDA_OK(cudaMemcpy(m.d_table_sizes, sizes.data(), sizes.size() * 4, cudaMemcpyHostToDevice));
+
+  // --- RVQ output projections as ONE GEMM over [sum_first | sum_rest] (ST.swift:161-169, 214-226) ---
+  {
+    const HostTensor& p1 = T(ck, "decoder.quantizer.rvq_first.output_proj.weight");   // [dim,1,half]
+    const HostTensor& p2 = T(ck, "decoder.quantizer.rvq_rest.output_proj.weight");
+    const int64_t dim = p1.shape[0], half = p1.shape[2];
+    std::vector<float> p((size_t)(dim * 2 * half));
+    for (int64_t n = 0; n < dim; ++n) {
+      std::memcpy(&p[(size_t)(n * 2 * half)], &p1.data[(size_t)(n * half)], (size_t)half * 4);
+      std::memcpy(&p[(size_t)(n * 2 * half + half)], &p2.data[(size_t)(n * half)], (size_t)half * 4);
+    }
+    m.rvq_proj.taps = 1; m.rvq_proj.N = (int)dim; m.rvq_proj.Cin = (int)(2 * half); m.rvq_proj.dil = 1;
+    finish_gemm(m, m.rvq_proj, p, nullptr);
+  }
+  pack_conv(m, m.pre_conv, T(ck, "decoder.pre_conv.conv.weight"), &T(ck, "decoder.pre_conv.conv.bias"), 1);
+  const std::string pt = "decoder.pre_transformer.";
+  pack_linear(m, m.in_proj, {&T(ck, pt + "input_proj.weight")}, &T(ck, pt + "input_proj.bias"));
+  pack_linear(m, m.out_proj, {&T(ck, pt + "output_proj.weight")}, &T(ck, pt + "output_proj.bias"));
+  m.final_norm = upload(m, T(ck, pt + "norm.weight").data);
+  m.layers.resize((size_t)c.num_hidden_layers);
+  for (int n = 0; n < c.num_hidden_layers; ++n) {
+    const std::string p = pt + "layers." + std::to_string(n) + ".";
+    LayerW& L = m.layers[(size_t)n];
+    pack_linear(m, L.qkv, {&T(ck, p + "self_attn.q_proj.weight"), &T(ck, p + "self_attn.k_proj.weight"), &T(ck, p + "self_attn.v_proj.weight")}, nullptr);
+    pack_linear(m, L.o, {&T(ck, p + "self_attn.o_proj.weight")}, nullptr);
+    pack_linear(m, L.gate_up, {&T(ck, p + "mlp.gate_proj.weight"), &T(ck, p + "mlp.up_proj.weight")}, nullptr, true);
+    pack_linear(m, L.down, {&T(ck, p + "mlp.down_proj.weight")}, nullptr);
+    L.ln1 = upload(m, T(ck, p + "input_layernorm.weight").data);
+    L.ln2 = upload(m, T(ck, p + "post_attention_layernorm.weight").data);
+    L.ls_attn = upload(m, T(ck, p + "self_attn_layer_scale.scale").data);
+    L.ls_mlp = upload(m, T(ck, p + "mlp_layer_scale.scale").data);
+  }
+  m.ups.resize((size_t)c.num_upsampling_ratios);
+  for (int i = 0; i < c.num_upsampling_ratios; ++i) {
+    const std::string u = "decoder.upsample." + std::to_string(i) + ".";
+    UpsampleW& U = m.ups[(size_t)i];
+    U.ratio = c.upsampling_ratios[i];
+    pack_tconv(m, U.tconv, T(ck, u + "0.conv.weight"), T(ck, u + "0.conv.bias"), U.ratio);
+    const HostTensor& dw = T(ck, u + "1.dwconv.conv.weight");   // [L,7,1]
+    U.dw_w = upload(m, dw.data);
+    U.dw_b = upload(m, T(ck, u + "1.dwconv.conv.bias").data);
+    U.ln_w = upload(m, T(ck, u + "1.norm.weight").data);
+    U.ln_b = upload(m, T(ck, u + "1.norm.bias").data);
+    pack_linear(m, U.pw1, {&T(ck, u + "1.pwconv1.weight")}, &T(ck, u + "1.pwconv1.bias"));
+    pack_linear(m, U.pw2, {&T(ck, u + "1.pwconv2.weight")}, &T(ck, u + "1.pwconv2.bias"));
+    U.gamma = upload(m, T(ck, u + "1.gamma").data);
+  }
+  const std::string dd = "decoder.decoder.";
+  pack_conv(m, m.init_conv, T(ck, dd + "initConv.conv.weight"), &T(ck, dd + "initConv.conv.bias"), 1);
+  static const int kDil[3] = {1, 3, 9};   // ST.swift:468-470
+  for (int i = 0; i < 4; ++i) {
+    const std::string b = dd + "block" + std::to_string(i) + ".";
+    BlockW& B = m.blocks[i];
+    B.rate = c.upsample_rates[i];
+    B.cin = c.decoder_dim >> i;
+    B.cout = c.decoder_dim >> (i + 1);
+    m.block_in_snake[i] = pack_snake(m, T(ck, b + "snake.alpha"), T(ck, b + "snake.beta"), 1);
+    pack_tconv(m, B.tconv, T(ck, b + "upsample.conv.weight"), T(ck, b + "upsample.conv.bias"), B.rate);
+    for (int j = 0; j < 3; ++j) {
+      const std::string r = b + "res" + std::to_string(j + 1) + ".";
+      // act1 of res j is applied by the producer of the res unit's input: the transposed conv (j = 0,
+      // replicated over the r phases) or the previous res unit's conv1 epilogue.
+      B.act_in_next[j] = pack_snake(m, T(ck, r + "act1.alpha"), T(ck, r + "act1.beta"), j == 0 ? B.rate : 1);
+      pack_conv(m, B.conv7[j], T(ck, r + "conv1.conv.weight"), &T(ck, r + "conv1.conv.bias"), kDil[j]);
+      B.act2[j] = pack_snake(m, T(ck, r + "act2.alpha"), T(ck, r + "act2.beta"), 1);
+      pack_conv(m, B.conv1[j], T(ck, r + "conv2.conv.weight"), &T(ck, r + "conv2.conv.bias"), 1);
+    }
+  }
+  m.out_snake = pack_snake(m, T(ck, dd + "outSnake.alpha"), T(ck, dd + "outSnake.beta"), 1);
+  {
+    const HostTensor& w = T(ck, dd + "outConv.conv.weight");   // [1,7,C]
+    m.tail_w = upload(m, w.data);
+    m.tail_bias = T(ck, dd + "outConv.conv.bias").data[0];
+  }
+  CUDA_OK(cudaMalloc(&m.d_err, sizeof(int)));
+  CUDA_OK(cudaMemset(m.d_err, 0, sizeof(int)));
+  CUDA_OK(cudaMallocHost(&m.h_err, sizeof(int)));
+  *m.h_err = 0;
+  static const char* kStages[] = {"rvq", "pre_conv", "transformer", "upsample", "init_conv",
+                                  "block0", "block1", "block2", "block3", "tail"};
+  for (const char* n : kStages) {
+    StageProfile sp;
+    sp.name = n;
+    CUDA_OK(cudaEventCreate(&sp.ev0));
+    CUDA_OK(cudaEventCreate(&sp.ev1));
+    m.prof.push_back(sp);
+  }
+  CUDA_OK(cudaStreamSynchronize(m.stream));
+  CUDA_OK(cudaGetLastError());
+  return mp.release();
+}
+
+// ---- workspace plan ------------------------------------------------------------------------------
+namespace {
+struct Arena {
+  char* base;
+  size_t off = 0;
+  template <typename Tp = void>
+  Tp* take(size_t bytes) {
+    off = (off + 255) & ~(size_t)255;
+    Tp* p = base ? (Tp*)(base + off) : nullptr;
+    off += bytes;
+    return p;
+  }
+};
+
+struct Plan {
+  void *Q, *QP, *PC, *NB, *QKV, *AO, *GU, *TO, *A0;
+  float* H;
+  struct Up { float* X; void *N, *G, *XO; } up[8];
+  struct Blk { void *X, *A, *C; } blk[4];
+  size_t total;
+};
+
+Plan make_plan(const Model& m, char* base, int B, int Tmax) {
+  const q3tts_config& c = m.cfg;
+  const size_t R = (size_t)B * Tmax, op = dt_size(m.op_dtype), st = dt_size(m.st_dtype);
+  const size_t A = (size_t)c.num_attention_heads * c.head_dim, KV = (size_t)c.num_key_value_heads * c.head_dim;
+  Arena a{base};
+  Plan p{};
+  p.Q = a.take(R * c.codebook_dim * op);
+  p.QP = a.take(R * c.codebook_dim * op);
+  p.PC = a.take(R * c.latent_dim * op);
+  p.H = a.take<float>(R * c.hidden_size * 4);
+  p.NB = a.take(R * c.hidden_size * op);
+  p.QKV = a.take(R * (A + 2 * KV) * op);
+  p.AO = a.take(R * A * op);
+  p.GU = a.take(R * c.intermediate_size * op);
+  p.TO = a.take(R * c.latent_dim * op);
+  size_t rate = 1;
+  for (int i = 0; i < c.num_upsampling_ratios; ++i) {
+    rate *= (size_t)c.upsampling_ratios[i];
+    p.up[i].X = a.take<float>(R * rate * c.latent_dim * 4);
+    p.up[i].N = a.take(R * rate * c.latent_dim * op);
+    p.up[i].G = a.take(R * rate * 4 * c.latent_dim * op);
+    p.up[i].XO = a.take(R * rate * c.latent_dim * op);
+  }
+  p.A0 = a.take(R * rate * c.decoder_dim * op);
+  for (int i = 0; i < 4; ++i) {
+    rate *= (size_t)c.upsample_rates[i];
+    const size_t C = (size_t)(c.decoder_dim >> (i + 1));
+    p.blk[i].X = a.take(R * rate * C * st);
+    p.blk[i].A = a.take(R * rate * C * op);
+    p.blk[i].C = a.take(R * rate * C * op);
+  }
+  p.total = a.off + 256;
+  return p;
+}
+}  // namespace
+
+size_t plan_bytes(const Model& m, int B, int Tmax) { return make_plan(m, nullptr, B, Tmax).total; }
+
+// ---- launch chain ----------------------------------------------------------------------------------
+namespace {
+
+struct Ctx {
+  Model& m;
+  BatchGeom g;
+  cudaStream_t s;
+  int64_t valid_frames;   // sum of len_frames over the micro-batch (host copy, for the work model)
+  int cur_stage = -1;
+};
+
+void account(Ctx& x, double flops, double bytes) {
+  if (x.m.profile_enabled && x.cur_stage >= 0) {
+    x.m.prof[(size_t)x.cur_stage].flops += flops;
+    x.m.prof[(size_t)x.cur_stage].bytes += bytes;
+  }
+}
+
+void stage_begin(Ctx& x, int idx) {
+  x.cur_stage = idx;
+  if (x.m.profile_enabled) {
+    StageProfile& sp = x.m.prof[(size_t)idx];
+    cudaEventRecord(sp.ev0, x.s);
+    sp.used = true;
+    sp.launches = 0;
+  }
+}
+void stage_end(Ctx& x) {
+  if (x.m.profile_enabled) cudaEventRecord(x.m.prof[(size_t)x.cur_stage].ev1, x.s);
+}
+void count_launch(Ctx& x, int n = 1) {
+  x.m.launches += n;
+  if (x.m.profile_enabled && x.cur_stage >= 0) x.m.prof[(size_t)x.cur_stage].launches += n;
+}
+
+float* tap_buffer(Model& m, const std::string& name, int B, int C, int64_t L) {
+  TapBuf& t = m.taps[name];
+  const size_t need = (size_t)B * C * L * 4;
+  if (need > t.cap) {
+    if (t.d) cudaFree(t.d);
+    t.d = nullptr;
+    CUDA_OK(cudaMalloc(&t.d, need));
+    t.cap = need;
+  }
+  t.B = B; t.C = C; t.L = L;
+  return t.d;
+}
+
+void tap(Ctx& x, const char* name, const void* src, int dtype, int rows_per_frame, int ld, int C) {
+  if (!x.m.taps_enabled) return;
+  const int64_t L = (int64_t)x.g.Tmax * rows_per_frame;
+  float* dst = tap_buffer(x.m, name, x.g.B, C, L);
+  launch_tap_copy(src, dtype, L * ld, ld, dst, x.g.B, C, L, x.s);
+  count_launch(x);
+}
+
+struct Epi {
+  int act = ACT_NONE;
+  const void* res = nullptr; const float* scale = nullptr;
+  void* out_y = nullptr; int y_dtype = DT_F32;
+  void* out_a = nullptr;
+  const SnakeW* snake = nullptr;
+  void* out_tap = nullptr;
+};
+
+// One multi-tap GEMM over the micro-batch.  A: [B, Tmax*rpf, Cin] operand; outputs have N (or N/2) columns.
+void gemm(Ctx& x, const GemmW& w, const void* A, int rows_per_frame, const Epi& e) {
+  Model& m = x.m;
+  ConvGemmParams p{};
+  const int64_t slot = (int64_t)x.g.Tmax * rows_per_frame;
+  p.A = A; p.lda = w.Cin; p.a_bstride = slot * w.Cin;
+  p.W = (m.op_dtype == DT_F32) ? (const void*)w.w32 : (const void*)w.w16;
+  p.rows_per_frame = rows_per_frame;
+  p.N = w.N; p.Cin = w.Cin; p.taps = w.taps; p.dil = w.dil;
+  p.bias = w.bias;
+  p.act = e.act;
+  const int outN = (e.act == ACT_SWIGLU) ? w.N / 2 : w.N;
+  p.res = e.res; p.ldres = outN; p.res_bstride = slot * outN;
+  p.scale = e.scale;
+  p.out_y = e.out_y; p.ldy = outN; p.y_bstride = slot * outN;
+  p.out_a = e.out_a; p.lda_out = outN; p.ao_bstride = slot * outN;
+  if (e.snake) {
+    if (e.snake->n != w.N) throw Error(Q3TTS_EINVAL, "internal: snake width does not match GEMM N");
+    p.snake_ea = e.snake->ea; p.snake_ib = e.snake->ib;
+  }
+  p.out_tap = e.out_tap; p.ldt = outN; p.tap_bstride = slot * outN;
+  const int y_dtype = (m.op_dtype == DT_F32) ? DT_F32 : e.y_dtype;
+  {
+    const double rows = (double)x.valid_frames * rows_per_frame, ops = (double)dt_size(m.op_dtype);
+    double bytes = rows * w.Cin * ops + (double)w.taps * w.N * w.Cin * ops;
+    if (e.res) bytes += rows * outN * dt_size(y_dtype);
+    if (e.out_y) bytes += rows * outN * dt_size(y_dtype);
+    if (e.out_a) bytes += rows * outN * ops;
+    account(x, 2.0 * rows * w.taps * w.N * w.Cin, bytes);
+  }
+  if (m.op_dtype != DT_F32 && tc_supported(p, m.op_dtype)) {
+    cudaError_t err = launch_conv_gemm_tc(p, x.g, m.op_dtype, y_dtype, x.s);
+    if (err != cudaSuccess) throw Error(Q3TTS_ECUDA, std::string("tcgen05 GEMM launch: ") + cudaGetErrorString(err));
+  } else {
+    launch_conv_gemm_simt(p, x.g, m.op_dtype, y_dtype, x.s);
+  }
+  count_launch(x);
+}
+
+}  // namespace
+
+void run_microbatch(Model& m, const int32_t* d_codes, const int64_t* d_code_base, int64_t sq, int64_t st,
+                    const int* d_len, const int64_t* d_pcm_base, float* d_pcm, int B, int Tmax, int64_t valid_frames,
+                    cudaStream_t s) {
+  const q3tts_config& c = m.cfg;
+  const size_t need = plan_bytes(m, B, Tmax);
+  if (need > m.arena_cap) {
+    CUDA_OK(cudaStreamSynchronize(s));
+    if (m.arena) cudaFree(m.arena);
+    m.arena = nullptr;
+    m.arena_cap = 0;
+    CUDA_OK(cudaMalloc(&m.arena, need));
+    m.arena_cap = need;
+  }
+  Plan P = make_plan(m, m.arena, B, Tmax);
+  Ctx x{m, BatchGeom{B, Tmax, d_len}, s, valid_frames};
+  const int op = m.op_dtype;
+  const int64_t R = (int64_t)B * Tmax;
+  const int half = c.codebook_dim / 2;
+  const bool taps = m.taps_enabled;
+
+  // 1. RVQ dequantise (ST.swift:214-226)
+  stage_begin(x, 0);
+  {
+    RvqParams rp{};
+    rp.codes = d_codes; rp.code_base = d_code_base; rp.sq = sq; rp.st = st;
+    rp.tables = m.d_tables; rp.table_sizes = m.d_table_sizes;
+    rp.num_q = c.num_quantizers; rp.num_sem = c.num_semantic_quantizers; rp.half = half;
+    rp.out = P.Q; rp.out_dtype = op; rp.err_flag = m.d_err;
+    launch_rvq(rp, x.g, s);
+    count_launch(x);
+    account(x, (double)valid_frames * (c.num_quantizers - 2) * half,
+            (double)valid_frames * (c.num_quantizers * (4.0 + half * 4.0) + 2.0 * half * dt_size(op)));
+    if (taps) {
+      const int64_t L = Tmax;
+      launch_tap_copy(P.Q, op, L * 2 * half, 2 * half, tap_buffer(m, "rvq_sum_first", B, half, L), B, half, L, s);
+      launch_tap_copy((const char*)P.Q + (size_t)half * dt_size(op), op, L * 2 * half, 2 * half,
+                      tap_buffer(m, "rvq_sum_rest", B, half, L), B, half, L, s);
+      count_launch(x, 2);
+    }
+    Epi e; e.out_a = P.QP;
+    gemm(x, m.rvq_proj, P.Q, 1, e);
+    tap(x, "quantized", P.QP, op, 1, c.codebook_dim, c.codebook_dim);
+  }
+  stage_end(x);
+
+  // 2. pre_conv (ST.swift:724-728, 759)
+  stage_begin(x, 1);
+  { Epi e; e.out_a = P.PC; gemm(x, m.pre_conv, P.QP, 1, e); }
+  tap(x, "pre_conv", P.PC, op, 1, c.latent_dim, c.latent_dim);
+  stage_end(x);
+
+  // 3. pre_transformer (ST.swift:629-643)
+  stage_begin(x, 2);
+  { Epi e; e.out_y = P.H; e.y_dtype = DT_F32; gemm(x, m.in_proj, P.PC, 1, e); }
+  const float scale = 1.0f / sqrtf((float)c.head_dim);   // ST.swift:502
+  const int window = (m.opts.attn_mode == Q3TTS_ATTN_CAUSAL_SW) ? c.sliding_window : 0;
+  for (auto& L : m.layers) {
+    launch_rmsnorm(P.H, L.ln1, c.rms_norm_eps, P.NB, op, R, c.hidden_size, s); count_launch(x);
+    { Epi e; e.out_a = P.QKV; gemm(x, L.qkv, P.NB, 1, e); }
+    launch_attention(P.QKV, op, P.AO, op, x.g, c.num_attention_heads, c.num_key_value_heads, c.head_dim, scale, window, s);
+    count_launch(x);
+    {  // 4*nh*hd*T_kv FLOP per query frame; keys = own utterance (approximated by the mean valid length)
+      const double tkv = window > 0 ? std::min<double>(window, (double)valid_frames / B) : (double)valid_frames / B;
+      account(x, 4.0 * c.num_attention_heads * c.head_dim * tkv * valid_frames,
+              (double)valid_frames * ((double)(c.num_attention_heads + 2 * c.num_key_value_heads) * c.head_dim + (double)c.num_attention_heads * c.head_dim) * dt_size(op));
+    }
+    { Epi e; e.res = P.H; e.scale = L.ls_attn; e.out_y = P.H; e.y_dtype = DT_F32; gemm(x, L.o, P.AO, 1, e); }
+    launch_rmsnorm(P.H, L.ln2, c.rms_norm_eps, P.NB, op, R, c.hidden_size, s); count_launch(x);
+    { Epi e; e.act = ACT_SWIGLU; e.out_a = P.GU; gemm(x, L.gate_up, P.NB, 1, e); }
+    { Epi e; e.res = P.H; e.scale = L.ls_mlp; e.out_y = P.H; e.y_dtype = DT_F32; gemm(x, L.down, P.GU, 1, e); }
+  }
+  launch_rmsnorm(P.H, m.final_norm, c.rms_norm_eps, P.NB, op, R, c.hidden_size, s); count_launch(x);
+  { Epi e; e.out_a = P.TO; gemm(x, m.out_proj, P.NB, 1, e); }
+  tap(x, "pre_transformer", P.TO, op, 1, c.latent_dim, c.latent_dim);
+  stage_end(x);
+
+  // 4. upsample: (transposed conv k=s=r, ConvNeXt) x2 (ST.swift:766-775, 385-401)
+  stage_begin(x, 3);
+  const void* cur = P.TO;
+  int rate = 1;
+  for (size_t i = 0; i < m.ups.size(); ++i) {
+    UpsampleW& U = m.ups[i];
+    { Epi e; e.out_y = P.up[i].X; e.y_dtype = DT_F32; gemm(x, U.tconv, cur, rate, e); }   // [T*rate, r*L] == [T*rate*r, L]
+    rate *= U.ratio;
+    launch_dwconv_ln(P.up[i].X, U.dw_w, U.dw_b, U.ln_w, U.ln_b, 1e-6f, P.up[i].N, op, x.g, rate, c.latent_dim, s);
+    count_launch(x);
+    { Epi e; e.act = ACT_GELU; e.out_a = P.up[i].G; gemm(x, U.pw1, P.up[i].N, rate, e); }
+    { Epi e; e.res = P.up[i].X; e.scale = U.gamma; e.y_dtype = DT_F32; e.out_a = P.up[i].XO; gemm(x, U.pw2, P.up[i].G, rate, e); }
+    cur = P.up[i].XO;
+    tap(x, i == 0 ? "upsample0" : "upsample1", cur, op, rate, c.latent_dim, c.latent_dim);
+  }
+  stage_end(x);
+
+  // 5. main decoder (ST.swift:681-690): initConv, then 4 x (snake, transposed conv, 3 residual units)
+  stage_begin(x, 4);
+  {
+    Epi e; e.out_a = P.A0; e.snake = &m.block_in_snake[0];
+    if (taps) e.out_tap = tap_buffer(m, "init_conv_cl", B, c.decoder_dim, (int64_t)Tmax * rate);
+    gemm(x, m.init_conv, cur, rate, e);
+    if (taps) tap(x, "init_conv", m.taps["init_conv_cl"].d, DT_F32, rate, c.decoder_dim, c.decoder_dim);
+  }
+  stage_end(x);
+  const void* a_in = P.A0;
+  for (int i = 0; i < 4; ++i) {
+    stage_begin(x, 5 + i);
+    BlockW& Bk = m.blocks[i];
+    // snake(x) was applied by the producer; transposed conv -> X (stream) and A = res1.act1(X)
+    { Epi e; e.out_y = P.blk[i].X; e.y_dtype = m.st_dtype; e.out_a = P.blk[i].A; e.snake = &Bk.act_in_next[0]; gemm(x, Bk.tconv, a_in, rate, e); }
+    rate *= Bk.rate;
+    for (int j = 0; j < 3; ++j) {
+      { Epi e; e.out_a = P.blk[i].C; e.snake = &Bk.act2[j]; gemm(x, Bk.conv7[j], P.blk[i].A, rate, e); }
+      const SnakeW* next = (j < 2) ? &Bk.act_in_next[j + 1] : (i < 3 ? &m.block_in_snake[i + 1] : &m.out_snake);
+      { Epi e; e.res = P.blk[i].X; e.out_y = P.blk[i].X; e.y_dtype = m.st_dtype; e.out_a = P.blk[i].A; e.snake = next; gemm(x, Bk.conv1[j], P.blk[i].C, rate, e); }
+    }
+    static const char* kNames[4] = {"block0", "block1", "block2", "block3"};
+    tap(x, kNames[i], P.blk[i].X, m.st_dtype, rate, Bk.cout, Bk.cout);
+    a_in = P.blk[i].A;
+    stage_end(x);
+  }
+
+  // 6. outConv + clip (ST.swift:687-688, 781); outSnake was applied by block3's last epilogue
+  stage_begin(x, 9);
+  {
+    const int C = m.blocks[3].cout;
+    float* tp = taps ? tap_buffer(m, "out_conv", B, 1, (int64_t)Tmax * rate) : nullptr;
+    launch_tail(a_in, op, (int64_t)Tmax * rate * C, m.tail_w, m.tail_bias, C, d_pcm, d_pcm_base, tp, (int64_t)Tmax * rate, x.g, rate, s);
+    count_launch(x);
+    account(x, 2.0 * 7 * C * (double)valid_frames * rate, (double)valid_frames * rate * (C * (double)dt_size(op) + 4.0));
+  }
+  stage_end(x);
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) throw Error(Q3TTS_ECUDA, std::string("kernel launch: ") + cudaGetErrorString(err));
+}
+
+}  // namespace q3

@@ -1,0 +1,115 @@
+// Decoder engine: packed device weights + workspace + the launch chain for one micro-batch.
+// Stage order follows Qwen3TTSSpeechTokenizerDecoder.callAsFunction (ST.swift:754-784).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "checkpoint.hpp"
+#include "kernels.cuh"
+
+namespace q3 {
+
+struct GemmW {            // one packed multi-tap GEMM weight (see ConvGemmParams)
+  float* w32 = nullptr;   // [taps][N][Cin] fp32 (always kept: parity mode + source for 16-bit copies)
+  void* w16 = nullptr;    // same, operand dtype (fast mode only)
+  float* bias = nullptr;  // [N] or null
+  int taps = 1, N = 0, Cin = 0, dil = 1;
+};
+
+struct SnakeW { float* ea = nullptr; float* ib = nullptr; int n = 0; };
+
+struct LayerW {
+  float *ln1 = nullptr, *ln2 = nullptr, *ls_attn = nullptr, *ls_mlp = nullptr;
+  GemmW qkv, o, gate_up, down;
+};
+
+struct UpsampleW {
+  GemmW tconv, pw1, pw2;
+  float *dw_w = nullptr, *dw_b = nullptr, *ln_w = nullptr, *ln_b = nullptr, *gamma = nullptr;
+  int ratio = 2;
+};
+
+struct BlockW {
+  GemmW tconv;            // taps=2, N = r*cout
+  SnakeW act_in_next[3];  // snake applied to the block's running output before res1/res2/res3's conv7
+  GemmW conv7[3], conv1[3];
+  SnakeW act2[3];
+  int rate = 1, cin = 0, cout = 0;
+};
+
+struct StageProfile {
+  std::string name;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool used = false;
+  int launches = 0;
+  double flops = 0, bytes = 0;
+  float ms_accum = 0;
+};
+
+struct TapBuf { float* d = nullptr; int B = 0, C = 0; int64_t L = 0; size_t cap = 0; };
+
+struct Model {
+  q3tts_config cfg{};
+  q3tts_options opts{};
+  int device = 0;
+  int op_dtype = DT_F32;      // operand dtype (GEMM inputs)
+  int st_dtype = DT_F32;      // stream dtype inside the decoder blocks
+  cudaStream_t stream = nullptr;
+  std::mutex mu;
+
+  // weights
+  std::vector<void*> allocs;              // every device allocation made for weights
+  std::vector<float*> codebooks;          // [num_q] device fp32 tables
+  const float** d_tables = nullptr;       // device array of table pointers
+  int32_t* d_table_sizes = nullptr;
+  GemmW rvq_proj, pre_conv, in_proj, out_proj, init_conv;
+  float* final_norm = nullptr;
+  std::vector<LayerW> layers;
+  std::vector<UpsampleW> ups;
+  SnakeW block_in_snake[4];               // blockN.snake (applied by the producer of the block's input)
+  BlockW blocks[4];
+  SnakeW out_snake;
+  float* tail_w = nullptr;                // [7][C]
+  float tail_bias = 0.f;
+  std::map<std::string, std::vector<int64_t>> weight_shapes;  // Swift key -> MLX shape
+
+  // workspace
+  char* arena = nullptr;
+  size_t arena_cap = 0;
+  int32_t* d_codes = nullptr; size_t d_codes_cap = 0;
+  float* d_pcm = nullptr;     size_t d_pcm_cap = 0;
+  int32_t* d_lengths = nullptr; size_t d_lengths_cap = 0;
+  char* d_meta = nullptr;     size_t d_meta_cap = 0;     // len_frames / code_base / pcm_base per micro-batch
+  char* h_meta = nullptr;     size_t h_meta_cap = 0;     // pinned staging
+  std::vector<char> meta_key;                            // last uploaded metadata (skip re-upload when equal)
+  int* d_err = nullptr;
+  int* h_err = nullptr;                                  // pinned
+
+  // taps / profiling
+  bool taps_enabled = false;
+  std::map<std::string, TapBuf> taps;
+  bool profile_enabled = false;
+  std::vector<StageProfile> prof;
+  int64_t launches = 0;
+
+  ~Model();
+};
+
+struct MicroBatch { int first = 0, B = 0, Tmax = 0; };   // utterances [first, first+B) of the sorted order
+
+// Build a model from a parsed checkpoint (uploads weights).  Throws q3::Error.
+Model* model_create(const Checkpoint& ck, const q3tts_options& opts);
+
+// Bytes of arena needed for a micro-batch of B utterances x Tmax frames.
+size_t plan_bytes(const Model& m, int B, int Tmax);
+
+// Enqueue the whole launch chain for one micro-batch on `s`.  len/code_base/pcm_base are device arrays.
+void run_microbatch(Model& m, const int32_t* d_codes, const int64_t* d_code_base, int64_t sq, int64_t st,
+                    const int* d_len, const int64_t* d_pcm_base, float* d_pcm, int B, int Tmax, int64_t valid_frames,
+                    cudaStream_t s);
+
+}  // namespace q3

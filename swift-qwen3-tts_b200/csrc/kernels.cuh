@@ -1,0 +1,97 @@
+// Kernel-level interface of libqwen3tts_cuda (internal).  All activations are channels-last:
+// a stage tensor is [B, rows_per_utt (stride), C] with C contiguous, so every conv / linear /
+// transposed conv of the decoder is a GEMM whose A operand is a row-shifted view of its input
+// (tap j of a causal conv with dilation d reads row t - (taps-1-j)*d; rows < 0 are zero).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace q3 {
+
+enum ActKind : int { ACT_NONE = 0, ACT_GELU = 1, ACT_SWIGLU = 2 };
+enum DType : int { DT_F32 = 0, DT_F16 = 1, DT_BF16 = 2 };
+
+// Batch geometry shared by every kernel of one launch chain (one micro-batch).
+struct BatchGeom {
+  int B;                   // utterances in this micro-batch
+  int Tmax;                // frames per utterance slot (row stride at rate 1)
+  const int* len_frames;   // [B] device: valid frames per utterance
+};
+
+// Generic "multi-tap GEMM": out[b,t,n] = epi( sum_{j<taps} sum_c A[b, t-(taps-1-j)*dil, c] * W[j,n,c] ).
+//  - plain conv:        W[j,n,c] = w_mlx[n,j,c]
+//  - linear:            taps = 1
+//  - transposed conv k=2r,s=r: taps = 2, N = r*Cout, W[1,p*Cout+co,c] = w_mlx[co,p,c], W[0,..] = w_mlx[co,p+r,c];
+//    GEMM row t of [T, r*Cout] is rows t*r..t*r+r-1 of the [T*r, Cout] output (ST.swift:339-353).
+struct ConvGemmParams {
+  const void* A;  int lda;  int64_t a_bstride;   // elements; rows of utterance b start at A + b*a_bstride
+  const void* W;                                  // [taps][N][Cin], Cin contiguous
+  int rows_per_frame;                             // GEMM rows per codec frame at this stage
+  int N, Cin, taps, dil;
+  // epilogue: v = acc (+ bias[n]); v = act(v); v = res[b,t,n] + scale[n]*v (if res); y = v; a = snake(v)
+  const float* bias;                              // [N] or null
+  int act;                                        // ActKind (SWIGLU: columns (2i,2i+1) = (gate,up) -> out col i)
+  const void* res; int ldres; int64_t res_bstride;// residual (stream dtype), or null
+  const float* scale;                             // [N] layer-scale / gamma or null (only with res)
+  void* out_y; int ldy; int64_t y_bstride;        // stream output or null
+  void* out_a; int lda_out; int64_t ao_bstride;   // operand output or null
+  const float* snake_ea;                          // [N] exp(alpha) or null: out_a = v + snake_ib*sin^2(v*ea)
+  const float* snake_ib;                          // [N] 1/(exp(beta)+1e-9)
+  void* out_tap;  int ldt; int64_t tap_bstride;   // optional fp32 copy of v (pre-snake) for stage taps
+};
+
+// ---- CUDA-core GEMM: the fp32 parity engine, and the 16-bit fallback for shapes tcgen05 skips ----
+// op_dtype: type of A, W, out_a.  y_dtype: type of res / out_y (fp32, or == op_dtype).  out_tap is fp32.
+void launch_conv_gemm_simt(const ConvGemmParams& p, const BatchGeom& g, int op_dtype, int y_dtype, cudaStream_t s);
+
+// ---- row kernels, templated on storage types via DType tags -----------------------------------
+// RVQ gather-and-sum: codes -> [rows, 2*half] = [ sum of semantic rows | sum of acoustic rows ]
+// (sequential left-to-right fp32 adds, ST.swift:84-93).  code address = codes + code_base[b] + q*sq + t*st.
+struct RvqParams {
+  const int32_t* codes; const int64_t* code_base; int64_t sq, st;
+  const float* const* tables;   // [num_quantizers] device pointers to [size_q, half] fp32 codebooks
+  const int32_t* table_sizes;   // [num_quantizers]
+  int num_q, num_sem, half;
+  void* out; int out_dtype;     // [B*Tmax, 2*half]
+  int* err_flag;                // set to 1 when a code id is out of range
+};
+void launch_rvq(const RvqParams& p, const BatchGeom& g, cudaStream_t s);
+
+void launch_rmsnorm(const float* x, const float* w, float eps, void* out, int out_dtype, int64_t rows, int C,
+                    cudaStream_t s);
+
+// depthwise causal conv k=7 (+bias) followed by LayerNorm(eps) over C (ST.swift:389-393); x fp32 stream.
+void launch_dwconv_ln(const float* x, const float* w7 /*[C][7]*/, const float* wb, const float* ln_w,
+                      const float* ln_b, float eps, void* out, int out_dtype, const BatchGeom& g,
+                      int rows_per_frame, int C, cudaStream_t s);
+
+// Attention over one utterance's frames.  qkv: [B*Tmax, (nh+2*nkv)*hd] (q | k | v), out [B*Tmax, nh*hd].
+void launch_attention(const void* qkv, int qkv_dtype, void* out, int out_dtype, const BatchGeom& g, int nh,
+                      int nkv, int hd, float scale, int causal_window /*0 = full*/, cudaStream_t s);
+
+// Tail: causal conv C->1, k=7 on the (already outSnake-activated) operand, + bias, clip to [-1,1].
+// pcm address = pcm + pcm_base[b] + t.  Optional unclipped fp32 copy for the "out_conv" tap.
+void launch_tail(const void* a, int a_dtype, int64_t a_bstride, const float* w /*[7][C]*/, float bias, int C,
+                 float* pcm, const int64_t* pcm_base, float* tap, int64_t tap_bstride, const BatchGeom& g,
+                 int rows_per_frame, cudaStream_t s);
+
+// audioLengths = count(code[b,t,0] > 0) * rate (ST.swift:831-833).
+void launch_lengths(const int32_t* codes, const int64_t* code_base, int64_t st, const int* len_frames, int B,
+                    int rate, int32_t* out, cudaStream_t s);
+
+// Stage tap: [B, rows(stride), C] (any dtype) -> fp32 NCT [B, C, L].
+void launch_tap_copy(const void* src, int dtype, int64_t bstride, int ld, float* dst, int B, int C, int64_t L,
+                     cudaStream_t s);
+
+// float <-> 16-bit conversion of packed weights.
+void launch_convert(const float* src, void* dst, int dtype, int64_t n, cudaStream_t s);
+
+// ---- tcgen05 tensor-core path (kernels_tc.cu) -------------------------------------------------
+bool tc_supported(const ConvGemmParams& p, int op_dtype);
+// A/W/out_a are `op_dtype` (F16/BF16) operands, fp32 accumulate in TMEM; res/out_y are `y_dtype`.
+cudaError_t launch_conv_gemm_tc(const ConvGemmParams& p, const BatchGeom& g, int op_dtype, int y_dtype,
+                                cudaStream_t s);
+
+}  // namespace q3

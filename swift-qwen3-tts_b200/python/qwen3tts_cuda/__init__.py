@@ -1,0 +1,300 @@
+"""Host-side mirror of the reference's speech-tokenizer API over the C ABI (ctypes).
+
+The reference is Swift (no toolchain in this image), so the host layer above
+``libqwen3tts_cuda.so`` is mirrored here in Python with the reference's names and argument
+meaning, so that parity tests read like the reference's own test
+(Tests/Qwen3TTSTests/Qwen3TTSTests.swift:25-283):
+
+  Qwen3TTSSpeechTokenizer.decode(audio_codes [B,T,16]) -> (audio [B,1920*T], audio_lengths [B])
+      -- Sources/Qwen3TTS/Models/SpeechTokenizer.swift:823-836
+  Qwen3TTSSpeechTokenizerDecoder.__call__(codes [B,16,T]) -> [B,1,1920*T]
+      -- SpeechTokenizer.swift:754-784
+  .has_encoder -- SpeechTokenizer.swift:816
+
+There is NO CPU fallback: if the shared library is missing or no sm_100 GPU is usable, loading a
+model raises.  Nothing here imports ``oracle``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+
+__all__ = ["Qwen3TTSSpeechTokenizer", "Qwen3TTSSpeechTokenizerDecoder", "AudioDecodingFailed", "lib",
+           "partition_lpt", "PREC_FP32", "PREC_FP16", "PREC_BF16", "ATTN_REFERENCE", "ATTN_CAUSAL_SW",
+           "library_path", "checkpoint_inspect", "pcm_to_int16", "write_wav", "trim_length",
+           "voice_clone_cut", "device_count"]
+
+PREC_FP32, PREC_FP16, PREC_BF16 = 0, 1, 2
+ATTN_REFERENCE, ATTN_CAUSAL_SW = 0, 1
+CODES_BQT, CODES_BTQ = 0, 1
+_STATUS = {0: "OK", 1: "EINVAL", 2: "EIO", 3: "EFORMAT", 4: "ECUDA", 5: "ENOMEM", 6: "ESTATE"}
+
+
+class AudioDecodingFailed(RuntimeError):
+    """Maps a non-zero C status, like the Swift shim maps it to
+    AudioGenerationError.audioDecodingFailed(String) (Core/GenerationTypes.swift:67)."""
+
+    def __init__(self, status: int, message: str):
+        super().__init__(f"[{_STATUS.get(status, status)}] {message}")
+        self.status = status
+
+
+class Options(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("device", C.c_int32), ("precision", C.c_int32),
+                ("attn_mode", C.c_int32), ("workspace_bytes", C.c_uint64),
+                ("max_frames_per_launch", C.c_int32), ("reserved", C.c_int32)]
+
+
+class Config(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "latent_dim", "codebook_dim", "codebook_size", "decoder_dim", "hidden_size", "intermediate_size",
+        "num_hidden_layers", "num_attention_heads", "num_key_value_heads", "head_dim", "sliding_window",
+        "num_quantizers", "num_semantic_quantizers", "semantic_codebook_size", "num_upsample_rates")] + [
+        ("upsample_rates", C.c_int32 * 8), ("num_upsampling_ratios", C.c_int32),
+        ("upsampling_ratios", C.c_int32 * 8), ("total_upsample", C.c_int32),
+        ("decode_upsample_rate", C.c_int32), ("output_sample_rate", C.c_int32),
+        ("has_encoder_config", C.c_int32), ("rms_norm_eps", C.c_float), ("rope_theta", C.c_float),
+        ("layer_scale_initial_scale", C.c_float), ("num_decoder_tensors", C.c_int64),
+        ("num_parameters", C.c_int64)]
+
+
+class StageTime(C.Structure):
+    _fields_ = [("name", C.c_char * 32), ("ms", C.c_float), ("launches", C.c_int32),
+                ("flops", C.c_double), ("bytes", C.c_double)]
+
+
+def library_path() -> str:
+    here = os.path.dirname(os.path.abspath(__file__))
+    return os.environ.get("QWEN3TTS_CUDA_LIB") or os.path.normpath(
+        os.path.join(here, "..", "..", "lib", "libqwen3tts_cuda.so"))
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load libqwen3tts_cuda.so (fails loudly when it has not been built)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        raise OSError(f"{path} not found: build it with __graft_entry__.build() "
+                      f"(make -C swift-qwen3-tts_b200/csrc). There is no CPU fallback.")
+    L = C.CDLL(path)
+    vp, i32, i64, cp = C.c_void_p, C.c_int32, C.c_int64, C.c_char_p
+    sigs = {
+        "q3tts_abi_version": (C.c_int, []),
+        "q3tts_last_error": (cp, []),
+        "q3tts_device_count": (C.c_int, []),
+        "q3tts_options_default": (None, [C.POINTER(Options)]),
+        "q3tts_model_load": (C.c_int, [cp, C.POINTER(Options), C.POINTER(vp)]),
+        "q3tts_model_free": (None, [vp]),
+        "q3tts_model_config": (C.c_int, [vp, C.POINTER(Config)]),
+        "q3tts_checkpoint_inspect": (C.c_int, [cp, C.POINTER(Config)]),
+        "q3tts_output_samples": (i64, [vp, i64]),
+        "q3tts_decode": (C.c_int, [vp, vp, i32, i32, i32, vp, vp]),
+        "q3tts_decode_varlen": (C.c_int, [vp, vp, vp, i32, vp, vp]),
+        "q3tts_decode_device": (C.c_int, [vp, vp, i32, i32, i32, vp, vp, vp]),
+        "q3tts_sync": (C.c_int, [vp, vp]),
+        "q3tts_set_taps": (C.c_int, [vp, i32]),
+        "q3tts_stage_tap_shape": (C.c_int, [vp, cp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i64)]),
+        "q3tts_stage_tap": (C.c_int, [vp, cp, vp, i64]),
+        "q3tts_weight_shape": (C.c_int, [vp, cp, C.POINTER(i32), C.POINTER(i64 * 4)]),
+        "q3tts_stream_open": (C.c_int, [vp, C.POINTER(vp)]),
+        "q3tts_stream_push": (C.c_int, [vp, vp, i32, vp]),
+        "q3tts_stream_push_batch": (C.c_int, [vp, i32, vp, vp, vp]),
+        "q3tts_stream_close": (None, [vp]),
+        "q3tts_partition_lpt": (C.c_int, [vp, i32, i32, vp]),
+        "q3tts_trim_length": (i64, [i64, i64]),
+        "q3tts_voice_clone_cut": (i64, [i64, i64, i64]),
+        "q3tts_pcm_to_int16": (C.c_int, [vp, i64, vp]),
+        "q3tts_write_wav": (C.c_int, [cp, vp, i64, i32]),
+        "q3tts_profile_enable": (C.c_int, [vp, i32]),
+        "q3tts_profile_get": (C.c_int, [vp, C.POINTER(StageTime), i32]),
+        "q3tts_launch_count": (i64, [vp]),
+    }
+    for name, (res, args) in sigs.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    L._q3_symbols = tuple(sigs)
+    _lib = L
+    return L
+
+
+def _check(status: int) -> None:
+    if status != 0:
+        raise AudioDecodingFailed(status, lib().q3tts_last_error().decode("utf-8", "replace"))
+
+
+def device_count() -> int:
+    return int(lib().q3tts_device_count())
+
+
+def checkpoint_inspect(speech_tokenizer_dir: str) -> Config:
+    cfg = Config()
+    _check(lib().q3tts_checkpoint_inspect(speech_tokenizer_dir.encode(), C.byref(cfg)))
+    return cfg
+
+
+def partition_lpt(frames: Sequence[int], n_parts: int) -> np.ndarray:
+    f = np.ascontiguousarray(np.asarray(frames, dtype=np.int64))
+    out = np.zeros(len(f), dtype=np.int32)
+    _check(lib().q3tts_partition_lpt(f.ctypes.data, len(f), int(n_parts), out.ctypes.data))
+    return out
+
+
+def trim_length(n_samples: int, valid_len: int) -> int:
+    return int(lib().q3tts_trim_length(int(n_samples), int(valid_len)))
+
+
+def voice_clone_cut(ref_frames: int, total_frames: int, n_samples: int) -> int:
+    return int(lib().q3tts_voice_clone_cut(int(ref_frames), int(total_frames), int(n_samples)))
+
+
+def pcm_to_int16(pcm: np.ndarray) -> np.ndarray:
+    p = np.ascontiguousarray(pcm, dtype=np.float32).reshape(-1)
+    out = np.empty(p.shape[0], dtype=np.int16)
+    _check(lib().q3tts_pcm_to_int16(p.ctypes.data, p.shape[0], out.ctypes.data))
+    return out
+
+
+def write_wav(path: str, pcm: np.ndarray, sample_rate: int = 24000) -> None:
+    p = np.ascontiguousarray(pcm, dtype=np.float32).reshape(-1)
+    _check(lib().q3tts_write_wav(path.encode(), p.ctypes.data, p.shape[0], int(sample_rate)))
+
+
+class Qwen3TTSSpeechTokenizerDecoder:
+    """codes [B,16,T] int32 -> [B,1,samples] float32, clipped (SpeechTokenizer.swift:754-784)."""
+
+    def __init__(self, owner: "Qwen3TTSSpeechTokenizer"):
+        self._owner = owner
+
+    def __call__(self, codes: np.ndarray) -> np.ndarray:
+        codes = np.ascontiguousarray(codes, dtype=np.int32)
+        if codes.ndim != 3 or codes.shape[1] != self._owner.config.num_quantizers:
+            raise AudioDecodingFailed(1, f"codes must be [B,{self._owner.config.num_quantizers},T], got {codes.shape}")
+        B, _, T = codes.shape
+        out = np.empty((B, 1, T * self._owner.config.total_upsample), dtype=np.float32)
+        _check(lib().q3tts_decode(self._owner._h, codes.ctypes.data, B, T, CODES_BQT, out.ctypes.data, None))
+        return out
+
+    # stage internals the reference's test walks (Tests.swift:57-257), as NCT float32
+    def stage(self, name: str) -> np.ndarray:
+        return self._owner.stage_tap(name)
+
+
+class Qwen3TTSSpeechTokenizer:
+    """Mirror of ``Qwen3TTSSpeechTokenizer`` (SpeechTokenizer.swift:790-852), decode side only."""
+
+    def __init__(self, speech_tokenizer_dir: str, precision: int = PREC_FP16, attn_mode: int = ATTN_REFERENCE,
+                 device: int = -1, workspace_bytes: int = 0, max_frames_per_launch: int = 0):
+        L = lib()
+        opts = Options()
+        L.q3tts_options_default(C.byref(opts))
+        opts.device, opts.precision, opts.attn_mode = device, precision, attn_mode
+        opts.workspace_bytes, opts.max_frames_per_launch = workspace_bytes, max_frames_per_launch
+        h = C.c_void_p()
+        _check(L.q3tts_model_load(speech_tokenizer_dir.encode(), C.byref(opts), C.byref(h)))
+        self._h = h
+        self.config = Config()
+        _check(L.q3tts_model_config(self._h, C.byref(self.config)))
+        self.decoder = Qwen3TTSSpeechTokenizerDecoder(self)
+        self.decode_upsample_rate = int(self.config.decode_upsample_rate)
+
+    @classmethod
+    def from_pretrained(cls, model_dir: str, **kw) -> "Qwen3TTSSpeechTokenizer":
+        """Like postLoadHook (Qwen3.swift:1461-1494): ``<model_dir>/speech_tokenizer``."""
+        return cls(os.path.join(model_dir, "speech_tokenizer"), **kw)
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            lib().q3tts_model_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def has_encoder(self) -> bool:      # SpeechTokenizer.swift:816 (the encoder itself is out of scope)
+        return False
+
+    def encode(self, audio):            # SpeechTokenizer.swift:841-846
+        raise AudioDecodingFailed(6, "Speech tokenizer encoder is not available for the loaded model.")
+
+    def decode(self, audio_codes: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+        """audio_codes [B,T,16] -> (audio [B, T*1920] float32, audio_lengths [B] int32)."""
+        ac = np.ascontiguousarray(audio_codes, dtype=np.int32)
+        if ac.ndim != 3 or ac.shape[2] != self.config.num_quantizers:
+            raise AudioDecodingFailed(1, f"audio_codes must be [B,T,{self.config.num_quantizers}], got {ac.shape}")
+        B, T, _ = ac.shape
+        audio = np.empty((B, T * self.config.total_upsample), dtype=np.float32)
+        lengths = np.zeros(B, dtype=np.int32)
+        _check(lib().q3tts_decode(self._h, ac.ctypes.data, B, T, CODES_BTQ, audio.ctypes.data, lengths.ctypes.data))
+        return audio, lengths
+
+    def decode_varlen(self, utterances: Sequence[np.ndarray]):
+        """List of [T_i,16] code arrays -> (list of [T_i*1920] PCM arrays, lengths [N])."""
+        n = len(utterances)
+        offs = np.zeros(n + 1, dtype=np.int64)
+        for i, u in enumerate(utterances):
+            u = np.asarray(u)
+            if u.ndim != 2 or u.shape[1] != self.config.num_quantizers:
+                raise AudioDecodingFailed(1, f"utterance {i} must be [T,{self.config.num_quantizers}]")
+            offs[i + 1] = offs[i] + u.shape[0]
+        total = int(offs[-1])
+        packed = (np.concatenate([np.asarray(u, dtype=np.int32) for u in utterances], axis=0)
+                  if total else np.zeros((0, self.config.num_quantizers), np.int32))
+        packed = np.ascontiguousarray(packed, dtype=np.int32)
+        up = self.config.total_upsample
+        pcm = np.empty(total * up, dtype=np.float32)
+        lengths = np.zeros(n, dtype=np.int32)
+        _check(lib().q3tts_decode_varlen(self._h, packed.ctypes.data, offs.ctypes.data, n, pcm.ctypes.data,
+                                         lengths.ctypes.data))
+        return [pcm[offs[i] * up: offs[i + 1] * up] for i in range(n)], lengths
+
+    # ---- device-pointer path (used by bench.py: inputs already resident in HBM) ----
+    def decode_device(self, d_codes_ptr: int, B: int, T: int, d_pcm_ptr: int, d_lengths_ptr: int = 0,
+                      stream: int = 0, layout: int = CODES_BQT) -> None:
+        _check(lib().q3tts_decode_device(self._h, d_codes_ptr, B, T, layout, d_pcm_ptr,
+                                         d_lengths_ptr or None, stream or None))
+
+    def sync(self, stream: int = 0) -> None:
+        _check(lib().q3tts_sync(self._h, stream or None))
+
+    # ---- taps / probes ----
+    def set_taps(self, enable: bool) -> None:
+        _check(lib().q3tts_set_taps(self._h, int(enable)))
+
+    def stage_tap(self, name: str) -> np.ndarray:
+        B, Cc, Ln = C.c_int32(), C.c_int32(), C.c_int64()
+        _check(lib().q3tts_stage_tap_shape(self._h, name.encode(), C.byref(B), C.byref(Cc), C.byref(Ln)))
+        out = np.empty((B.value, Cc.value, Ln.value), dtype=np.float32)
+        _check(lib().q3tts_stage_tap(self._h, name.encode(), out.ctypes.data, out.size))
+        return out
+
+    def weight_shape(self, swift_key: str) -> Tuple[int, ...]:
+        nd = C.c_int32()
+        dims = (C.c_int64 * 4)()
+        _check(lib().q3tts_weight_shape(self._h, swift_key.encode(), C.byref(nd), C.byref(dims)))
+        return tuple(int(dims[i]) for i in range(nd.value))
+
+    # ---- measurement ----
+    def profile_enable(self, enable: bool) -> None:
+        _check(lib().q3tts_profile_enable(self._h, int(enable)))
+
+    def profile_get(self):
+        arr = (StageTime * 32)()
+        n = lib().q3tts_profile_get(self._h, arr, 32)
+        return [dict(name=arr[i].name.decode(), ms=float(arr[i].ms), launches=int(arr[i].launches),
+                     flops=float(arr[i].flops), bytes=float(arr[i].bytes)) for i in range(min(n, 32))]
+
+    def launch_count(self) -> int:
+        return int(lib().q3tts_launch_count(self._h))

@@ -1,0 +1,262 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (ctypes mirror of the reference's
+Swift API), against the CPU oracle on the same seeded inputs and against the committed golden
+fixtures.  Tolerances are north_star's: bit-exact codebook indexing / dequantised sums and PCM
+max-abs <= 1e-4 in fp32 mode; SNR >= 40 dB in the 16-bit tensor-core mode."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import qwen3tts_cuda as q
+from oracle import decoder as od
+from oracle import weights as ow
+from tools.fixtures import checkpoint_dir
+from tools.q3cfg import GOLDEN_CODES_5x16
+from tools.synth_checkpoint import synth_codes
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+FP32_TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def tiny_tok(tiny_dir):
+    tok = q.Qwen3TTSSpeechTokenizer(tiny_dir, precision=q.PREC_FP32)
+    yield tok
+    tok.close()
+
+
+@pytest.fixture(scope="module")
+def full_tok(full_dir):
+    tok = q.Qwen3TTSSpeechTokenizer(full_dir, precision=q.PREC_FP32)
+    yield tok
+    tok.close()
+
+
+def _nct_codes(cfg, B, T, seed, **kw):
+    return synth_codes(cfg, B, T, seed, **kw)
+
+
+def test_native_library_is_loaded_and_sees_the_gpu():
+    assert q.device_count() >= 1
+    assert os.path.exists(q.library_path())
+
+
+# ---- fp32 mode: tiny architecture, every stage -----------------------------------------------------
+@pytest.mark.parametrize("B,T", [(1, 1), (1, 6), (2, 9), (3, 33)])
+def test_fp32_stage_taps_match_oracle_tiny(tiny_tok, tiny_oracle, B, T):
+    cfg, w, dec = tiny_oracle
+    codes = _nct_codes(cfg, B, T, 100 + T)
+    taps = {}
+    ref = dec.forward(codes, taps).numpy()
+    tiny_tok.set_taps(True)
+    out = tiny_tok.decoder(codes)
+    assert out.shape == ref.shape
+    # bit-exact dequantised sums (sequential fp32 adds, ST.swift:84-93) -- compare against an fp32 oracle
+    taps32 = {}
+    od.OracleDecoder(cfg, w, torch.float32).forward(codes, taps32)
+    for name in ("rvq_sum_first", "rvq_sum_rest"):
+        got = tiny_tok.stage_tap(name)
+        assert np.array_equal(got, taps32[name].numpy()), name
+    for name in ("quantized", "pre_conv", "pre_transformer", "upsample0", "upsample1", "init_conv",
+                 "block0", "block1", "block2", "block3", "out_conv"):
+        got = tiny_tok.stage_tap(name)
+        want = taps[name].numpy()
+        assert got.shape == want.shape, name
+        scale = max(1.0, float(np.abs(want).max()))
+        assert np.abs(got - want).max() <= 2e-5 * scale, (name, float(np.abs(got - want).max()))
+    tiny_tok.set_taps(False)
+    assert np.abs(out - ref).max() <= FP32_TOL
+
+
+def test_fp32_tiny_golden_fixture(tiny_tok):
+    gold = np.load(os.path.join(GOLD, "golden_tiny.npz"))
+    out = tiny_tok.decoder(gold["codes"])
+    assert np.abs(out - gold["reference_audio"]).max() <= FP32_TOL
+
+
+def test_fp32_causal_sw_mode_matches_oracle(tiny_dir, tiny_oracle):
+    cfg, w, _ = tiny_oracle
+    tok = q.Qwen3TTSSpeechTokenizer(tiny_dir, precision=q.PREC_FP32, attn_mode=q.ATTN_CAUSAL_SW)
+    codes = _nct_codes(cfg, 2, 11, 77)
+    ref = od.OracleDecoder(cfg, w, torch.float64, attn_mode="causal_sw").forward(codes).numpy()
+    out = tok.decoder(codes)
+    assert np.abs(out - ref).max() <= FP32_TOL
+    gold = np.load(os.path.join(GOLD, "golden_tiny.npz"))
+    assert np.abs(tok.decoder(gold["codes"]) - gold["causal_sw_audio"]).max() <= FP32_TOL
+    tok.close()
+
+
+# ---- the reference's API surface ---------------------------------------------------------------------
+def test_decode_api_lengths_and_layouts(tiny_tok, tiny_oracle):
+    cfg, w, dec = tiny_oracle
+    codes = _nct_codes(cfg, 3, 8, 5, zero_frac=0.3)       # zeros sprinkled in codebook 0
+    bt16 = np.ascontiguousarray(np.transpose(codes, (0, 2, 1)))
+    ref_audio, ref_len = dec.decode(bt16)
+    audio, lengths = tiny_tok.decode(bt16)
+    assert audio.shape == (3, 8 * cfg.total_upsample) and audio.dtype == np.float32
+    assert np.array_equal(lengths, ref_len) and lengths.dtype == np.int32
+    assert np.abs(audio - ref_audio.numpy()).max() <= FP32_TOL
+    nct = tiny_tok.decoder(codes)                           # [B,16,T] -> [B,1,S]
+    assert nct.shape == (3, 1, 8 * cfg.total_upsample)
+    assert np.array_equal(nct[:, 0, :], audio)              # both entry points run the same chain
+
+
+def test_batch_rows_equal_single_decodes(tiny_tok, tiny_oracle):
+    cfg, _, _ = tiny_oracle
+    codes = _nct_codes(cfg, 4, 7, 8)
+    full = tiny_tok.decoder(codes)
+    for b in range(4):
+        one = tiny_tok.decoder(codes[b:b + 1])
+        assert np.array_equal(full[b], one[0])              # same kernels, same order: bit-identical
+
+
+def test_varlen_equals_per_utterance_decode(tiny_tok, tiny_oracle):
+    cfg, w, dec = tiny_oracle
+    rng = np.random.default_rng(3)
+    lens = [1, 17, 5, 0, 9, 17, 2]
+    utts = [np.ascontiguousarray(np.transpose(_nct_codes(cfg, 1, max(L, 1), 200 + i)[0], (1, 0)))[:L] for i, L in enumerate(lens)]
+    pcms, lengths = tiny_tok.decode_varlen(utts)
+    assert [p.shape[0] for p in pcms] == [L * cfg.total_upsample for L in lens]
+    for i, (u, L) in enumerate(zip(utts, lens)):
+        if L == 0:
+            assert lengths[i] == 0
+            continue
+        ref_audio, ref_len = dec.decode(u[None])
+        assert np.abs(pcms[i] - ref_audio.numpy()[0]).max() <= FP32_TOL, i
+        assert lengths[i] == ref_len[0]
+        single, _ = tiny_tok.decode(u[None])
+        assert np.abs(pcms[i] - single[0]).max() <= 1e-6      # padding never leaks into valid frames (H5)
+
+
+def test_microbatching_is_invisible(tiny_dir, tiny_oracle):
+    cfg, _, _ = tiny_oracle
+    codes = _nct_codes(cfg, 5, 12, 31)
+    a = q.Qwen3TTSSpeechTokenizer(tiny_dir, precision=q.PREC_FP32)
+    b = q.Qwen3TTSSpeechTokenizer(tiny_dir, precision=q.PREC_FP32, max_frames_per_launch=25)   # 2 utterances per launch
+    assert np.array_equal(a.decoder(codes), b.decoder(codes))
+    a.close()
+    b.close()
+
+
+def test_empty_and_error_inputs(tiny_tok, tiny_oracle):
+    cfg, _, _ = tiny_oracle
+    out = tiny_tok.decoder(np.zeros((0, cfg.num_quantizers, 4), np.int32))
+    assert out.shape == (0, 1, 4 * cfg.total_upsample)
+    out = tiny_tok.decoder(np.zeros((2, cfg.num_quantizers, 0), np.int32))
+    assert out.shape == (2, 1, 0)
+    pcms, lengths = tiny_tok.decode_varlen([])
+    assert pcms == [] and lengths.shape == (0,)
+    bad = _nct_codes(cfg, 1, 4, 1)
+    bad[0, 3, 2] = cfg.codebook_size                        # acoustic id out of range
+    with pytest.raises(q.AudioDecodingFailed) as e:
+        tiny_tok.decoder(bad)
+    assert e.value.status == 1
+    ok = _nct_codes(cfg, 1, 4, 1)
+    ok[0, 0, 1] = cfg.semantic_codebook_size - 1            # semantic ids may exceed codebook_size (4096 table)
+    tiny_tok.decoder(ok)
+    with pytest.raises(q.AudioDecodingFailed):
+        tiny_tok.decoder(np.zeros((1, 3, 4), np.int32))     # wrong number of codebooks
+    with pytest.raises(q.AudioDecodingFailed):
+        tiny_tok.stage_tap("no_such_stage")
+
+
+@pytest.mark.parametrize("kw", [dict(dtype="float16"), dict(with_encoder_stub=True), dict(mlx_layout=True)])
+def test_checkpoint_variants_decode_identically(tiny_cfg, tiny_oracle, kw):
+    cfg, w, dec = tiny_oracle
+    st = os.path.join(checkpoint_dir(tiny_cfg, seed=7, **kw), "speech_tokenizer")
+    tok = q.Qwen3TTSSpeechTokenizer(st, precision=q.PREC_FP32)
+    codes = _nct_codes(cfg, 1, 6, 12)
+    out = tok.decoder(codes)
+    if kw.get("dtype") == "float16":     # the lite variant: fp16 on disk: compare against an oracle on the same file
+        c2, w2 = ow.load_decoder(st)
+        ref = od.OracleDecoder(c2.decoder_config, w2, torch.float64).forward(codes).numpy()
+    else:
+        ref = dec.forward(codes).numpy()
+    assert np.abs(out - ref).max() <= FP32_TOL
+    tok.close()
+
+
+def test_device_pointer_path(tiny_tok, tiny_oracle):
+    cfg, _, _ = tiny_oracle
+    codes = _nct_codes(cfg, 2, 10, 19)
+    want = tiny_tok.decoder(codes)
+    d_codes = torch.from_numpy(codes).cuda()
+    d_pcm = torch.empty((2, 10 * cfg.total_upsample), dtype=torch.float32, device="cuda")
+    d_len = torch.empty(2, dtype=torch.int32, device="cuda")
+    s = torch.cuda.current_stream()
+    tiny_tok.decode_device(d_codes.data_ptr(), 2, 10, d_pcm.data_ptr(), d_len.data_ptr(), s.cuda_stream)
+    tiny_tok.sync(s.cuda_stream)
+    assert np.array_equal(d_pcm.cpu().numpy(), want[:, 0, :])
+    assert d_len.cpu().tolist() == [10 * cfg.total_upsample] * 2
+
+
+# ---- full-size architecture ----------------------------------------------------------------------------
+def test_full_golden_grid_fp32(full_tok, full_oracle):
+    cfg, w, dec = full_oracle
+    gold = np.load(os.path.join(GOLD, "golden_full_5x16.npz"))
+    codes = np.asarray(GOLDEN_CODES_5x16, dtype=np.int32)[None]          # [1,5,16]  Tests.swift:37-47
+    full_tok.set_taps(True)
+    audio, lengths = full_tok.decode(codes)
+    assert audio.shape == (1, 9600) and lengths.tolist() == [9600]       # Tests.swift:253; ST.swift:833
+    assert np.abs(audio - gold["audio"]).max() <= FP32_TOL
+    # the reference test's stage walk (Tests.swift:57-257): shapes and statistics per stage
+    for name, shp in (("quantized", (1, 512, 5)), ("pre_conv", (1, 1024, 5)), ("pre_transformer", (1, 1024, 5)),
+                      ("upsample0", (1, 1024, 10)), ("upsample1", (1, 1024, 20)), ("init_conv", (1, 1536, 20)),
+                      ("block0", (1, 768, 160)), ("block1", (1, 384, 800)), ("block2", (1, 192, 3200)),
+                      ("block3", (1, 96, 9600)), ("out_conv", (1, 1, 9600))):
+        t = full_tok.stage_tap(name)
+        assert t.shape == shp, name
+        assert abs(float(t.std()) - gold[f"stat_{name}"][0]) <= 1e-3 * max(1.0, float(t.std())), name
+    assert np.abs(full_tok.stage_tap("quantized")[0, :10, 0] - gold["quantized_0_10_0"]).max() <= 1e-4
+    assert full_tok.weight_shape("decoder.decoder.initConv.conv.weight") == (1536, 7, 1024)   # Tests.swift:131-132
+    full_tok.set_taps(False)
+
+
+def test_full_fp32_vs_oracle_and_rvq_bit_exact(full_tok, full_oracle):
+    cfg, w, dec = full_oracle
+    codes = _nct_codes(cfg, 2, 20, 1001)
+    taps = {}
+    ref = dec.forward(codes, taps).numpy()
+    full_tok.set_taps(True)
+    out = full_tok.decoder(codes)
+    assert np.array_equal(full_tok.stage_tap("rvq_sum_first"), taps["rvq_sum_first"].numpy())
+    assert np.array_equal(full_tok.stage_tap("rvq_sum_rest"), taps["rvq_sum_rest"].numpy())
+    full_tok.set_taps(False)
+    assert np.abs(out - ref).max() <= FP32_TOL
+    assert float(np.abs(ref).max()) < 1.0
+
+
+@pytest.mark.parametrize("prec,floor", [(q.PREC_FP16, 40.0), (q.PREC_BF16, 22.0)])
+def test_full_16bit_snr(full_dir, full_oracle, prec, floor):
+    # north_star: SNR >= 40 dB in the 16-bit mode.  fp16 operands meet it; bf16 operands cannot on this
+    # decoder (27 dB even with ideal fp32 accumulation -- see DESIGN.md "precision"), so bf16 is
+    # checked against its own documented floor.
+    cfg, w, dec = full_oracle
+    codes = _nct_codes(cfg, 2, 20, 1001)
+    ref = dec.forward(codes).numpy()
+    tok = q.Qwen3TTSSpeechTokenizer(full_dir, precision=prec)
+    out = tok.decoder(codes)
+    snr = od.snr_db(ref, out)
+    print(f"precision {prec}: SNR {snr:.1f} dB")
+    assert snr >= floor
+    tok.close()
+
+
+def test_full_size_properties_config1(full_dir):
+    # BASELINE config 1 (B=1, T=125) and a slice of config 2: size-independent properties --
+    # batch rows == single decodes, prefix-invariance of everything but attention is covered at tiny
+    # size; here: determinism, range, lengths.
+    from tools.q3cfg import DecoderConfig
+    cfg = DecoderConfig()
+    tok = q.Qwen3TTSSpeechTokenizer(full_dir, precision=q.PREC_FP16)
+    codes = _nct_codes(cfg, 2, 125, 1001)
+    bt16 = np.ascontiguousarray(np.transpose(codes, (0, 2, 1)))
+    a1, l1 = tok.decode(bt16)
+    a2, l2 = tok.decode(bt16)
+    assert a1.shape == (2, 240000) and np.array_equal(a1, a2) and l1.tolist() == [240000, 240000]
+    assert np.isfinite(a1).all() and np.abs(a1).max() <= 1.0 and a1.std() > 0.01
+    single, _ = tok.decode(bt16[1:2])
+    assert np.abs(single[0] - a1[1]).max() <= 1e-6
+    tok.close()
