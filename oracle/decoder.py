@@ -36,7 +36,7 @@ STAGES = ("quantized", "pre_conv", "pre_transformer", "upsample0", "upsample1", 
 class OracleDecoder:
     def __init__(self, cfg: DecoderConfig, weights: Dict[str, np.ndarray], dtype=torch.float32,
                  attn_mode: str = "reference", operand: str = "native", use_rope: bool = False,
-                 store: str = "native"):
+                 store: str = "native", decode_upsample_rate: int = 0):
         assert attn_mode in ("reference", "causal_sw")
         assert operand in ("native", "bf16", "fp16")
         self.cfg = cfg
@@ -44,6 +44,7 @@ class OracleDecoder:
         self.attn_mode = attn_mode
         self.operand = operand
         self.use_rope = use_rope
+        self.decode_upsample_rate = decode_upsample_rate or cfg.total_upsample
         assert store in ("native", "bf16", "fp16")
         self.store = store   # rounding of the residual stream when a stage writes it to HBM
         self.w = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dtype) for k, v in weights.items()
@@ -257,7 +258,7 @@ class OracleDecoder:
         codes = np.transpose(ac, (0, 2, 1))
         wav = self.forward(codes, taps).squeeze(1)
         valid = (ac[:, :, 0] > 0).sum(axis=1)
-        lengths = (valid * self.cfg.total_upsample).astype(np.int32)
+        lengths = (valid * self.decode_upsample_rate).astype(np.int32)   # ST.swift:833 uses the tokenizer-level rate
         return wav, lengths
 
 

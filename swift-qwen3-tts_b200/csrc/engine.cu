@@ -39,7 +39,10 @@ static float* upload(Model& m, const std::vector<float>& v) {
   float* d = nullptr;
   CUDA_OK(cudaMalloc(&d, std::max<size_t>(v.size(), 1) * sizeof(float)));
   m.allocs.push_back(d);
-  CUDA_OK(cudaMemcpy(d, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));
+  // Stream-ordered with the fp32->16-bit convert kernels that follow on m.stream.  (A plain cudaMemcpy from pageable
+  // memory may return before the DMA lands, and m.stream is non-blocking: the convert could read stale bytes.)
+  CUDA_OK(cudaMemcpyAsync(d, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice, m.stream));
+  CUDA_OK(cudaStreamSynchronize(m.stream));
   return d;
 }
 
@@ -148,6 +151,7 @@ Model* model_create(const Checkpoint& ck, const q3tts_options& opts) {
     throw Error(Q3TTS_ECUDA, std::string("device ") + prop.name + " is not sm_100: libqwen3tts_cuda is built for sm_100a only and has no fallback");
   m.op_dtype = opts.precision == Q3TTS_PREC_FP32 ? DT_F32 : (opts.precision == Q3TTS_PREC_FP16 ? DT_F16 : DT_BF16);
   m.st_dtype = m.op_dtype;
+  if (const char* e = getenv("Q3TTS_STREAM_F32")) { if (e[0] == '1') m.st_dtype = DT_F32; }   // keep the blocks' residual stream in fp32
   CUDA_OK(cudaStreamCreateWithFlags(&m.stream, cudaStreamNonBlocking));
   const q3tts_config& c = m.cfg;
   if (c.latent_dim > 2048) throw Error(Q3TTS_EFORMAT, "latent_dim > 2048 is not supported");
@@ -170,10 +174,11 @@ Model* model_create(const Checkpoint& ck, const q3tts_options& opts) {
   }
   CUDA_OK(cudaMalloc(&m.d_tables, tabs.size() * sizeof(float*)));
   m.allocs.push_back((void*)m.d_tables);
-  CUDA_OK(cudaMemcpy((void*)m.d_tables, tabs.data(), tabs.size() * sizeof(float*), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpyAsync((void*)m.d_tables, tabs.data(), tabs.size() * sizeof(float*), cudaMemcpyHostToDevice, m.stream));
   CUDA_OK(cudaMalloc(&m.d_table_sizes, sizes.size() * 4));
   m.allocs.push_back(m.d_table_sizes);
-  CUDA_OK(cudaMemcpy(m.d_table_sizes, sizes.data(), sizes.size() * 4, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpyAsync(m.d_table_sizes, sizes.data(), sizes.size() * 4, cudaMemcpyHostToDevice, m.stream));
+  CUDA_OK(cudaStreamSynchronize(m.stream));
 
   // --- RVQ output projections as ONE GEMM over [sum_first | sum_rest] (ST.swift:161-169, 214-226) ---
   {

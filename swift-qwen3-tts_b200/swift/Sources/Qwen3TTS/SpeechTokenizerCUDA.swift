@@ -1,0 +1,158 @@
+//
+//  SpeechTokenizerCUDA.swift
+//
+//  Drop-in replacement for the decode side of Sources/Qwen3TTS/Models/SpeechTokenizer.swift
+//  (Qwen3TTSSpeechTokenizer / Qwen3TTSSpeechTokenizerDecoder, lines 696-852 of the reference)
+//  whose MLXArray ops are replaced by calls into libqwen3tts_cuda through the CQwen3TTSCUDA
+//  system-library module.  Same type names, method names, argument labels and shapes; MLXArray is
+//  replaced by the minimal host tensors below because MLX is not a dependency of this path.
+//
+//  NOTE: authored against the C header, NOT compiled in the build image (no Swift toolchain there);
+//  the same C ABI is exercised by the C++/ctypes tests.  See INTEGRATION.md.
+//
+
+import Foundation
+import CQwen3TTSCUDA
+
+/// Minimal row-major host tensors (what the decode path needs from MLXArray).
+public struct Int32Tensor {
+    public var shape: [Int]
+    public var data: [Int32]
+    public init(shape: [Int], data: [Int32]) {
+        precondition(shape.reduce(1, *) == data.count, "shape does not match element count")
+        self.shape = shape
+        self.data = data
+    }
+}
+
+public struct FloatTensor {
+    public var shape: [Int]
+    public var data: [Float]
+    public subscript(row: Int) -> ArraySlice<Float> {          // audio[0]  (Qwen3.swift:748)
+        let n = shape.dropFirst().reduce(1, *)
+        return data[(row * n)..<((row + 1) * n)]
+    }
+}
+
+/// Mirrors `AudioGenerationError.audioDecodingFailed(String)` (Core/GenerationTypes.swift:67).
+public enum Qwen3TTSCUDAError: Error, LocalizedError {
+    case audioDecodingFailed(String)
+    public var errorDescription: String? {
+        if case .audioDecodingFailed(let m) = self { return "Audio decoding failed: \(m)" }
+        return nil
+    }
+}
+
+@inline(__always)
+private func check(_ status: Int32) throws {
+    if status != Q3TTS_OK.rawValue.toInt32 {
+        throw Qwen3TTSCUDAError.audioDecodingFailed(String(cString: q3tts_last_error()))
+    }
+}
+
+private extension UInt32 { var toInt32: Int32 { Int32(self) } }
+
+public enum Qwen3TTSPrecision: Int32 { case fp32 = 0, fp16 = 1, bf16 = 2 }
+
+/// Main decoder: codes -> audio waveform (SpeechTokenizer.swift:696-785).
+public final class Qwen3TTSSpeechTokenizerDecoder {
+    let handle: OpaquePointer
+    let totalUpsample: Int
+    let numQuantizers: Int
+
+    init(handle: OpaquePointer, config: q3tts_config) {
+        self.handle = handle
+        self.totalUpsample = Int(config.total_upsample)
+        self.numQuantizers = Int(config.num_quantizers)
+    }
+
+    /// Decode codes to audio.
+    /// - Parameter codes: [batch, num_quantizers, time]
+    /// - Returns: [batch, 1, samples], clipped to [-1, 1]      (SpeechTokenizer.swift:754-784)
+    public func callAsFunction(_ codes: Int32Tensor) throws -> FloatTensor {
+        precondition(codes.shape.count == 3 && codes.shape[1] == numQuantizers)
+        let (b, t) = (codes.shape[0], codes.shape[2])
+        var pcm = [Float](repeating: 0, count: b * t * totalUpsample)
+        try codes.data.withUnsafeBufferPointer { c in
+            try pcm.withUnsafeMutableBufferPointer { p in
+                try check(q3tts_decode(handle, c.baseAddress, Int32(b), Int32(t), Int32(Q3TTS_CODES_BQT.rawValue),
+                                       p.baseAddress, nil))
+            }
+        }
+        return FloatTensor(shape: [b, 1, t * totalUpsample], data: pcm)
+    }
+}
+
+/// Main speech tokenizer class (SpeechTokenizer.swift:790-852), decode side.
+public final class Qwen3TTSSpeechTokenizer {
+    public let decoder: Qwen3TTSSpeechTokenizerDecoder
+    let decodeUpsampleRate: Int
+    private let handle: OpaquePointer
+
+    /// Replaces the speech-tokenizer half of `postLoadHook(modelDir:)` (Qwen3.swift:1461-1494):
+    /// `speechTokenizerDir` = `<modelDir>/speech_tokenizer` (config.json + *.safetensors).
+    public init(speechTokenizerDir: URL, precision: Qwen3TTSPrecision = .fp16, device: Int32 = -1) throws {
+        var opts = q3tts_options()
+        q3tts_options_default(&opts)
+        opts.precision = precision.rawValue
+        opts.device = device
+        var h: OpaquePointer?
+        try check(q3tts_model_load(speechTokenizerDir.path, &opts, &h))
+        guard let model = h else { throw Qwen3TTSCUDAError.audioDecodingFailed("q3tts_model_load returned NULL") }
+        var cfg = q3tts_config()
+        try check(q3tts_model_config(model, &cfg))
+        self.handle = model
+        self.decodeUpsampleRate = Int(cfg.decode_upsample_rate)
+        self.decoder = Qwen3TTSSpeechTokenizerDecoder(handle: model, config: cfg)
+    }
+
+    deinit { q3tts_model_free(handle) }
+
+    /// The CUDA path is decode-only (the encoder stays on the reference implementation).
+    public var hasEncoder: Bool { false }                      // SpeechTokenizer.swift:816
+
+    /// Decode codes to audio
+    /// - Parameter audioCodes: [batch, seq_len, num_quantizers]
+    /// - Returns: (audio [batch, samples], audio_lengths [batch])   (SpeechTokenizer.swift:823-836)
+    public func decode(_ audioCodes: Int32Tensor) throws -> (audio: FloatTensor, audioLengths: [Int32]) {
+        precondition(audioCodes.shape.count == 3 && audioCodes.shape[2] == decoder.numQuantizers)
+        let (b, t) = (audioCodes.shape[0], audioCodes.shape[1])
+        var pcm = [Float](repeating: 0, count: b * t * decoder.totalUpsample)
+        var lengths = [Int32](repeating: 0, count: b)
+        try audioCodes.data.withUnsafeBufferPointer { c in
+            try pcm.withUnsafeMutableBufferPointer { p in
+                try lengths.withUnsafeMutableBufferPointer { l in
+                    try check(q3tts_decode(handle, c.baseAddress, Int32(b), Int32(t), Int32(Q3TTS_CODES_BTQ.rawValue),
+                                           p.baseAddress, l.baseAddress))
+                }
+            }
+        }
+        return (FloatTensor(shape: [b, t * decoder.totalUpsample], data: pcm), lengths)
+    }
+
+    /// Batch of utterances of different lengths, each [T_i, 16]; every result equals its own B=1 decode.
+    public func decodeBatch(_ utterances: [Int32Tensor]) throws -> (audio: [[Float]], audioLengths: [Int32]) {
+        var offsets = [Int64](repeating: 0, count: utterances.count + 1)
+        var packed = [Int32]()
+        for (i, u) in utterances.enumerated() {
+            precondition(u.shape.count == 2 && u.shape[1] == decoder.numQuantizers)
+            offsets[i + 1] = offsets[i] + Int64(u.shape[0])
+            packed.append(contentsOf: u.data)
+        }
+        let up = decoder.totalUpsample
+        var pcm = [Float](repeating: 0, count: Int(offsets.last!) * up)
+        var lengths = [Int32](repeating: 0, count: utterances.count)
+        try packed.withUnsafeBufferPointer { c in
+            try offsets.withUnsafeBufferPointer { o in
+                try pcm.withUnsafeMutableBufferPointer { p in
+                    try lengths.withUnsafeMutableBufferPointer { l in
+                        try check(q3tts_decode_varlen(handle, c.baseAddress, o.baseAddress, Int32(utterances.count),
+                                                      p.baseAddress, l.baseAddress))
+                    }
+                }
+            }
+        }
+        let audio = (0..<utterances.count).map { i in Array(pcm[(Int(offsets[i]) * up)..<(Int(offsets[i + 1]) * up)]) }
+        return (audio, lengths)
+    }
+}

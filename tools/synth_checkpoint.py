@@ -162,7 +162,8 @@ def write_checkpoint(model_dir: str, cfg: Optional[DecoderConfig] = None, seed: 
             state[k] = (v.permute(1, 2, 0) if is_t else v.permute(0, 2, 1)).contiguous()
     tdtype = {"float32": torch.float32, "float16": torch.float16, "bfloat16": torch.bfloat16}[dtype]
     out = {k: v.to(tdtype).contiguous() for k, v in state.items()}
-    tok = TokenizerConfig(decoder_config=cfg)
+    # decode_upsample_rate is a separate tokenizer-level key (Cfg.swift:590); keep it consistent with the decoder
+    tok = TokenizerConfig(decoder_config=cfg, decode_upsample_rate=cfg.total_upsample, encode_downsample_rate=cfg.total_upsample)
     if with_encoder_stub:
         out["encoder.encoder.layers.0.conv.weight"] = torch.zeros(4, 1, 7, dtype=tdtype)
         out["encoder.quantizer.semantic_residual_vector_quantizer.layers.0.codebook.embed_sum"] = torch.zeros(8, 4, dtype=tdtype)
