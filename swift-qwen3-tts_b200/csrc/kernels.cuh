@@ -71,6 +71,11 @@ void launch_dwconv_ln(const float* x, const float* w7 /*[C][7]*/, const float* w
 void launch_attention(const void* qkv, int qkv_dtype, void* out, int out_dtype, const BatchGeom& g, int nh,
                       int nkv, int hd, float scale, int causal_window /*0 = full*/, cudaStream_t s);
 
+// Tensor-core (mma.sync) flash-style attention for 16-bit operands, head_dim 64 (kernels_attn.cu).
+bool attention_mma_supported(int dtype, int hd);
+void launch_attention_mma(const void* qkv, int dtype, void* out, const BatchGeom& g, int nh, int nkv, float scale,
+                          int causal_window, cudaStream_t s);
+
 // Tail: causal conv C->1, k=7 on the (already outSnake-activated) operand, + bias, clip to [-1,1].
 // pcm address = pcm + pcm_base[b] + t.  Optional unclipped fp32 copy for the "out_conv" tap.
 void launch_tail(const void* a, int a_dtype, int64_t a_bstride, const float* w /*[7][C]*/, float bias, int C,
@@ -93,5 +98,9 @@ bool tc_supported(const ConvGemmParams& p, int op_dtype);
 // A/W/out_a are `op_dtype` (F16/BF16) operands, fp32 accumulate in TMEM; res/out_y are `y_dtype`.
 cudaError_t launch_conv_gemm_tc(const ConvGemmParams& p, const BatchGeom& g, int op_dtype, int y_dtype,
                                 cudaStream_t s);
+// Second generation (kernels_tc2.cu): halo tiles (one TMA box serves every tap) + cluster-multicast weights.
+bool tc2_supported(const ConvGemmParams& p, int op_dtype);
+cudaError_t launch_conv_gemm_tc2(const ConvGemmParams& p, const BatchGeom& g, int op_dtype, int y_dtype,
+                                 cudaStream_t s);
 
 }  // namespace q3

@@ -3,6 +3,7 @@
 // Semantics follow /root/reference/Sources/Qwen3TTS/Models/SpeechTokenizer.swift (ST.swift);
 // each kernel cites the lines it implements.
 #include <math.h>
+#include <stdlib.h>
 
 #include "kernels.cuh"
 
@@ -396,6 +397,11 @@ static void attention_dispatch(const void* qkv, void* out, const BatchGeom& g, i
 void launch_attention(const void* qkv, int qkv_dtype, void* out, int out_dtype, const BatchGeom& g, int nh, int nkv,
                       int hd, float scale, int causal_window, cudaStream_t s) {
   // fp32 softmax accumulation in every mode (MLX's fused SDPA does the same)
+  static const bool no_mma = [] { const char* e = getenv("Q3TTS_NO_MMA_ATTN"); return e && e[0] == '1'; }();
+  if (!no_mma && attention_mma_supported(qkv_dtype, hd)) {
+    launch_attention_mma(qkv, qkv_dtype, out, g, nh, nkv, scale, causal_window, s);
+    return;
+  }
   if (qkv_dtype == DT_F32) attention_dispatch<float, float>(qkv, out, g, nh, nkv, hd, scale, causal_window, s);
   else if (qkv_dtype == DT_F16) attention_dispatch<__half, __half>(qkv, out, g, nh, nkv, hd, scale, causal_window, s);
   else attention_dispatch<__nv_bfloat16, __nv_bfloat16>(qkv, out, g, nh, nkv, hd, scale, causal_window, s);
@@ -432,9 +438,73 @@ tail_kernel(const TI* a, int64_t a_bstride, const float* w, float bias, int C, f
   }
 }
 
+// 16-bit operand, C in {72, 96}: one thread per output sample, the 7-row x C window staged once per CTA in shared
+// memory with 128-bit loads (row stride C+8 halves = conflict-free LDS.128), weights as FFMA constant operands.
+constexpr int TAIL_TILE = 192;
+__constant__ float c_tail_w[7 * 128];
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8], __half) {
+  const float2 a = __half22float2(*(const __half2*)&u.x), b = __half22float2(*(const __half2*)&u.y),
+               c = __half22float2(*(const __half2*)&u.z), d = __half22float2(*(const __half2*)&u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8], __nv_bfloat16) {
+  const float2 a = __bfloat1622float2(*(const __nv_bfloat162*)&u.x), b = __bfloat1622float2(*(const __nv_bfloat162*)&u.y),
+               c = __bfloat1622float2(*(const __nv_bfloat162*)&u.z), d = __bfloat1622float2(*(const __nv_bfloat162*)&u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+
+template <typename T16, int C>
+__global__ void __launch_bounds__(TAIL_TILE)
+tail16_kernel(const T16* a, int64_t a_bstride, float bias, float* pcm, const int64_t* pcm_base, float* tap,
+              int64_t tap_bstride, BatchGeom g, int rows_per_frame, int tiles_per_utt) {
+  constexpr int STRIDE = C + 8, ROWS = TAIL_TILE + 6, V = C / 8;
+  __shared__ __align__(16) T16 tile[ROWS * STRIDE];
+  const int b = blockIdx.x / tiles_per_utt;
+  const int64_t t0 = (int64_t)(blockIdx.x % tiles_per_utt) * TAIL_TILE;
+  const int64_t slot_rows = (int64_t)g.Tmax * rows_per_frame, valid = (int64_t)g.len_frames[b] * rows_per_frame;
+  if (t0 >= valid) return;
+  const T16* ab = a + (int64_t)b * a_bstride;
+  for (int idx = threadIdx.x; idx < ROWS * V; idx += TAIL_TILE) {
+    const int row = idx / V, c8 = idx % V;
+    const int64_t tin = t0 - 6 + row;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (tin >= 0 && tin < slot_rows) v = __ldg((const uint4*)(ab + tin * C + c8 * 8));
+    *(uint4*)&tile[row * STRIDE + c8 * 8] = v;
+  }
+  __syncthreads();
+  const int64_t t = t0 + threadIdx.x;
+  float acc = 0.f;
+#pragma unroll
+  for (int j = 0; j < 7; ++j) {
+#pragma unroll
+    for (int c8 = 0; c8 < V; ++c8) {
+      float f[8];
+      unpack8(*(const uint4*)&tile[(threadIdx.x + j) * STRIDE + c8 * 8], f, T16());
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc = fmaf(c_tail_w[j * C + c8 * 8 + e], f[e], acc);
+    }
+  }
+  if (t < valid) {
+    const float v = acc + bias;
+    if (tap) tap[(int64_t)b * tap_bstride + t] = v;
+    pcm[pcm_base[b] + t] = fminf(fmaxf(v, -1.0f), 1.0f);
+  }
+}
+
 void launch_tail(const void* a, int a_dtype, int64_t a_bstride, const float* w, float bias, int C, float* pcm,
                  const int64_t* pcm_base, float* tap, int64_t tap_bstride, const BatchGeom& g, int rows_per_frame,
                  cudaStream_t s) {
+  if (a_dtype != DT_F32 && (C == 96 || C == 72)) {
+    cudaMemcpyToSymbolAsync(c_tail_w, w, (size_t)7 * C * sizeof(float), 0, cudaMemcpyDeviceToDevice, s);
+    const int tiles = (int)(((int64_t)g.Tmax * rows_per_frame + TAIL_TILE - 1) / TAIL_TILE);
+    const unsigned blocks = (unsigned)(g.B * tiles);
+#define Q3_TAIL(T, CC) tail16_kernel<T, CC><<<blocks, TAIL_TILE, 0, s>>>((const T*)a, a_bstride, bias, pcm, pcm_base, tap, tap_bstride, g, rows_per_frame, tiles)
+    if (a_dtype == DT_F16) { if (C == 96) Q3_TAIL(__half, 96); else Q3_TAIL(__half, 72); }
+    else { if (C == 96) Q3_TAIL(__nv_bfloat16, 96); else Q3_TAIL(__nv_bfloat16, 72); }
+#undef Q3_TAIL
+    return;
+  }
   const int64_t warps = (int64_t)g.B * g.Tmax * rows_per_frame;
   const unsigned blocks = (unsigned)((warps * 32 + 255) / 256);
   Q3_DISPATCH_DT(a_dtype, T, (tail_kernel<T><<<blocks, 256, 0, s>>>((const T*)a, a_bstride, w, bias, C, pcm, pcm_base, tap, tap_bstride, g, rows_per_frame)));
