@@ -27,8 +27,8 @@ using namespace tc;
 
 constexpr int T2_BM = 128, T2_BK = 64, T2_MAX_NA = 8, T2_MAX_NW = 12, T2_MAX_BN = 256;
 constexpr uint32_t T2_CHUNK_BYTES = 128 * 32;            // one staged output chunk: 128 rows x 16 columns x 2 B
-constexpr uint32_t T2_STAGING_BYTES = 2 * 2 * 2 * T2_CHUNK_BYTES;   // 2 warp groups x 2 outputs x 2 buffers
-constexpr int T2_THREADS = 384, T2_EPI_WARPS = 8;
+constexpr uint32_t T2_STAGING_BYTES = 48 * 1024;   // generic: 2 groups x 2 outputs x 2 buffers x 4 KB; block mode: 12 warps x 2 outputs x 2 KB
+constexpr int T2_THREADS = 512, T2_EPI_WARPS = 8, T2_EPI_WARPS_BLOCK = 12;
 constexpr uint32_t T2_TMEM_COLS = 512;
 
 struct Tc2Params {
@@ -38,8 +38,11 @@ struct Tc2Params {
   int tiles_per_utt, n_tiles, m_tiles_total, cs; // cs = cluster size (1 or 2)
   uint32_t idesc, a_stage_bytes, a_tx_bytes, w_stage_bytes;
   int desc_mode;                                 // 1: base_offset 0, 2: base_offset = (addr >> 7) & 7
-  int na, nw;                                    // ring depths (A halo tiles, W tiles)
+  int na, nw;                                    // ring depths (A halo tiles, W stages)
+  int wg;                                        // taps per W stage: one barrier wait / commit per wg*nk MMAs
+  uint32_t w_tap_bytes;                          // bytes of one tap's weight tile in this CTA (BN/cs rows x 128 B)
   int tma_y, tma_a;                              // 16-bit outputs leave through smem staging + TMA store
+  int epi_block;                                 // 0: generic epilogue (8 warps); 1: specialised block epilogue (12 warps)
   const float* bias; int act;
   const void* res; int ldres; long long res_bstride;
   const float* scale;
@@ -52,6 +55,57 @@ struct Tc2Params {
 __device__ __forceinline__ void ld4(const float* p, float (&v)[16], int i) {
   const float4 t = __ldg((const float4*)p + i);
   v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+}
+
+
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+}
+
+// Specialised epilogue of the decoder blocks' GEMMs (transposed conv, conv7, conv1 -- ~95 % of the step's elements):
+//   v = acc + bias [+ res16];   y = v (16-bit, kY);   a = v + ib * sin^2(v * ea) (16-bit)
+// 12 warps (3 per TMEM lane quarter) take the tile's 32-column chunks round-robin.  Each WARP stages its own 32 rows
+// (64-byte rows, 64B swizzle) and issues its own TMA stores: no cross-warp barrier, no scattered global stores, and no
+// per-element branches (everything the generic epilogue decides at run time is a template parameter here).
+template <typename T16, bool kRes, bool kY>
+__device__ __forceinline__ void epi_block_chunk(const uint32_t (&r)[32], const float* __restrict__ bias, const float* __restrict__ ea,
+                                                const float* __restrict__ ib, const uint4 (&rres)[4], uint8_t* buf_y,
+                                                uint8_t* buf_a, int lane) {
+  const uint32_t sw = (uint32_t)((lane >> 1) & 3);   // SWIZZLE_64B: 16-byte chunk index ^= address bits [7,9)
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {   // 8 columns per step
+    float v[8];
+    const float4 b0 = __ldg((const float4*)(bias + 8 * c)), b1 = __ldg((const float4*)(bias + 8 * c + 4));
+    v[0] = __uint_as_float(r[8 * c + 0]) + b0.x; v[1] = __uint_as_float(r[8 * c + 1]) + b0.y;
+    v[2] = __uint_as_float(r[8 * c + 2]) + b0.z; v[3] = __uint_as_float(r[8 * c + 3]) + b0.w;
+    v[4] = __uint_as_float(r[8 * c + 4]) + b1.x; v[5] = __uint_as_float(r[8 * c + 5]) + b1.y;
+    v[6] = __uint_as_float(r[8 * c + 6]) + b1.z; v[7] = __uint_as_float(r[8 * c + 7]) + b1.w;
+    if (kRes) {
+      const uint4 u = rres[c];
+      const float2 r0 = Cvt<T16>::unpack(u.x), r1 = Cvt<T16>::unpack(u.y), r2 = Cvt<T16>::unpack(u.z), r3 = Cvt<T16>::unpack(u.w);
+      v[0] += r0.x; v[1] += r0.y; v[2] += r1.x; v[3] += r1.y; v[4] += r2.x; v[5] += r2.y; v[6] += r3.x; v[7] += r3.y;
+    }
+    if (kY)
+      *(uint4*)(buf_y + lane * 64 + ((c ^ sw) << 4)) = make_uint4(Cvt<T16>::pack(v[0], v[1]), Cvt<T16>::pack(v[2], v[3]),
+                                                                  Cvt<T16>::pack(v[4], v[5]), Cvt<T16>::pack(v[6], v[7]));
+    const float4 e0 = __ldg((const float4*)(ea + 8 * c)), e1 = __ldg((const float4*)(ea + 8 * c + 4));
+    const float4 i0 = __ldg((const float4*)(ib + 8 * c)), i1 = __ldg((const float4*)(ib + 8 * c + 4));
+    const float ee[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w}, ii[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float sn = __sinf(v[e] * ee[e]);
+      v[e] = fmaf(ii[e], sn * sn, v[e]);
+    }
+    *(uint4*)(buf_a + lane * 64 + ((c ^ sw) << 4)) = make_uint4(Cvt<T16>::pack(v[0], v[1]), Cvt<T16>::pack(v[2], v[3]),
+                                                                Cvt<T16>::pack(v[4], v[5]), Cvt<T16>::pack(v[6], v[7]));
+  }
 }
 
 // kPair: the two CTAs of the cluster form a cta_group::2 pair -- ONE tcgen05.mma spans both SMs (M = 256), each CTA
@@ -94,7 +148,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < T2_NA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < T2_NW; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], kPair ? 1u : (uint32_t)cs); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], kPair ? 2 * T2_EPI_WARPS : T2_EPI_WARPS); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], (uint32_t)((kPair ? 2 : 1) * (p.epi_block ? T2_EPI_WARPS_BLOCK : T2_EPI_WARPS))); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -161,16 +215,21 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             tma_load_3d(a_ring + (size_t)sa * p.a_stage_bytes, &map_a, &a_full[sa], cb * T2_BK, t0 - p.halo, b);
           }
           if (++sa == T2_NA) { sa = 0; pa ^= 1; }
-          for (int tap = 0; tap < p.taps; ++tap) {
+          for (int tap0 = 0; tap0 < p.taps; tap0 += p.wg) {
+            const int ntap = min(p.wg, p.taps - tap0);
             mbar_wait(&w_empty[sw], pw ^ 1);            // every CTA of the cluster has drained this slot
-            if (kPair) {   // this CTA's half of the weight tile (rows rank*BN/2 ..), at the SAME smem offset in both CTAs
-              if (rank == 0) mbar_expect_tx(&w_full[sw], (uint32_t)p.BN * 128u);
-              tma_load_2d_2sm(w_ring + (size_t)sw * p.w_stage_bytes, &map_w, &w_full[sw], cb * T2_BK, tap * p.N + n0 + (int)rank * wrows);
+            uint8_t* wst = w_ring + (size_t)sw * p.w_stage_bytes;
+            if (kPair) {   // this CTA's half of each weight tile (rows rank*BN/2 ..), at the SAME smem offsets in both CTAs
+              if (rank == 0) mbar_expect_tx(&w_full[sw], (uint32_t)ntap * (uint32_t)p.BN * 128u);
+              for (int j = 0; j < ntap; ++j)
+                tma_load_2d_2sm(wst + (size_t)j * p.w_tap_bytes, &map_w, &w_full[sw], cb * T2_BK, (tap0 + j) * p.N + n0 + (int)rank * wrows);
             } else {
-              mbar_expect_tx(&w_full[sw], (uint32_t)p.BN * 128u);
-              uint8_t* dst = w_ring + (size_t)sw * p.w_stage_bytes + (size_t)rank * wrows * 128;
-              if (cs == 1) tma_load_2d(dst, &map_w, &w_full[sw], cb * T2_BK, tap * p.N + n0);
-              else tma_load_2d_mc(dst, &map_w, &w_full[sw], cb * T2_BK, tap * p.N + n0 + (int)rank * wrows, mc_mask);
+              mbar_expect_tx(&w_full[sw], (uint32_t)ntap * (uint32_t)p.BN * 128u);
+              for (int j = 0; j < ntap; ++j) {
+                uint8_t* dst = wst + (size_t)j * p.w_tap_bytes + (size_t)rank * wrows * 128;
+                if (cs == 1) tma_load_2d(dst, &map_w, &w_full[sw], cb * T2_BK, (tap0 + j) * p.N + n0);
+                else tma_load_2d_mc(dst, &map_w, &w_full[sw], cb * T2_BK, (tap0 + j) * p.N + n0 + (int)rank * wrows, mc_mask);
+              }
             }
             if (++sw == T2_NW) { sw = 0; pw ^= 1; }
           }
@@ -195,15 +254,19 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
           tc_fence_after();
           const uint32_t a_base = smem_u32(a_ring + (size_t)sa * p.a_stage_bytes);
           const int nk = min(T2_BK, p.Cin - cb * T2_BK) / 16;
-          for (int tap = 0; tap < p.taps; ++tap) {
+          for (int tap0 = 0; tap0 < p.taps; tap0 += p.wg) {
+            const int ntap = min(p.wg, p.taps - tap0);
             mbar_wait(&w_full[sw], pw);
             tc_fence_after();
-            const uint32_t a_tap = a_base + (uint32_t)(tap * p.dil) * 128u;   // row-shifted view of the halo tile
             const uint32_t w_base = smem_u32(w_ring + (size_t)sw * p.w_stage_bytes);
-            for (int k = 0; k < nk; ++k) {
-              if (kPair) tc_mma_f16_2sm(d_tmem, make_smem_desc_shifted(a_tap + 32u * k, false), make_smem_desc(w_base + 32u * k), p.idesc, accumulate);
-              else tc_mma_f16(d_tmem, make_smem_desc_shifted(a_tap + 32u * k, p.desc_mode == 2), make_smem_desc(w_base + 32u * k), p.idesc, accumulate);
-              accumulate = 1;
+            for (int j = 0; j < ntap; ++j) {
+              const uint32_t a_tap = a_base + (uint32_t)((tap0 + j) * p.dil) * 128u;   // row-shifted view of the halo tile
+              const uint32_t w_tap = w_base + (uint32_t)j * p.w_tap_bytes;
+              for (int k = 0; k < nk; ++k) {
+                if (kPair) tc_mma_f16_2sm(d_tmem, make_smem_desc_shifted(a_tap + 32u * k, false), make_smem_desc(w_tap + 32u * k), p.idesc, accumulate);
+                else tc_mma_f16(d_tmem, make_smem_desc_shifted(a_tap + 32u * k, p.desc_mode == 2), make_smem_desc(w_tap + 32u * k), p.idesc, accumulate);
+                accumulate = 1;
+              }
             }
             if (kPair) tc_commit_2sm(&w_empty[sw], mc_mask);
             else if (cs == 1) tc_commit(&w_empty[sw]); else tc_commit_mc(&w_empty[sw], mc_mask);
@@ -216,7 +279,65 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         if (++acc == 2) { acc = 0; pacc ^= 1; }
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && p.epi_block) {
+    // ================= specialised block epilogue (12 warps) =================
+    const int ew = warp - 4, quarter = warp & 3, grp = ew >> 2;          // grp 0..2 takes chunks grp, grp+3, ...
+    const int nch = p.BN / 32;
+    uint8_t* buf_y = staging + (size_t)ew * 4096;                         // this warp's 32 rows x 64 B, y then a
+    uint8_t* buf_a = buf_y + 2048;
+    const bool has_res = p.res != nullptr, has_y = p.out_y != nullptr;
+    const int slot_rows = p.Tmax * p.rows_per_frame;
+    int acc = 0;
+    uint32_t pacc = 0;
+    for (int item = cid; item < items; item += ncl) {
+      int b, t0, n0; bool mine;
+      if (!coords(item, b, t0, n0, mine)) continue;
+      const int t = min(t0 + quarter * 32 + lane, slot_rows - 1);         // clamp: rows past the slot are clipped by the TMA store
+      const T16* res_row = (has_res && mine) ? (const T16*)p.res + (long long)b * p.res_bstride + (long long)t * p.ldres + n0 : nullptr;
+      uint4 rres[4] = {};
+      if (res_row && grp < nch) {   // residual of my first chunk: in flight while the MMAs of this tile finish
+#pragma unroll
+        for (int c = 0; c < 4; ++c) rres[c] = __ldg((const uint4*)(res_row + grp * 32 + 8 * c));
+      }
+      mbar_wait(&tmem_full[acc], pacc);
+      tc_fence_after();
+      if (mine) {
+        for (int ch = grp; ch < nch; ch += 3) {
+          uint32_t r[32];
+          tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * T2_MAX_BN + ch * 32), r);
+          if (has_res && ch != grp) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) rres[c] = __ldg((const uint4*)(res_row + ch * 32 + 8 * c));
+          }
+          tc_wait_ld();
+          if (lane == 0) tma_store_wait_read0();                          // my previous stores have drained the staging rows
+          __syncwarp();
+          const int n = n0 + ch * 32;
+          if (has_res) {
+            if (has_y) epi_block_chunk<T16, true, true>(r, p.bias + n, p.snake_ea + n, p.snake_ib + n, rres, buf_y, buf_a, lane);
+            else epi_block_chunk<T16, true, false>(r, p.bias + n, p.snake_ea + n, p.snake_ib + n, rres, buf_y, buf_a, lane);
+          } else {
+            if (has_y) epi_block_chunk<T16, false, true>(r, p.bias + n, p.snake_ea + n, p.snake_ib + n, rres, buf_y, buf_a, lane);
+            else epi_block_chunk<T16, false, false>(r, p.bias + n, p.snake_ea + n, p.snake_ib + n, rres, buf_y, buf_a, lane);
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (has_y) tma_store_3d(&map_y, buf_y, n, t0 + quarter * 32, b);
+            tma_store_3d(&map_o, buf_a, n, t0 + quarter * 32, b);
+            tma_store_commit();
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (kPair && rank != 0) mbar_arrive_cluster(&tmem_empty[acc], 0); else mbar_arrive(&tmem_empty[acc]);
+      }
+      if (++acc == 2) { acc = 0; pacc ^= 1; }
+    }
+    if (lane == 0) tma_store_wait_all();
+  } else if (warp >= 4 && warp < 12) {
     // ================= epilogue =================
     // Two groups of four warps (one warp per TMEM lane quarter) split the tile's 16-column chunks.  16-bit outputs
     // are written to a 128B-per-4-rows swizzled staging chunk in smem and leave through ONE TMA store per chunk and
@@ -387,10 +508,19 @@ EncodeTiledFn encode_fn2() {
   });
   return fn;
 }
-int pick_bn2(int N) {
+int pick_bn2(int N, bool prefer32 = false) {
+  if (prefer32)
+    for (int bn = T2_MAX_BN; bn >= 64; bn -= 32)
+      if (N % bn == 0) return bn;
   for (int bn = T2_MAX_BN; bn >= 16; bn -= 16)
     if (N % bn == 0) return bn;
   return 0;
+}
+// The specialised block epilogue: bias + [16-bit residual] + [16-bit stream out] + SnakeBeta operand out, nothing else.
+bool block_epilogue_ok(const ConvGemmParams& p, int y_dtype) {
+  return p.out_a && p.snake_ea && p.bias && p.act == ACT_NONE && !p.out_tap && !p.scale &&
+         (!p.res || (p.out_y && p.res == p.out_y)) && (!p.out_y || y_dtype != DT_F32) && pick_bn2(p.N, true) % 32 == 0 &&
+         pick_bn2(p.N, true) >= 64;
 }
 int env_int(const char* name, int dflt) {
   const char* e = getenv(name);
@@ -419,10 +549,13 @@ cudaError_t launch_conv_gemm_tc2(const ConvGemmParams& p, const BatchGeom& g, in
   if (!enc) return cudaErrorNotSupported;
   static const int cs_env = env_int("Q3TTS_TC_CLUSTER", 2);
   static const int pair_env = env_int("Q3TTS_TC_PAIR", 1);
-  const int BN = pick_bn2(p.N);
+  static const int block_env = env_int("Q3TTS_TC_BLOCK_EPI", 1);
+  const bool epi_block = block_env && block_epilogue_ok(p, y_dtype);
+  const int BN = pick_bn2(p.N, epi_block);
   const int slot_rows = g.Tmax * p.rows_per_frame;
   const int halo = (p.taps - 1) * p.dil;
   Tc2Params q{};
+  q.epi_block = epi_block;
   q.B = g.B; q.Tmax = g.Tmax; q.rows_per_frame = p.rows_per_frame; q.len_frames = g.len_frames;
   q.N = p.N; q.BN = BN; q.Cin = p.Cin; q.taps = p.taps; q.dil = p.dil; q.ncb = (p.Cin + T2_BK - 1) / T2_BK; q.halo = halo;
   q.tiles_per_utt = (slot_rows + T2_BM - 1) / T2_BM;
@@ -455,7 +588,15 @@ cudaError_t launch_conv_gemm_tc2(const ConvGemmParams& p, const BatchGeom& g, in
   q.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((pair ? 2 * T2_BM : T2_BM) >> 4) << 24);
   q.a_tx_bytes = (uint32_t)(T2_BM + halo) * 128u;
   q.a_stage_bytes = (q.a_tx_bytes + 1023u) & ~1023u;
-  q.w_stage_bytes = (uint32_t)(pair ? BN / 2 : BN) * 128u;   // pair mode: each CTA stages half of the weight tile
+  q.w_tap_bytes = (uint32_t)(pair ? BN / 2 : BN) * 128u;     // pair mode: each CTA stages half of the weight tile
+  {  // several taps share one W stage when the tiles are small: the single MMA thread then waits / commits once per
+     // wg*nk MMAs instead of once per nk (its per-stage overhead was what kept the tensor pipe at 30 % for N = 96)
+    static const int wg_env = env_int("Q3TTS_TC_WG_KB", 40);
+    const int wg_max = std::max(1, (wg_env * 1024) / (int)q.w_tap_bytes);
+    const int ngroups = (p.taps + wg_max - 1) / wg_max;
+    q.wg = (p.taps + ngroups - 1) / ngroups;
+  }
+  q.w_stage_bytes = q.w_tap_bytes * (uint32_t)q.wg;
   q.desc_mode = tc2_mode();
   q.bias = p.bias; q.act = p.act;
   q.res = p.res; q.ldres = p.ldres; q.res_bstride = p.res_bstride; q.scale = p.scale;
@@ -472,9 +613,11 @@ cudaError_t launch_conv_gemm_tc2(const ConvGemmParams& p, const BatchGeom& g, in
   auto out_map = [&](CUtensorMap* m, void* base, int ld, long long bstride) -> bool {
     cuuint64_t dims[3] = {(cuuint64_t)ld, (cuuint64_t)slot_rows, (cuuint64_t)g.B};
     cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)bstride * 2};
-    cuuint32_t box[3] = {16, T2_BM, 1};
+    cuuint32_t box[3] = {16, T2_BM, 1};                       // generic: one 16-column chunk of the whole tile
+    if (epi_block) { box[0] = 32; box[1] = 32; }               // block mode: one warp's 32 rows x 32 columns
     cuuint32_t es[3] = {1, 1, 1};
-    return enc(m, dt, 3, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B,
+    return enc(m, dt, 3, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               epi_block ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
                CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
   };
   if (q.tma_y && !out_map(&map_y, p.out_y, p.ldy, p.y_bstride)) return cudaErrorInvalidValue;
@@ -484,7 +627,7 @@ cudaError_t launch_conv_gemm_tc2(const ConvGemmParams& p, const BatchGeom& g, in
   // Little's law: bytes in flight must cover HBM/L2 latency, so the budget is split between the two rings in
   // proportion to what a tile consumes from each (a 1x1 conv streams mostly A, a k=7 conv mostly W).
   {
-    const double a_tile = (double)q.ncb * q.a_stage_bytes, w_tile = (double)q.ncb * q.taps * q.w_stage_bytes;
+    const double a_tile = (double)q.ncb * q.a_stage_bytes, w_tile = (double)q.ncb * q.taps * q.w_tap_bytes;
     int na = (int)((double)budget * a_tile / (a_tile + w_tile) / q.a_stage_bytes + 0.5);
     na = std::max(2, std::min(T2_MAX_NA, na));
     while (na > 2 && (size_t)na * q.a_stage_bytes + 3 * (size_t)q.w_stage_bytes > budget) --na;
