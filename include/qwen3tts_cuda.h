@@ -51,7 +51,7 @@ typedef struct q3tts_options {
   int32_t device;             /* CUDA device ordinal; -1 = current device                      */
   int32_t precision;          /* Q3TTS_PREC_*                                                  */
   int32_t attn_mode;          /* Q3TTS_ATTN_*                                                  */
-  uint64_t workspace_bytes;   /* activation workspace cap per model; 0 = default (24 GiB)      */
+  uint64_t workspace_bytes;   /* activation workspace cap; 0 = min(64 GiB, 45 % of free HBM)   */
   int32_t max_frames_per_launch; /* micro-batch cap in codec frames; 0 = derive from workspace */
   int32_t reserved;
 } q3tts_options;
@@ -180,6 +180,15 @@ int q3tts_profile_enable(q3tts_model* m, int32_t enable);
 int q3tts_profile_get(q3tts_model* m, q3tts_stage_time* out, int32_t cap);
 /* Kernels launched by this model since load (all decodes).                                      */
 int64_t q3tts_launch_count(const q3tts_model* m);
+
+/* ---- kernel-level test hook (no reference counterpart) ------------------------------------------
+ * One multi-tap GEMM (the op behind every conv / linear / transposed conv, ST.swift:293-305, 339-353)
+ * on seeded random data: the tcgen05 kernel against the CUDA-core kernel of the same op, then
+ * `iters` timed launches.  mode 0 conv7-like, 1 conv1-like (in-place residual), 2 transposed-conv-like,
+ * 3 plain.  Outputs: mean ms per launch, max |tc - simt| of the stream and operand outputs.       */
+int q3tts_debug_conv_gemm(int32_t B, int32_t rows, int32_t Cin, int32_t N, int32_t taps, int32_t dil,
+                          int32_t mode, int32_t precision, int32_t iters, float* ms_out,
+                          float* max_diff_y, float* max_diff_a);
 
 #ifdef __cplusplus
 }

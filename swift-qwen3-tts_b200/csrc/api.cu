@@ -55,7 +55,7 @@ struct Utt { int64_t code_base, pcm_base; int frames, orig; };
 
 int64_t frames_cap(const Model& m) {
   const size_t per = (plan_bytes(m, 1, 256) + 255) / 256;
-  uint64_t ws = m.opts.workspace_bytes ? m.opts.workspace_bytes : (24ull << 30);
+  uint64_t ws = m.opts.workspace_bytes ? m.opts.workspace_bytes : m.default_workspace;
   int64_t cap = (int64_t)(ws / per);
   if (m.opts.max_frames_per_launch > 0) cap = std::min<int64_t>(cap, m.opts.max_frames_per_launch);
   return std::max<int64_t>(cap, 1);
@@ -440,6 +440,118 @@ int q3tts_write_wav(const char* path, const float* pcm, int64_t n, int32_t rate)
   const size_t wrote = std::fwrite(buf.data(), 2, (size_t)n, f);
   std::fclose(f);
   return wrote == (size_t)n ? Q3TTS_OK : fail(Q3TTS_EIO, "short write");
+}
+
+
+// ---- kernel-level test / micro-benchmark hook -----------------------------------------------------------------------
+// One multi-tap GEMM on seeded random data: the tcgen05 path against the CUDA-core 16-bit path of the same op, then
+// `iters` timed launches (CUDA events).  mode 0: conv7-like (bias, SnakeBeta operand out); 1: conv1-like (bias,
+// in-place 16-bit residual stream, SnakeBeta operand out); 2: transposed-conv-like (bias, stream out, SnakeBeta operand
+// out); 3: plain (bias, operand out).  Utterance b has rows - 37*b valid rows (ragged tiles).
+int q3tts_debug_conv_gemm(int32_t B, int32_t rows, int32_t Cin, int32_t N, int32_t taps, int32_t dil, int32_t mode,
+                          int32_t precision, int32_t iters, float* ms_out, float* max_diff_y, float* max_diff_a) {
+  return guarded([&]() {
+    if (B < 1 || rows < 1 || Cin < 16 || N < 16 || taps < 1 || dil < 1 || mode < 0 || mode > 3) return fail(Q3TTS_EINVAL, "bad GEMM shape");
+    const int op = precision == Q3TTS_PREC_BF16 ? DT_BF16 : DT_F16;
+    cudaStream_t s = nullptr;
+    CUDA_OK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    std::vector<void*> allocs;
+    auto dmalloc = [&](size_t bytes) { void* d = nullptr; CUDA_OK(cudaMalloc(&d, bytes)); allocs.push_back(d); return d; };
+    uint64_t seed = 0x9E3779B97F4A7C15ull ^ ((uint64_t)Cin << 32) ^ (uint64_t)N ^ ((uint64_t)taps << 20);
+    auto rnd = [&]() { seed = seed * 6364136223846793005ull + 1442695040888963407ull; return (float)((seed >> 40) & 0xFFFFFF) / 8388608.0f - 1.0f; };
+    auto upload16 = [&](size_t n, float scale) {
+      std::vector<float> h(n);
+      for (auto& v : h) v = rnd() * scale;
+      float* d32 = (float*)dmalloc(n * 4);
+      void* d16 = dmalloc(n * 2);
+      CUDA_OK(cudaMemcpyAsync(d32, h.data(), n * 4, cudaMemcpyHostToDevice, s));
+      CUDA_OK(cudaStreamSynchronize(s));
+      launch_convert(d32, d16, op, (int64_t)n, s);
+      return d16;
+    };
+    auto upload32 = [&](size_t n, float scale, float offset) {
+      std::vector<float> h(n);
+      for (auto& v : h) v = offset + rnd() * scale;
+      float* d = (float*)dmalloc(n * 4);
+      CUDA_OK(cudaMemcpyAsync(d, h.data(), n * 4, cudaMemcpyHostToDevice, s));
+      CUDA_OK(cudaStreamSynchronize(s));
+      return d;
+    };
+    const size_t R = (size_t)B * rows;
+    void* A = upload16(R * Cin, 1.0f);
+    void* W = upload16((size_t)taps * N * Cin, 1.0f / sqrtf((float)(taps * Cin)));
+    void* X = upload16(R * N, 1.0f);
+    float* bias = upload32((size_t)N, 0.1f, 0.f);
+    float* ea = upload32((size_t)N, 0.3f, 1.0f);
+    float* ib = upload32((size_t)N, 0.3f, 1.0f);
+    std::vector<int> len((size_t)B);
+    for (int b = 0; b < B; ++b) len[(size_t)b] = std::max(1, rows - 37 * b);
+    int* d_len = (int*)dmalloc((size_t)B * 4);
+    CUDA_OK(cudaMemcpyAsync(d_len, len.data(), (size_t)B * 4, cudaMemcpyHostToDevice, s));
+    void* y[2] = {dmalloc(R * N * 2), dmalloc(R * N * 2)};
+    void* a[2] = {dmalloc(R * N * 2), dmalloc(R * N * 2)};
+    BatchGeom g{B, rows, d_len};
+    auto params = [&](int which) {
+      ConvGemmParams p{};
+      p.A = A; p.lda = Cin; p.a_bstride = (int64_t)rows * Cin;
+      p.W = W; p.rows_per_frame = 1; p.N = N; p.Cin = Cin; p.taps = taps; p.dil = dil;
+      p.bias = bias; p.act = ACT_NONE;
+      p.out_a = a[which]; p.lda_out = N; p.ao_bstride = (int64_t)rows * N;
+      if (mode != 3) { p.snake_ea = ea; p.snake_ib = ib; }
+      if (mode == 1 || mode == 2) { p.out_y = y[which]; p.ldy = N; p.y_bstride = (int64_t)rows * N; }
+      if (mode == 1) { p.res = y[which]; p.ldres = N; p.res_bstride = (int64_t)rows * N; }
+      return p;
+    };
+    for (int w = 0; w < 2; ++w) {
+      CUDA_OK(cudaMemcpyAsync(y[w], X, R * N * 2, cudaMemcpyDeviceToDevice, s));
+      CUDA_OK(cudaMemsetAsync(a[w], 0, R * N * 2, s));
+    }
+    ConvGemmParams p0 = params(0), p1 = params(1);
+    launch_conv_gemm_simt(p0, g, op, op, s);
+    if (!tc2_supported(p1, op)) return fail(Q3TTS_EINVAL, "shape not supported by the tcgen05 GEMM");
+    CUDA_OK(launch_conv_gemm_tc2(p1, g, op, op, s));
+    CUDA_OK(cudaStreamSynchronize(s));
+    auto max_diff = [&](void* d0, void* d1) {
+      std::vector<uint16_t> h0(R * N), h1(R * N);
+      CUDA_OK(cudaMemcpy(h0.data(), d0, R * N * 2, cudaMemcpyDeviceToHost));
+      CUDA_OK(cudaMemcpy(h1.data(), d1, R * N * 2, cudaMemcpyDeviceToHost));
+      auto tof = [&](uint16_t u) {
+        if (op == DT_BF16) { uint32_t v = (uint32_t)u << 16; float f; std::memcpy(&f, &v, 4); return f; }
+        const uint32_t sgn = (u >> 15) & 1, e = (u >> 10) & 31, m = u & 1023;
+        float f = e == 0 ? ldexpf((float)m, -24) : (e == 31 ? INFINITY : ldexpf((float)(m | 1024), (int)e - 25));
+        return sgn ? -f : f;
+      };
+      float worst = 0.f;
+      for (int b = 0; b < B; ++b)
+        for (int t = 0; t < len[(size_t)b]; ++t)
+          for (int n = 0; n < N; ++n) {
+            const size_t i = ((size_t)b * rows + t) * N + n;
+            const float d = fabsf(tof(h0[i]) - tof(h1[i]));
+            if (!(d <= worst)) worst = d;   // NaN-propagating
+          }
+      return worst;
+    };
+    if (max_diff_a) *max_diff_a = max_diff(a[0], a[1]);
+    if (max_diff_y) *max_diff_y = (mode == 1 || mode == 2) ? max_diff(y[0], y[1]) : 0.f;
+    if (iters > 0 && ms_out) {
+      cudaEvent_t e0, e1;
+      CUDA_OK(cudaEventCreate(&e0));
+      CUDA_OK(cudaEventCreate(&e1));
+      for (int i = 0; i < 2; ++i) CUDA_OK(launch_conv_gemm_tc2(p1, g, op, op, s));
+      CUDA_OK(cudaEventRecord(e0, s));
+      for (int i = 0; i < iters; ++i) CUDA_OK(launch_conv_gemm_tc2(p1, g, op, op, s));
+      CUDA_OK(cudaEventRecord(e1, s));
+      CUDA_OK(cudaStreamSynchronize(s));
+      float ms = 0;
+      CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+      *ms_out = ms / iters;
+      cudaEventDestroy(e0);
+      cudaEventDestroy(e1);
+    }
+    for (void* d : allocs) cudaFree(d);
+    cudaStreamDestroy(s);
+    return (int)Q3TTS_OK;
+  });
 }
 
 // ---- measurement --------------------------------------------------------------------------------------------

@@ -253,6 +253,11 @@ Model* model_create(const Checkpoint& ck, const q3tts_options& opts) {
     m.tail_w = upload(m, w.data);
     m.tail_bias = T(ck, dd + "outConv.conv.bias").data[0];
   }
+  {  // default activation budget: 64 GiB (a batch of 64 x 30 s in one launch chain) or 45 % of what is free now
+    size_t free_b = 0, total_b = 0;
+    CUDA_OK(cudaMemGetInfo(&free_b, &total_b));
+    m.default_workspace = std::max<uint64_t>(1ull << 30, std::min<uint64_t>(64ull << 30, (uint64_t)(free_b * 0.45)));
+  }
   CUDA_OK(cudaMalloc(&m.d_err, sizeof(int)));
   CUDA_OK(cudaMemset(m.d_err, 0, sizeof(int)));
   CUDA_OK(cudaMallocHost(&m.h_err, sizeof(int)));

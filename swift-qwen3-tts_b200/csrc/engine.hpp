@@ -80,6 +80,7 @@ struct Model {
   // workspace
   char* arena = nullptr;
   size_t arena_cap = 0;
+  uint64_t default_workspace = 24ull << 30;   // activation budget when q3tts_options.workspace_bytes == 0 (set at load)
   int32_t* d_codes = nullptr; size_t d_codes_cap = 0;
   float* d_pcm = nullptr;     size_t d_pcm_cap = 0;
   int32_t* d_lengths = nullptr; size_t d_lengths_cap = 0;

@@ -1,15 +1,23 @@
-// tcgen05 multi-tap GEMM, second generation: HALO tiles + cluster-multicast weights.
+// tcgen05 multi-tap GEMM, second generation: HALO tiles + CTA-pair MMA + lean issue loops.
 //
 // v1 (kernels_tc.cu) re-reads the activation tile once per tap and the weight tile once per 128-row tile; ncu showed
 // block3's conv7 moving 18 GB L2->SM for 1.1 GB of input (profiles/r1_v1_*).  Here:
 //  * the A operand of ALL taps of a 64-channel block comes from ONE TMA box of 128 + (taps-1)*dil rows (the halo
 //    tile).  Tap j is the same smem tile viewed from row j*dil: its UMMA descriptor simply starts j*dil*128 bytes
 //    later (the 128B swizzle is a function of the absolute smem address, which TMA and the MMA unit share);
-//  * the CTAs of a cluster work on consecutive M tiles of the same N tile; each loads 1/cs of every weight tile and
-//    TMA-multicasts it to the whole cluster, so L2 reads of W drop by the cluster size;
+//  * the two CTAs of a cluster form a cta_group::2 pair on consecutive M tiles of the same N tile: ONE tcgen05.mma
+//    spans both SMs (M = 256), each CTA stages its own rows of A and HALF of the weight tile;
+//  * weights that fit stay RESIDENT in smem for the whole kernel (block 3's convs, block 2's 1x1): every stage of the
+//    weight ring is then loaded exactly once instead of once per tile, which takes ~2/3 of the L2->SM traffic away;
+//  * the producer and MMA warps run WARP-UNIFORM loops (tile validity goes through a vote, so ptxas keeps descriptors,
+//    coordinates and barrier addresses in uniform registers) and elect one lane only around the TMA / MMA / commit
+//    instructions.  The first version wrapped the loops in `if (lane == 0)`: every tcgen05.mma was then preceded by a
+//    VOTEU/ELECT/5xR2UR.BROADCAST/BRA.U.ANY uniformisation loop and the tensor pipe idled 84 % of the time on N = 96;
 //  * partial K blocks (Cin % 64 != 0, e.g. 96) issue only the k-steps that hold data instead of multiplying zeros;
-//  * the epilogue prefetches its 16-bit residual rows while the MMAs of the tile are still running.
-// Roles, rings and the fused epilogue are otherwise those of v1.
+//  * small-N GEMMs (BN <= 128) use a 4-deep TMEM accumulator ring instead of 2, so the epilogue may lag three tiles;
+//  * two epilogues, compiled as separate kernels: the BLOCK epilogue (bias [+ residual] [+ stream out] + SnakeBeta
+//    operand out, all 16-bit; 12 warps, per-warp TMA stores, per-column constants staged in smem) used by the decoder
+//    blocks, and the GENERIC one (GELU / SwiGLU / layer scale / fp32 streams / taps; 8 warps).
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -25,11 +33,12 @@ namespace q3 {
 namespace {
 using namespace tc;
 
-constexpr int T2_BM = 128, T2_BK = 64, T2_MAX_NA = 8, T2_MAX_NW = 12, T2_MAX_BN = 256;
-constexpr uint32_t T2_CHUNK_BYTES = 128 * 32;            // one staged output chunk: 128 rows x 16 columns x 2 B
-constexpr uint32_t T2_STAGING_BYTES = 48 * 1024;   // generic: 2 groups x 2 outputs x 2 buffers x 4 KB; block mode: 12 warps x 2 outputs x 2 KB
-constexpr int T2_THREADS = 512, T2_EPI_WARPS = 8, T2_EPI_WARPS_BLOCK = 12;
+constexpr int T2_BM = 128, T2_BK = 64, T2_MAX_NA = 8, T2_MAX_NW = 16, T2_MAX_ACC = 4;
+constexpr uint32_t T2_CHUNK_BYTES = 128 * 32;            // generic epilogue: one staged chunk = 128 rows x 16 columns x 2 B
+constexpr uint32_t T2_STAGING_BYTES = 32 * 1024;         // generic epilogue: 2 groups x 2 outputs x 2 buffers x 4 KB
+constexpr int T2_THREADS_GENERIC = 384, T2_THREADS_BLOCK = 512, T2_EPI_WARPS = 8, T2_EPI_WARPS_BLOCK = 12;
 constexpr uint32_t T2_TMEM_COLS = 512;
+constexpr int T2_CST_MAX_N = 768;                        // per-column constants (bias, snake) staged in smem up to this N
 
 struct Tc2Params {
   int B, Tmax, rows_per_frame;
@@ -39,10 +48,15 @@ struct Tc2Params {
   uint32_t idesc, a_stage_bytes, a_tx_bytes, w_stage_bytes;
   int desc_mode;                                 // 1: base_offset 0, 2: base_offset = (addr >> 7) & 7
   int na, nw;                                    // ring depths (A halo tiles, W stages)
-  int wg;                                        // taps per W stage: one barrier wait / commit per wg*nk MMAs
+  int wg, ngroups;                               // taps per W stage; W stages per 64-channel block
   uint32_t w_tap_bytes;                          // bytes of one tap's weight tile in this CTA (BN/cs rows x 128 B)
+  int w_resident;                                // every W stage of the kernel has its own slot: loaded once
+  int nacc, acc_stride;                          // TMEM accumulator ring: depth (2 or 4) and column stride
+  int nmma;                                      // MMA issuer warps (1 or 2)
+  int cst_staged;                                // bias / snake constants of all N columns live in smem
   int tma_y, tma_a;                              // 16-bit outputs leave through smem staging + TMA store
-  int epi_block;                                 // 0: generic epilogue (8 warps); 1: specialised block epilogue (12 warps)
+  uint32_t staging_bytes;                        // smem reserved for the output staging buffers
+  uint32_t div_nt_m, div_nt_s, div_tpu_m, div_tpu_s;   // magic numbers: x / n_tiles, x / tiles_per_utt (x < 2^31)
   const float* bias; int act;
   const void* res; int ldres; long long res_bstride;
   const float* scale;
@@ -57,7 +71,6 @@ __device__ __forceinline__ void ld4(const float* p, float (&v)[16], int i) {
   v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
 }
 
-
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -69,20 +82,30 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr) : "memory");
 }
 
-// Specialised epilogue of the decoder blocks' GEMMs (transposed conv, conv7, conv1 -- ~95 % of the step's elements):
+// Four per-column constants: from smem (32-bit shared address, LDS.128) or from global memory (read-only path).
+template <bool kSmem>
+__device__ __forceinline__ float4 ldc4(const float* gptr, uint32_t saddr, int off) {
+  if (kSmem) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr + 4u * (uint32_t)off));
+    return v;
+  }
+  return __ldg((const float4*)(gptr + off));
+}
+
+// Block epilogue, one 32-row x 32-column chunk of one warp:
 //   v = acc + bias [+ res16];   y = v (16-bit, kY);   a = v + ib * sin^2(v * ea) (16-bit)
-// 12 warps (3 per TMEM lane quarter) take the tile's 32-column chunks round-robin.  Each WARP stages its own 32 rows
-// (64-byte rows, 64B swizzle) and issues its own TMA stores: no cross-warp barrier, no scattered global stores, and no
-// per-element branches (everything the generic epilogue decides at run time is a template parameter here).
-template <typename T16, bool kRes, bool kY>
-__device__ __forceinline__ void epi_block_chunk(const uint32_t (&r)[32], const float* __restrict__ bias, const float* __restrict__ ea,
-                                                const float* __restrict__ ib, const uint4 (&rres)[4], uint8_t* buf_y,
-                                                uint8_t* buf_a, int lane) {
+// Each WARP stages its own 32 rows (64-byte rows, 64B swizzle) and issues its own TMA stores: no cross-warp barrier, no
+// scattered global stores, and no per-element branches.  bias / ea / ib point into smem (staged) or global memory.
+template <typename T16, bool kRes, bool kY, bool kSmem>
+__device__ __forceinline__ void epi_block_chunk(const uint32_t (&r)[32], const float* bias, const float* ea, const float* ib,
+                                                uint32_t s_bias, uint32_t s_ea, uint32_t s_ib,
+                                                const uint4 (&rres)[4], uint8_t* buf_y, uint8_t* buf_a, int lane) {
   const uint32_t sw = (uint32_t)((lane >> 1) & 3);   // SWIZZLE_64B: 16-byte chunk index ^= address bits [7,9)
 #pragma unroll
   for (int c = 0; c < 4; ++c) {   // 8 columns per step
     float v[8];
-    const float4 b0 = __ldg((const float4*)(bias + 8 * c)), b1 = __ldg((const float4*)(bias + 8 * c + 4));
+    const float4 b0 = ldc4<kSmem>(bias, s_bias, 8 * c), b1 = ldc4<kSmem>(bias, s_bias, 8 * c + 4);
     v[0] = __uint_as_float(r[8 * c + 0]) + b0.x; v[1] = __uint_as_float(r[8 * c + 1]) + b0.y;
     v[2] = __uint_as_float(r[8 * c + 2]) + b0.z; v[3] = __uint_as_float(r[8 * c + 3]) + b0.w;
     v[4] = __uint_as_float(r[8 * c + 4]) + b1.x; v[5] = __uint_as_float(r[8 * c + 5]) + b1.y;
@@ -95,8 +118,8 @@ __device__ __forceinline__ void epi_block_chunk(const uint32_t (&r)[32], const f
     if (kY)
       *(uint4*)(buf_y + lane * 64 + ((c ^ sw) << 4)) = make_uint4(Cvt<T16>::pack(v[0], v[1]), Cvt<T16>::pack(v[2], v[3]),
                                                                   Cvt<T16>::pack(v[4], v[5]), Cvt<T16>::pack(v[6], v[7]));
-    const float4 e0 = __ldg((const float4*)(ea + 8 * c)), e1 = __ldg((const float4*)(ea + 8 * c + 4));
-    const float4 i0 = __ldg((const float4*)(ib + 8 * c)), i1 = __ldg((const float4*)(ib + 8 * c + 4));
+    const float4 e0 = ldc4<kSmem>(ea, s_ea, 8 * c), e1 = ldc4<kSmem>(ea, s_ea, 8 * c + 4);
+    const float4 i0 = ldc4<kSmem>(ib, s_ib, 8 * c), i1 = ldc4<kSmem>(ib, s_ib, 8 * c + 4);
     const float ee[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w}, ii[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -108,11 +131,28 @@ __device__ __forceinline__ void epi_block_chunk(const uint32_t (&r)[32], const f
   }
 }
 
+// `ntap` taps x NK k-steps of one W stage.  Descriptors advance by 2 (32 bytes) per k-step and by dA / dW per tap;
+// only the very first MMA of a tile runs with accumulate = 0.
+template <bool kPair, int NK>
+__device__ __forceinline__ void issue_taps(uint32_t d_tmem, uint64_t ad, uint64_t wd, uint64_t dA, uint64_t dW, uint32_t idesc,
+                                           uint32_t first, int ntap) {
+#pragma unroll 1
+  for (int j = 0; j < ntap; ++j) {
+#pragma unroll
+    for (int k = 0; k < NK; ++k) {
+      const uint32_t accumulate = k == 0 ? (first | (uint32_t)j) : 1u;
+      if (kPair) tc_mma_f16_2sm(d_tmem, ad + 2 * k, wd + 2 * k, idesc, accumulate);
+      else tc_mma_f16(d_tmem, ad + 2 * k, wd + 2 * k, idesc, accumulate);
+    }
+    ad += dA; wd += dW;
+  }
+}
+
 // kPair: the two CTAs of the cluster form a cta_group::2 pair -- ONE tcgen05.mma spans both SMs (M = 256), each CTA
 // stages its own 128(+halo) rows of A and HALF of the weight tile, so weight ingest and B-operand smem reads per SM
 // halve.  Only the leader (rank 0) issues MMAs; both CTAs run producers and epilogues (each on its own TMEM half).
-template <typename T16, bool kPair>
-__global__ void __launch_bounds__(T2_THREADS, 1)
+template <typename T16, bool kPair, bool kBlockEpi>
+__global__ void __launch_bounds__(kBlockEpi ? T2_THREADS_BLOCK : T2_THREADS_GENERIC, 1)
 conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                      const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_o, Tc2Params p,
                      int y_is_f32) {
@@ -122,14 +162,15 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   const int T2_NA = p.na, T2_NW = p.nw;
   uint8_t* w_ring = smem + (size_t)T2_NA * p.a_stage_bytes;
   uint8_t* staging = w_ring + (size_t)T2_NW * p.w_stage_bytes;          // 1024-aligned (all stage sizes are)
-  uint64_t* bars = (uint64_t*)(staging + ((p.tma_y | p.tma_a) ? T2_STAGING_BYTES : 0));
+  float* cst = (float*)(staging + p.staging_bytes);   // [bias | ea | ib] x N when staged
+  uint64_t* bars = (uint64_t*)((uint8_t*)cst + (p.cst_staged ? (size_t)3 * p.N * 4 : 0));
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + T2_MAX_NA;
   uint64_t* w_full = a_empty + T2_MAX_NA;
   uint64_t* w_empty = w_full + T2_MAX_NW;
   uint64_t* tmem_full = w_empty + T2_MAX_NW;
-  uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_ptr = (uint32_t*)(tmem_empty + 2);
+  uint64_t* tmem_empty = tmem_full + T2_MAX_ACC;
+  uint32_t* tmem_ptr = (uint32_t*)(tmem_empty + T2_MAX_ACC);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cs = p.cs;
@@ -138,6 +179,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   const int cid = blockIdx.x / cs, ncl = gridDim.x / cs;
   const int groups = (p.m_tiles_total + cs - 1) / cs;
   const int items = groups * p.n_tiles;
+  constexpr int kEpiWarps = kBlockEpi ? T2_EPI_WARPS_BLOCK : T2_EPI_WARPS;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -148,7 +190,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < T2_NA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < T2_NW; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], kPair ? 1u : (uint32_t)cs); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], (uint32_t)((kPair ? 2 : 1) * (p.epi_block ? T2_EPI_WARPS_BLOCK : T2_EPI_WARPS))); }
+    for (int i = 0; i < p.nacc; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], (uint32_t)((kPair ? 2 : 1) * kEpiWarps)); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -160,53 +202,73 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
   }
+  if (kBlockEpi && p.cst_staged && warp >= 4) {
+    for (int i = (int)threadIdx.x - 128; i < p.N; i += kEpiWarps * 32) {
+      cst[i] = __ldg(p.bias + i);
+      cst[p.N + i] = __ldg(p.snake_ea + i);
+      cst[2 * p.N + i] = __ldg(p.snake_ib + i);
+    }
+  }
   tc_fence_before();
   __syncthreads();
   if (cs > 1) cluster_sync_all();   // every CTA's barriers are initialised before any remote arrive / multicast lands
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  // item -> (n tile, this CTA's M tile); valid_any = some CTA of the cluster has rows to produce
+  // item -> (n tile, this CTA's M tile).  Returns "some CTA of the cluster has rows to produce"; the result and `mine`
+  // go through a vote so that the callers' control flow is warp-uniform by construction.  Divisions are multiplications
+  // by host-computed magic numbers: every warp of the CTA walks the item list, so this runs 16 times per tile.
   auto coords = [&](int item, int& b, int& t0, int& n0, bool& mine) -> bool {
-    const int nt = item % p.n_tiles, g = item / p.n_tiles;
+    int g = item, nt = 0;
+    if (p.n_tiles > 1) {
+      g = (int)(__umulhi((uint32_t)item, p.div_nt_m) >> p.div_nt_s);   // n_tiles >= 2
+      nt = item - g * p.n_tiles;
+    }
     n0 = nt * p.BN;
+    const int mg0 = g * cs;
+    const int b0 = p.tiles_per_utt == 1 ? mg0 : (int)(__umulhi((uint32_t)mg0, p.div_tpu_m) >> p.div_tpu_s);
+    const int i0 = mg0 - b0 * p.tiles_per_utt;                    // M tile index inside its utterance
     bool any = false;
     mine = false;
     b = p.B; t0 = 0;                 // out-of-range utterance: TMA zero-fills, epilogue stores nothing
     for (int r = 0; r < cs; ++r) {
-      const int mg = g * cs + r;
-      if (mg >= p.m_tiles_total) continue;
-      const int bb = mg / p.tiles_per_utt, tt = (mg % p.tiles_per_utt) * T2_BM;
-      const bool ok = tt < p.len_frames[bb] * p.rows_per_frame;
+      if (mg0 + r >= p.m_tiles_total) continue;
+      const bool wrap = i0 + r >= p.tiles_per_utt;                // cs <= 2: the pair's second tile may open the next utterance
+      const int bb = wrap ? b0 + 1 : b0, tt = (wrap ? 0 : i0 + r) * T2_BM;
+      const bool ok = tt < __ldg(p.len_frames + bb) * p.rows_per_frame;
       any |= ok;
       if (r == (int)rank) { b = bb; t0 = tt; mine = ok; }
     }
-    return any;
+    mine = __any_sync(0xffffffffu, mine);
+    return __any_sync(0xffffffffu, any);
   };
 
   if (warp == 0) {
-    // ================= TMA producer (lane 0) + residual L2 prefetch (all lanes) =================
+    // ================= TMA producer (one elected lane) + residual L2 prefetch (all lanes) =================
     // The producer runs one to two tiles ahead of the epilogue, so pulling this item's residual rows into L2 here
     // turns the epilogue's residual reads from HBM-latency loads into L2 hits.
     int sa = 0, sw = 0;
-    uint32_t pa = 0, pw = 0;
+    uint32_t pa = 0, pw = 0, w_loaded = 0;      // w_loaded: bit s = resident W stage s has been requested
     const int wrows = p.BN / cs;
     const int res_es = y_is_f32 ? 4 : 2;
+    const int stages_per_tile = p.ncb * p.ngroups;
     for (int item = cid; item < items; item += ncl) {
       int b, t0, n0; bool mine;
       if (!coords(item, b, t0, n0, mine)) continue;
       if (p.res != nullptr && mine) {
-        const int valid = p.len_frames[b] * p.rows_per_frame;
+        const int valid = __ldg(p.len_frames + b) * p.rows_per_frame;
         const int line_cnt = (p.BN * res_es + 127) / 128;
         for (int r = lane; r < T2_BM; r += 32) {
           if (t0 + r >= valid) break;
           const char* ptr = (const char*)p.res + ((long long)b * p.res_bstride + (long long)(t0 + r) * p.ldres + n0) * res_es;
           for (int l = 0; l < line_cnt; ++l) asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr + l * 128));
         }
+        __syncwarp();
       }
-      if (lane == 0) {
-        for (int cb = 0; cb < p.ncb; ++cb) {
-          mbar_wait(&a_empty[sa], pa ^ 1);
+      if (p.w_resident) sw = (item % p.n_tiles) * stages_per_tile;
+      for (int cb = 0; cb < p.ncb; ++cb) {
+        mbar_wait(&a_empty[sa], pa ^ 1);
+        if (elect_one()) {
           if (kPair) {   // both CTAs' boxes complete on the LEADER's barrier
             if (rank == 0) mbar_expect_tx(&a_full[sa], 2 * p.a_tx_bytes);
             tma_load_3d_2sm(a_ring + (size_t)sa * p.a_stage_bytes, &map_a, &a_full[sa], cb * T2_BK, t0 - p.halo, b);
@@ -214,10 +276,18 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             mbar_expect_tx(&a_full[sa], p.a_tx_bytes);
             tma_load_3d(a_ring + (size_t)sa * p.a_stage_bytes, &map_a, &a_full[sa], cb * T2_BK, t0 - p.halo, b);
           }
-          if (++sa == T2_NA) { sa = 0; pa ^= 1; }
-          for (int tap0 = 0; tap0 < p.taps; tap0 += p.wg) {
-            const int ntap = min(p.wg, p.taps - tap0);
+        }
+        if (++sa == T2_NA) { sa = 0; pa ^= 1; }
+        for (int tap0 = 0; tap0 < p.taps; tap0 += p.wg) {
+          const int ntap = min(p.wg, p.taps - tap0);
+          bool load = true;
+          if (p.w_resident) {
+            load = !((w_loaded >> sw) & 1u);
+            w_loaded |= 1u << sw;
+          } else {
             mbar_wait(&w_empty[sw], pw ^ 1);            // every CTA of the cluster has drained this slot
+          }
+          if (load && elect_one()) {
             uint8_t* wst = w_ring + (size_t)sw * p.w_stage_bytes;
             if (kPair) {   // this CTA's half of each weight tile (rows rank*BN/2 ..), at the SAME smem offsets in both CTAs
               if (rank == 0) mbar_expect_tx(&w_full[sw], (uint32_t)ntap * (uint32_t)p.BN * 128u);
@@ -231,62 +301,101 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 else tma_load_2d_mc(dst, &map_w, &w_full[sw], cb * T2_BK, (tap0 + j) * p.N + n0 + (int)rank * wrows, mc_mask);
               }
             }
-            if (++sw == T2_NW) { sw = 0; pw ^= 1; }
           }
+          if (++sw == T2_NW) { sw = 0; pw ^= 1; }
         }
       }
       __syncwarp();
     }
-  } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (lane == 0 && (!kPair || rank == 0)) {
+  } else if (warp == 1 || (warp == 3 && p.nmma == 2)) {
+    // ================= MMA issuers: warp-uniform loops, one elected lane issues =================
+    // Two issuer warps take alternate tiles (each tile has its own TMEM accumulator and its own ring slots, and a
+    // tcgen05.commit only tracks the MMAs of the thread that executes it), which doubles the issue rate of small tiles.
+    // The single issuing thread is latency-bound on its own instruction stream (uniform-datapath ops cost 5-10 cycles
+    // each when dependent), so the per-MMA work is two 64-bit descriptor adds: descriptors are linear in (tap, k-step)
+    // and the address field cannot carry out of its 14 bits (smem addresses are < 256 KB).
+    if (!kPair || rank == 0) {
       int sa = 0, sw = 0, acc = 0;
       uint32_t pa = 0, pw = 0, pacc = 0;
+      const uint64_t desc_fixed = ((uint64_t)((1024u >> 4) | (1u << 14) | (2u << 29)) << 32) | (1u << 16);   // SBO 1024 B, v1, SWIZZLE_128B, LBO 1
+      const int stages_per_tile = p.ncb * p.ngroups;
+      const int taps = p.taps, wg = p.wg, ncb = p.ncb, nacc = p.nacc, w_resident = p.w_resident;
+      const uint32_t idesc = p.idesc;
+      const uint64_t dA = (uint64_t)(p.dil * 8), dW = (uint64_t)(p.w_tap_bytes >> 4);   // per-tap descriptor steps (16-byte units)
+      const uint32_t a_ring_u32 = smem_u32(a_ring), w_ring_u32 = smem_u32(w_ring);
+      uint32_t w_seen = 0;                       // resident weights: bit s = stage s has been waited for once (it never changes again)
+      const int which = warp == 1 ? 0 : 1;
+      int turn = 0;
       for (int item = cid; item < items; item += ncl) {
         int b, t0, n0; bool mine;
         if (!coords(item, b, t0, n0, mine)) continue;
+        if (p.nmma == 2) {
+          const bool skip = turn != which;
+          turn ^= 1;
+          if (skip) {   // the other issuer's tile: step over its ring slots and its accumulator
+            sa += ncb;
+            while (sa >= T2_NA) { sa -= T2_NA; pa ^= 1; }
+            if (!w_resident) {
+              sw += stages_per_tile;
+              while (sw >= T2_NW) { sw -= T2_NW; pw ^= 1; }
+            }
+            if (++acc == nacc) { acc = 0; pacc ^= 1; }
+            continue;
+          }
+        }
         mbar_wait(&tmem_empty[acc], pacc ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * T2_MAX_BN);
-        uint32_t accumulate = 0;
-        for (int cb = 0; cb < p.ncb; ++cb) {
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_stride);
+        if (w_resident) sw = (item % p.n_tiles) * stages_per_tile;
+        for (int cb = 0; cb < ncb; ++cb) {
           mbar_wait(&a_full[sa], pa);
-          tc_fence_after();
-          const uint32_t a_base = smem_u32(a_ring + (size_t)sa * p.a_stage_bytes);
+          const uint64_t ad_cb = desc_fixed | (uint64_t)((a_ring_u32 + (uint32_t)sa * p.a_stage_bytes) >> 4);
           const int nk = min(T2_BK, p.Cin - cb * T2_BK) / 16;
-          for (int tap0 = 0; tap0 < p.taps; tap0 += p.wg) {
-            const int ntap = min(p.wg, p.taps - tap0);
-            mbar_wait(&w_full[sw], pw);
+          for (int tap0 = 0; tap0 < taps; tap0 += wg) {
+            const int ntap = min(wg, taps - tap0);
+            if (!w_resident) {
+              mbar_wait(&w_full[sw], pw);
+            } else if (!((w_seen >> sw) & 1u)) {
+              mbar_wait(&w_full[sw], 0u);
+              w_seen |= 1u << sw;
+            }
             tc_fence_after();
-            const uint32_t w_base = smem_u32(w_ring + (size_t)sw * p.w_stage_bytes);
-            for (int j = 0; j < ntap; ++j) {
-              const uint32_t a_tap = a_base + (uint32_t)((tap0 + j) * p.dil) * 128u;   // row-shifted view of the halo tile
-              const uint32_t w_tap = w_base + (uint32_t)j * p.w_tap_bytes;
-              for (int k = 0; k < nk; ++k) {
-                if (kPair) tc_mma_f16_2sm(d_tmem, make_smem_desc_shifted(a_tap + 32u * k, false), make_smem_desc(w_tap + 32u * k), p.idesc, accumulate);
-                else tc_mma_f16(d_tmem, make_smem_desc_shifted(a_tap + 32u * k, p.desc_mode == 2), make_smem_desc(w_tap + 32u * k), p.idesc, accumulate);
-                accumulate = 1;
+            if (elect_one()) {
+              uint64_t ad = ad_cb + (uint64_t)tap0 * dA;
+              uint64_t wd = desc_fixed | (uint64_t)((w_ring_u32 + (uint32_t)sw * p.w_stage_bytes) >> 4);
+              const uint32_t first = (cb | tap0) != 0 ? 1u : 0u;
+              if (nk == 4) issue_taps<kPair, 4>(d_tmem, ad, wd, dA, dW, idesc, first, ntap);
+              else if (nk == 2) issue_taps<kPair, 2>(d_tmem, ad, wd, dA, dW, idesc, first, ntap);
+              else if (nk == 3) issue_taps<kPair, 3>(d_tmem, ad, wd, dA, dW, idesc, first, ntap);
+              else issue_taps<kPair, 1>(d_tmem, ad, wd, dA, dW, idesc, first, ntap);
+              if (!w_resident) {
+                if (kPair) tc_commit_2sm(&w_empty[sw], mc_mask);
+                else if (cs == 1) tc_commit(&w_empty[sw]); else tc_commit_mc(&w_empty[sw], mc_mask);
+              }
+              if (tap0 + ntap >= taps) {   // last W stage of this 64-channel block: the A halo tile is free
+                if (kPair) tc_commit_2sm(&a_empty[sa], mc_mask); else tc_commit(&a_empty[sa]);
+                if (cb == ncb - 1) {
+                  if (kPair) tc_commit_2sm(&tmem_full[acc], mc_mask); else tc_commit(&tmem_full[acc]);
+                }
               }
             }
-            if (kPair) tc_commit_2sm(&w_empty[sw], mc_mask);
-            else if (cs == 1) tc_commit(&w_empty[sw]); else tc_commit_mc(&w_empty[sw], mc_mask);
+            __syncwarp();
             if (++sw == T2_NW) { sw = 0; pw ^= 1; }
           }
-          if (kPair) tc_commit_2sm(&a_empty[sa], mc_mask); else tc_commit(&a_empty[sa]);
           if (++sa == T2_NA) { sa = 0; pa ^= 1; }
         }
-        if (kPair) tc_commit_2sm(&tmem_full[acc], mc_mask); else tc_commit(&tmem_full[acc]);
-        if (++acc == 2) { acc = 0; pacc ^= 1; }
+        if (++acc == nacc) { acc = 0; pacc ^= 1; }
       }
     }
-  } else if (warp >= 4 && p.epi_block) {
-    // ================= specialised block epilogue (12 warps) =================
+  } else if (kBlockEpi && warp >= 4) {
+    // ================= block epilogue (12 warps) =================
     const int ew = warp - 4, quarter = warp & 3, grp = ew >> 2;          // grp 0..2 takes chunks grp, grp+3, ...
     const int nch = p.BN / 32;
-    uint8_t* buf_y = staging + (size_t)ew * 4096;                         // this warp's 32 rows x 64 B, y then a
-    uint8_t* buf_a = buf_y + 2048;
     const bool has_res = p.res != nullptr, has_y = p.out_y != nullptr;
+    uint8_t* buf_a = staging + (size_t)ew * (has_y ? 4096 : 2048);       // this warp's 32 rows x 64 B: a, then y
+    uint8_t* buf_y = buf_a + 2048;
     const int slot_rows = p.Tmax * p.rows_per_frame;
+    const uint32_t cst_u32 = smem_u32(cst);
     int acc = 0;
     uint32_t pacc = 0;
     for (int item = cid; item < items; item += ncl) {
@@ -304,7 +413,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
       if (mine) {
         for (int ch = grp; ch < nch; ch += 3) {
           uint32_t r[32];
-          tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * T2_MAX_BN + ch * 32), r);
+          tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.acc_stride + ch * 32), r);
           if (has_res && ch != grp) {
 #pragma unroll
             for (int c = 0; c < 4; ++c) rres[c] = __ldg((const uint4*)(res_row + ch * 32 + 8 * c));
@@ -313,13 +422,16 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
           if (lane == 0) tma_store_wait_read0();                          // my previous stores have drained the staging rows
           __syncwarp();
           const int n = n0 + ch * 32;
-          if (has_res) {
-            if (has_y) epi_block_chunk<T16, true, true>(r, p.bias + n, p.snake_ea + n, p.snake_ib + n, rres, buf_y, buf_a, lane);
-            else epi_block_chunk<T16, true, false>(r, p.bias + n, p.snake_ea + n, p.snake_ib + n, rres, buf_y, buf_a, lane);
+          const uint32_t sb = cst_u32 + 4u * (uint32_t)n, se = sb + 4u * (uint32_t)p.N, si = se + 4u * (uint32_t)p.N;
+#define Q3_EPI(RES, Y, SM) epi_block_chunk<T16, RES, Y, SM>(r, p.bias + n, p.snake_ea + n, p.snake_ib + n, sb, se, si, rres, buf_y, buf_a, lane)
+          if (p.cst_staged) {
+            if (has_res) { if (has_y) Q3_EPI(true, true, true); else Q3_EPI(true, false, true); }
+            else { if (has_y) Q3_EPI(false, true, true); else Q3_EPI(false, false, true); }
           } else {
-            if (has_y) epi_block_chunk<T16, false, true>(r, p.bias + n, p.snake_ea + n, p.snake_ib + n, rres, buf_y, buf_a, lane);
-            else epi_block_chunk<T16, false, false>(r, p.bias + n, p.snake_ea + n, p.snake_ib + n, rres, buf_y, buf_a, lane);
+            if (has_res) { if (has_y) Q3_EPI(true, true, false); else Q3_EPI(true, false, false); }
+            else { if (has_y) Q3_EPI(false, true, false); else Q3_EPI(false, false, false); }
           }
+#undef Q3_EPI
           fence_async_smem();
           __syncwarp();
           if (lane == 0) {
@@ -332,13 +444,13 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if (kPair && rank != 0) mbar_arrive_cluster(&tmem_empty[acc], 0); else mbar_arrive(&tmem_empty[acc]);
+        if (kPair && rank != 0) mbar_arrive_remote(&tmem_empty[acc], 0); else mbar_arrive(&tmem_empty[acc]);
       }
-      if (++acc == 2) { acc = 0; pacc ^= 1; }
+      if (++acc == p.nacc) { acc = 0; pacc ^= 1; }
     }
     if (lane == 0) tma_store_wait_all();
-  } else if (warp >= 4 && warp < 12) {
-    // ================= epilogue =================
+  } else if (!kBlockEpi && warp >= 4) {
+    // ================= generic epilogue (8 warps) =================
     // Two groups of four warps (one warp per TMEM lane quarter) split the tile's 16-column chunks.  16-bit outputs
     // are written to a 128B-per-4-rows swizzled staging chunk in smem and leave through ONE TMA store per chunk and
     // tensor (coalesced, asynchronous) instead of 32-way scattered 16-byte global stores per warp instruction.
@@ -359,7 +471,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
       int b, t0, n0; bool mine;
       if (!coords(item, b, t0, n0, mine)) continue;
       const int t = t0 + rin;
-      const bool row_ok = mine && t < p.len_frames[min(b, p.B - 1)] * p.rows_per_frame;
+      const bool row_ok = mine && t < __ldg(p.len_frames + min(b, p.B - 1)) * p.rows_per_frame;
       uint4 pre[16];   // 16-bit residual rows of this thread's chunks, in flight while the MMAs run
       if (prefetch_res && row_ok) {
         const uint4* rp = (const uint4*)((const T16*)p.res + (long long)b * p.res_bstride + (long long)t * p.ldres + n0);
@@ -375,7 +487,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         if (ch >= c_end) break;
         uint32_t r[16];
         __syncwarp();
-        tc_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * T2_MAX_BN + ch * 16), r);
+        tc_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.acc_stride + ch * 16), r);
         tc_wait_ld();
         const int n = n0 + ch * 16;
         float v[16];
@@ -478,9 +590,9 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {   // pair mode: the accumulator ring is owned by the leader's MMA warp
-        if (kPair && rank != 0) mbar_arrive_cluster(&tmem_empty[acc], 0); else mbar_arrive(&tmem_empty[acc]);
+        if (kPair && rank != 0) mbar_arrive_remote(&tmem_empty[acc], 0); else mbar_arrive(&tmem_empty[acc]);
       }
-      if (++acc == 2) { acc = 0; pacc ^= 1; }
+      if (++acc == p.nacc) { acc = 0; pacc ^= 1; }
     }
     if (use_tma && leader) tma_store_wait_all();
   }
@@ -510,13 +622,13 @@ EncodeTiledFn encode_fn2() {
 }
 int pick_bn2(int N, bool prefer32 = false) {
   if (prefer32)
-    for (int bn = T2_MAX_BN; bn >= 64; bn -= 32)
+    for (int bn = 256; bn >= 64; bn -= 32)
       if (N % bn == 0) return bn;
-  for (int bn = T2_MAX_BN; bn >= 16; bn -= 16)
+  for (int bn = 256; bn >= 16; bn -= 16)
     if (N % bn == 0) return bn;
   return 0;
 }
-// The specialised block epilogue: bias + [16-bit residual] + [16-bit stream out] + SnakeBeta operand out, nothing else.
+// The block epilogue: bias + [16-bit residual] + [16-bit stream out] + SnakeBeta operand out, nothing else.
 bool block_epilogue_ok(const ConvGemmParams& p, int y_dtype) {
   return p.out_a && p.snake_ea && p.bias && p.act == ACT_NONE && !p.out_tap && !p.scale &&
          (!p.res || (p.out_y && p.res == p.out_y)) && (!p.out_y || y_dtype != DT_F32) && pick_bn2(p.N, true) % 32 == 0 &&
@@ -525,6 +637,24 @@ bool block_epilogue_ok(const ConvGemmParams& p, int y_dtype) {
 int env_int(const char* name, int dflt) {
   const char* e = getenv(name);
   return e ? atoi(e) : dflt;
+}
+
+template <typename T16>
+cudaError_t launch_variant(const cudaLaunchConfig_t& cfg, bool pair, bool block, const CUtensorMap& ma, const CUtensorMap& mw,
+                           const CUtensorMap& my, const CUtensorMap& mo, const Tc2Params& q, int yf) {
+  static std::once_flag once;
+  std::call_once(once, []() {
+    cudaFuncSetAttribute(conv_gemm_tc2_kernel<T16, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(conv_gemm_tc2_kernel<T16, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(conv_gemm_tc2_kernel<T16, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(conv_gemm_tc2_kernel<T16, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  });
+  if (pair) {
+    if (block) return cudaLaunchKernelEx(&cfg, conv_gemm_tc2_kernel<T16, true, true>, ma, mw, my, mo, q, yf);
+    return cudaLaunchKernelEx(&cfg, conv_gemm_tc2_kernel<T16, true, false>, ma, mw, my, mo, q, yf);
+  }
+  if (block) return cudaLaunchKernelEx(&cfg, conv_gemm_tc2_kernel<T16, false, true>, ma, mw, my, mo, q, yf);
+  return cudaLaunchKernelEx(&cfg, conv_gemm_tc2_kernel<T16, false, false>, ma, mw, my, mo, q, yf);
 }
 }  // namespace
 
@@ -550,12 +680,14 @@ cudaError_t launch_conv_gemm_tc2(const ConvGemmParams& p, const BatchGeom& g, in
   static const int cs_env = env_int("Q3TTS_TC_CLUSTER", 2);
   static const int pair_env = env_int("Q3TTS_TC_PAIR", 1);
   static const int block_env = env_int("Q3TTS_TC_BLOCK_EPI", 1);
+  static const int resident_env = env_int("Q3TTS_TC_W_RESIDENT", 1);
+  static const int nacc_env = env_int("Q3TTS_TC_NACC", 4);
+  static const int cst_env = env_int("Q3TTS_TC_CST", 1);
   const bool epi_block = block_env && block_epilogue_ok(p, y_dtype);
   const int BN = pick_bn2(p.N, epi_block);
   const int slot_rows = g.Tmax * p.rows_per_frame;
   const int halo = (p.taps - 1) * p.dil;
   Tc2Params q{};
-  q.epi_block = epi_block;
   q.B = g.B; q.Tmax = g.Tmax; q.rows_per_frame = p.rows_per_frame; q.len_frames = g.len_frames;
   q.N = p.N; q.BN = BN; q.Cin = p.Cin; q.taps = p.taps; q.dil = p.dil; q.ncb = (p.Cin + T2_BK - 1) / T2_BK; q.halo = halo;
   q.tiles_per_utt = (slot_rows + T2_BM - 1) / T2_BM;
@@ -564,6 +696,8 @@ cudaError_t launch_conv_gemm_tc2(const ConvGemmParams& p, const BatchGeom& g, in
   int cs = (cs_env == 2 && BN % 16 == 0 && q.m_tiles_total >= 2) ? 2 : 1;
   const bool pair = pair_env && cs == 2;
   q.cs = cs;
+  q.nacc = (BN <= 128 && nacc_env >= 4) ? 4 : 2;
+  q.acc_stride = (int)T2_TMEM_COLS / q.nacc;
   const CUtensorMapDataType dt = op_dtype == DT_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   CUtensorMap map_a, map_w;
   {
@@ -589,12 +723,12 @@ cudaError_t launch_conv_gemm_tc2(const ConvGemmParams& p, const BatchGeom& g, in
   q.a_tx_bytes = (uint32_t)(T2_BM + halo) * 128u;
   q.a_stage_bytes = (q.a_tx_bytes + 1023u) & ~1023u;
   q.w_tap_bytes = (uint32_t)(pair ? BN / 2 : BN) * 128u;     // pair mode: each CTA stages half of the weight tile
-  {  // several taps share one W stage when the tiles are small: the single MMA thread then waits / commits once per
-     // wg*nk MMAs instead of once per nk (its per-stage overhead was what kept the tensor pipe at 30 % for N = 96)
+  {  // several taps share one W stage when the tiles are small: one barrier wait / commit per wg*nk MMAs
     static const int wg_env = env_int("Q3TTS_TC_WG_KB", 40);
     const int wg_max = std::max(1, (wg_env * 1024) / (int)q.w_tap_bytes);
-    const int ngroups = (p.taps + wg_max - 1) / wg_max;
-    q.wg = (p.taps + ngroups - 1) / ngroups;
+    q.ngroups = (p.taps + wg_max - 1) / wg_max;
+    q.wg = (p.taps + q.ngroups - 1) / q.ngroups;
+    q.ngroups = (p.taps + q.wg - 1) / q.wg;
   }
   q.w_stage_bytes = q.w_tap_bytes * (uint32_t)q.wg;
   q.desc_mode = tc2_mode();
@@ -604,11 +738,12 @@ cudaError_t launch_conv_gemm_tc2(const ConvGemmParams& p, const BatchGeom& g, in
   q.out_a = p.out_a; q.lda_out = p.lda_out; q.ao_bstride = p.ao_bstride;
   q.snake_ea = p.snake_ea; q.snake_ib = p.snake_ib;
   q.out_tap = (float*)p.out_tap; q.ldt = p.ldt; q.tap_bstride = p.tap_bstride;
-  // 16-bit outputs leave through smem staging + TMA stores ({16 cols, 128 rows} boxes, 32-byte swizzle)
+  // 16-bit outputs leave through smem staging + TMA stores
   static const int tma_store_env = env_int("Q3TTS_TC_TMA_STORE", 1);
   const int yf = y_dtype == DT_F32;
-  q.tma_y = tma_store_env && p.out_y && !yf && p.act != ACT_SWIGLU;
-  q.tma_a = tma_store_env && p.out_a && p.act != ACT_SWIGLU;
+  q.tma_y = (epi_block || tma_store_env) && p.out_y && !yf && p.act != ACT_SWIGLU;
+  q.tma_a = (epi_block || tma_store_env) && p.out_a && p.act != ACT_SWIGLU;
+  q.cst_staged = epi_block && cst_env && p.N <= T2_CST_MAX_N;
   CUtensorMap map_y = map_a, map_o = map_a;   // placeholders when unused
   auto out_map = [&](CUtensorMap* m, void* base, int ld, long long bstride) -> bool {
     cuuint64_t dims[3] = {(cuuint64_t)ld, (cuuint64_t)slot_rows, (cuuint64_t)g.B};
@@ -622,11 +757,31 @@ cudaError_t launch_conv_gemm_tc2(const ConvGemmParams& p, const BatchGeom& g, in
   };
   if (q.tma_y && !out_map(&map_y, p.out_y, p.ldy, p.y_bstride)) return cudaErrorInvalidValue;
   if (q.tma_a && !out_map(&map_o, p.out_a, p.lda_out, p.ao_bstride)) return cudaErrorInvalidValue;
-  // ring depths from the smem budget: keep as many weight tiles in flight as fit (small-N convs need many)
-  const size_t budget = 225 * 1024 - 2048 - ((q.tma_y || q.tma_a) ? T2_STAGING_BYTES : 0);
-  // Little's law: bytes in flight must cover HBM/L2 latency, so the budget is split between the two rings in
-  // proportion to what a tile consumes from each (a 1x1 conv streams mostly A, a k=7 conv mostly W).
-  {
+  q.staging_bytes = !(q.tma_y || q.tma_a) ? 0u : (epi_block ? (uint32_t)T2_EPI_WARPS_BLOCK * (q.tma_y ? 4096u : 2048u) : T2_STAGING_BYTES);
+  const size_t fixed = q.staging_bytes + (q.cst_staged ? (size_t)3 * p.N * 4 : 0) + 512 + 1024;
+  auto magic = [](uint32_t d, uint32_t* m, uint32_t* sh) {   // x / d == umulhi(x, m) >> sh for 0 <= x < 2^31
+    uint32_t lg = 0;
+    while ((1u << lg) < d) ++lg;
+    const uint64_t mm = ((1ull << (31 + lg)) / d) + 1;
+    if (mm >> 32) return false;
+    *m = (uint32_t)mm; *sh = lg == 0 ? 0 : lg - 1;   // d == 1 is special-cased in the kernel
+    return true;
+  };
+  if (!magic((uint32_t)q.n_tiles, &q.div_nt_m, &q.div_nt_s) || !magic((uint32_t)q.tiles_per_utt, &q.div_tpu_m, &q.div_tpu_s))
+    return cudaErrorInvalidConfiguration;
+  const size_t budget = 227 * 1024 - fixed;
+  // Resident weights: every (n tile, 64-channel block, tap group) stage has its own slot and is loaded once.
+  const int stages_per_tile = q.ncb * q.ngroups;
+  const size_t resident_bytes = (size_t)q.n_tiles * stages_per_tile * q.w_stage_bytes;
+  const int items_per_cluster = ((q.m_tiles_total + cs - 1) / cs * q.n_tiles) / std::max(1, 148 / cs);
+  q.w_resident = resident_env && q.n_tiles * stages_per_tile <= T2_MAX_NW && items_per_cluster >= 4 &&
+                 resident_bytes + 64 * 1024 <= budget;   // and still >= 64 KB of A tiles in flight
+  if (q.w_resident) {
+    q.nw = q.n_tiles * stages_per_tile;
+    q.na = (int)std::min<size_t>(T2_MAX_NA, (budget - resident_bytes) / q.a_stage_bytes);
+  } else {
+    // Little's law: bytes in flight must cover HBM/L2 latency, so the budget is split between the two rings in
+    // proportion to what a tile consumes from each (a 1x1 conv streams mostly A, a k=7 conv mostly W).
     const double a_tile = (double)q.ncb * q.a_stage_bytes, w_tile = (double)q.ncb * q.taps * q.w_tap_bytes;
     int na = (int)((double)budget * a_tile / (a_tile + w_tile) / q.a_stage_bytes + 0.5);
     na = std::max(2, std::min(T2_MAX_NA, na));
@@ -634,8 +789,13 @@ cudaError_t launch_conv_gemm_tc2(const ConvGemmParams& p, const BatchGeom& g, in
     q.na = na;
     q.nw = (int)std::min<size_t>(T2_MAX_NW, (budget - (size_t)q.na * q.a_stage_bytes) / q.w_stage_bytes);
   }
-  if (q.nw < 2) return cudaErrorInvalidConfiguration;
-  size_t smem = (size_t)q.na * q.a_stage_bytes + (size_t)q.nw * q.w_stage_bytes + ((q.tma_y || q.tma_a) ? T2_STAGING_BYTES : 0) + 512 + 1024;
+  // Two MMA issuer warps on alternate tiles: a warp then waits on ring slots up to one tile ahead of the other's, and
+  // an mbarrier parity wait cannot tell phase n from phase n-2, so both rings must hold more than one tile.
+  static const int nmma_env = env_int("Q3TTS_TC_NMMA", 2);
+  q.nmma = (nmma_env == 2 && q.na >= q.ncb + 1 && (q.w_resident || q.nw >= stages_per_tile + 1)) ? 2 : 1;
+  if (q.nw < 2 && !q.w_resident) return cudaErrorInvalidConfiguration;
+  if (q.na < 2) return cudaErrorInvalidConfiguration;
+  size_t smem = (size_t)q.na * q.a_stage_bytes + (size_t)q.nw * q.w_stage_bytes + fixed;
   smem = std::max<size_t>(smem, 128 * 1024);   // one CTA per SM: it owns all 512 TMEM columns
   int sms = 0, dev = 0;
   cudaGetDevice(&dev);
@@ -645,7 +805,7 @@ cudaError_t launch_conv_gemm_tc2(const ConvGemmParams& p, const BatchGeom& g, in
   grid = std::max(grid / cs * cs, cs);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3(T2_THREADS);
+  cfg.blockDim = dim3(epi_block ? T2_THREADS_BLOCK : T2_THREADS_GENERIC);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
@@ -653,27 +813,8 @@ cudaError_t launch_conv_gemm_tc2(const ConvGemmParams& p, const BatchGeom& g, in
   attr[0].val.clusterDim.x = (unsigned)cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t err;
-  if (op_dtype == DT_F16) {
-    static bool done = false;
-    if (!done) {
-      cudaFuncSetAttribute(conv_gemm_tc2_kernel<__half, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-      cudaFuncSetAttribute(conv_gemm_tc2_kernel<__half, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-      done = true;
-    }
-    err = pair ? cudaLaunchKernelEx(&cfg, conv_gemm_tc2_kernel<__half, true>, map_a, map_w, map_y, map_o, q, yf)
-               : cudaLaunchKernelEx(&cfg, conv_gemm_tc2_kernel<__half, false>, map_a, map_w, map_y, map_o, q, yf);
-  } else {
-    static bool done = false;
-    if (!done) {
-      cudaFuncSetAttribute(conv_gemm_tc2_kernel<__nv_bfloat16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-      cudaFuncSetAttribute(conv_gemm_tc2_kernel<__nv_bfloat16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-      done = true;
-    }
-    err = pair ? cudaLaunchKernelEx(&cfg, conv_gemm_tc2_kernel<__nv_bfloat16, true>, map_a, map_w, map_y, map_o, q, yf)
-               : cudaLaunchKernelEx(&cfg, conv_gemm_tc2_kernel<__nv_bfloat16, false>, map_a, map_w, map_y, map_o, q, yf);
-  }
-  return err;
+  if (op_dtype == DT_F16) return launch_variant<__half>(cfg, pair, epi_block, map_a, map_w, map_y, map_o, q, yf);
+  return launch_variant<__nv_bfloat16>(cfg, pair, epi_block, map_a, map_w, map_y, map_o, q, yf);
 }
 
 }  // namespace q3

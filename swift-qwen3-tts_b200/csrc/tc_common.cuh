@@ -175,11 +175,20 @@ __device__ __forceinline__ void tc_commit_2sm(uint64_t* bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta_rank) {   // arrive on `bar` of CTA `cta_rank`
+// Arrive on `bar` of CTA `cta_rank` of the cluster.  Default (.release.cta) semantics on purpose: the only thing ordered
+// before this arrive is a completed tcgen05.ld (tcgen05.wait::ld + tcgen05.fence::before_thread_sync); the
+// .release.cluster form costs a MEMBAR.ALL.GPU + ERRBAR per arrive (7 % of the epilogue's cycles in the first capture).
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta_rank) {
   asm volatile(
       "{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
       ::"r"(smem_u32(bar)), "r"(cta_rank) : "memory");
+}
+// One lane of the (converged) warp: returns 1 in the elected lane, 0 elsewhere.
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred;
 }
 
 }  // namespace tc

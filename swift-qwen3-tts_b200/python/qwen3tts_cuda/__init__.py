@@ -116,6 +116,8 @@ def lib() -> C.CDLL:
         "q3tts_profile_enable": (C.c_int, [vp, i32]),
         "q3tts_profile_get": (C.c_int, [vp, C.POINTER(StageTime), i32]),
         "q3tts_launch_count": (i64, [vp]),
+        "q3tts_debug_conv_gemm": (C.c_int, [i32, i32, i32, i32, i32, i32, i32, i32, i32, C.POINTER(C.c_float),
+                                            C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(L, name)
@@ -129,6 +131,14 @@ def lib() -> C.CDLL:
 def _check(status: int) -> None:
     if status != 0:
         raise AudioDecodingFailed(status, lib().q3tts_last_error().decode("utf-8", "replace"))
+
+
+def debug_conv_gemm(B: int, rows: int, Cin: int, N: int, taps: int, dil: int, mode: int, precision: int = PREC_FP16,
+                    iters: int = 0) -> Tuple[float, float, float]:
+    """Kernel-level check: (ms per launch, max|tc - simt| stream, max|tc - simt| operand) of one multi-tap GEMM."""
+    ms, dy, da = C.c_float(0), C.c_float(0), C.c_float(0)
+    _check(lib().q3tts_debug_conv_gemm(B, rows, Cin, N, taps, dil, mode, precision, iters, C.byref(ms), C.byref(dy), C.byref(da)))
+    return float(ms.value), float(dy.value), float(da.value)
 
 
 def device_count() -> int:
