@@ -189,6 +189,10 @@ int64_t q3tts_launch_count(const q3tts_model* m);
 int q3tts_debug_conv_gemm(int32_t B, int32_t rows, int32_t Cin, int32_t N, int32_t taps, int32_t dil,
                           int32_t mode, int32_t precision, int32_t iters, float* ms_out,
                           float* max_diff_y, float* max_diff_a);
+/* The fused residual unit of the 96-channel block (ST.swift:430-437: x + conv1(snake(conv7(snake(x))))) against
+ * the same unit composed from three CUDA-core GEMM launches; out_snake = apply the consumer's SnakeBeta. */
+int q3tts_debug_resunit(int32_t B, int32_t rows, int32_t dil, int32_t out_snake, int32_t precision,
+                        int32_t iters, float* ms_out, float* max_diff);
 
 #ifdef __cplusplus
 }

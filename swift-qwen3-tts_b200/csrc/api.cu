@@ -490,7 +490,9 @@ int q3tts_debug_conv_gemm(int32_t B, int32_t rows, int32_t Cin, int32_t N, int32
     CUDA_OK(cudaMemcpyAsync(d_len, len.data(), (size_t)B * 4, cudaMemcpyHostToDevice, s));
     void* y[2] = {dmalloc(R * N * 2), dmalloc(R * N * 2)};
     void* a[2] = {dmalloc(R * N * 2), dmalloc(R * N * 2)};
-    BatchGeom g{B, rows, d_len};
+    long long valid_rows = 0;
+    for (int b = 0; b < B; ++b) valid_rows += len[(size_t)b];
+    BatchGeom g{B, rows, d_len, valid_rows};
     auto params = [&](int which) {
       ConvGemmParams p{};
       p.A = A; p.lda = Cin; p.a_bstride = (int64_t)rows * Cin;
@@ -540,6 +542,120 @@ int q3tts_debug_conv_gemm(int32_t B, int32_t rows, int32_t Cin, int32_t N, int32
       for (int i = 0; i < 2; ++i) CUDA_OK(launch_conv_gemm_tc2(p1, g, op, op, s));
       CUDA_OK(cudaEventRecord(e0, s));
       for (int i = 0; i < iters; ++i) CUDA_OK(launch_conv_gemm_tc2(p1, g, op, op, s));
+      CUDA_OK(cudaEventRecord(e1, s));
+      CUDA_OK(cudaStreamSynchronize(s));
+      float ms = 0;
+      CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+      *ms_out = ms / iters;
+      cudaEventDestroy(e0);
+      cudaEventDestroy(e1);
+    }
+    for (void* d : allocs) cudaFree(d);
+    cudaStreamDestroy(s);
+    return (int)Q3TTS_OK;
+  });
+}
+
+// Fused residual unit (kernels_res96.cu) against the same unit composed from three CUDA-core GEMM launches
+// (identity 1x1 + snake1, conv7 + snake2, conv1 + residual [+ snake3]) on seeded random data; then `iters` timed launches.
+int q3tts_debug_resunit(int32_t B, int32_t rows, int32_t dil, int32_t out_snake, int32_t precision, int32_t iters,
+                        float* ms_out, float* max_diff) {
+  return guarded([&]() {
+    if (B < 1 || rows < 1 || dil < 1) return fail(Q3TTS_EINVAL, "bad shape");
+    const int op = precision == Q3TTS_PREC_BF16 ? DT_BF16 : DT_F16;
+    const int C = 96;
+    cudaStream_t s = nullptr;
+    CUDA_OK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    std::vector<void*> allocs;
+    auto dmalloc = [&](size_t bytes) { void* d = nullptr; CUDA_OK(cudaMalloc(&d, bytes)); allocs.push_back(d); return d; };
+    uint64_t seed = 0xD1B54A32D192ED03ull ^ (uint64_t)dil;
+    auto rnd = [&]() { seed = seed * 6364136223846793005ull + 1442695040888963407ull; return (float)((seed >> 40) & 0xFFFFFF) / 8388608.0f - 1.0f; };
+    auto upload16v = [&](const std::vector<float>& h) {
+      float* d32 = (float*)dmalloc(h.size() * 4);
+      void* d16 = dmalloc(h.size() * 2);
+      CUDA_OK(cudaMemcpyAsync(d32, h.data(), h.size() * 4, cudaMemcpyHostToDevice, s));
+      CUDA_OK(cudaStreamSynchronize(s));
+      launch_convert(d32, d16, op, (int64_t)h.size(), s);
+      return d16;
+    };
+    auto rand_vec = [&](size_t n, float scale, float offset) { std::vector<float> h(n); for (auto& v : h) v = offset + rnd() * scale; return h; };
+    auto upload32 = [&](const std::vector<float>& h) {
+      float* d = (float*)dmalloc(h.size() * 4);
+      CUDA_OK(cudaMemcpyAsync(d, h.data(), h.size() * 4, cudaMemcpyHostToDevice, s));
+      CUDA_OK(cudaStreamSynchronize(s));
+      return d;
+    };
+    const size_t R = (size_t)B * rows;
+    void* X = upload16v(rand_vec(R * C, 1.5f, 0.f));
+    void* W7 = upload16v(rand_vec((size_t)7 * C * C, 1.0f / sqrtf(7.0f * C), 0.f));
+    void* W1 = upload16v(rand_vec((size_t)C * C, 1.0f / sqrtf((float)C), 0.f));
+    std::vector<float> eye((size_t)C * C, 0.f);
+    for (int i = 0; i < C; ++i) eye[(size_t)i * C + i] = 1.f;
+    void* WI = upload16v(eye);
+    float* zero = upload32(std::vector<float>((size_t)C, 0.f));
+    float* b7 = upload32(rand_vec((size_t)C, 0.1f, 0.f));
+    float* b1 = upload32(rand_vec((size_t)C, 0.1f, 0.f));
+    float *ea[3], *ib[3];
+    for (int i = 0; i < 3; ++i) { ea[i] = upload32(rand_vec((size_t)C, 0.3f, 1.0f)); ib[i] = upload32(rand_vec((size_t)C, 0.3f, 1.0f)); }
+    std::vector<int> len((size_t)B);
+    long long valid_rows = 0;
+    for (int b = 0; b < B; ++b) { len[(size_t)b] = std::max(1, rows - 301 * b); valid_rows += len[(size_t)b]; }
+    int* d_len = (int*)dmalloc((size_t)B * 4);
+    CUDA_OK(cudaMemcpyAsync(d_len, len.data(), (size_t)B * 4, cudaMemcpyHostToDevice, s));
+    void* A = dmalloc(R * C * 2);
+    void* Cb = dmalloc(R * C * 2);
+    void* Y = dmalloc(R * C * 2);       // reference stream (in place)
+    void* A3 = dmalloc(R * C * 2);      // reference snake3 output
+    void* O = dmalloc(R * C * 2);       // fused output
+    CUDA_OK(cudaMemsetAsync(O, 0, R * C * 2, s));
+    CUDA_OK(cudaMemsetAsync(A3, 0, R * C * 2, s));
+    CUDA_OK(cudaMemcpyAsync(Y, X, R * C * 2, cudaMemcpyDeviceToDevice, s));
+    BatchGeom g{B, rows, d_len, valid_rows};
+    auto base = [&](const void* in, const void* w, int taps, int d, const float* bias) {
+      ConvGemmParams p{};
+      p.A = in; p.lda = C; p.a_bstride = (int64_t)rows * C; p.W = w; p.rows_per_frame = 1; p.N = C; p.Cin = C; p.taps = taps; p.dil = d;
+      p.bias = bias; p.act = ACT_NONE; p.lda_out = C; p.ao_bstride = (int64_t)rows * C; p.ldy = C; p.y_bstride = (int64_t)rows * C;
+      p.ldres = C; p.res_bstride = (int64_t)rows * C;
+      return p;
+    };
+    { ConvGemmParams p = base(X, WI, 1, 1, zero); p.out_a = A; p.snake_ea = ea[0]; p.snake_ib = ib[0]; launch_conv_gemm_simt(p, g, op, op, s); }
+    { ConvGemmParams p = base(A, W7, 7, dil, b7); p.out_a = Cb; p.snake_ea = ea[1]; p.snake_ib = ib[1]; launch_conv_gemm_simt(p, g, op, op, s); }
+    { ConvGemmParams p = base(Cb, W1, 1, 1, b1); p.res = Y; p.out_y = Y; p.out_a = A3; p.snake_ea = ea[2]; p.snake_ib = ib[2]; launch_conv_gemm_simt(p, g, op, op, s); }
+    ResUnitParams rp{};
+    rp.x_in = X; rp.out = O; rp.w7 = W7; rp.w1 = W1; rp.b7 = b7; rp.b1 = b1;
+    rp.ea1 = ea[0]; rp.ib1 = ib[0]; rp.ea2 = ea[1]; rp.ib2 = ib[1];
+    if (out_snake) { rp.ea3 = ea[2]; rp.ib3 = ib[2]; }
+    rp.C = C; rp.dil = dil; rp.rows_per_frame = 1;
+    if (!resunit96_supported(rp, op)) return fail(Q3TTS_EINVAL, "fused residual unit not supported for this shape");
+    CUDA_OK(launch_resunit96(rp, g, op, s));
+    CUDA_OK(cudaStreamSynchronize(s));
+    {
+      std::vector<uint16_t> h0(R * C), h1(R * C);
+      CUDA_OK(cudaMemcpy(h0.data(), out_snake ? A3 : Y, R * C * 2, cudaMemcpyDeviceToHost));
+      CUDA_OK(cudaMemcpy(h1.data(), O, R * C * 2, cudaMemcpyDeviceToHost));
+      auto tof = [&](uint16_t u) {
+        if (op == DT_BF16) { uint32_t v = (uint32_t)u << 16; float f; std::memcpy(&f, &v, 4); return f; }
+        const uint32_t sgn = (u >> 15) & 1, e = (u >> 10) & 31, m = u & 1023;
+        float f = e == 0 ? ldexpf((float)m, -24) : (e == 31 ? INFINITY : ldexpf((float)(m | 1024), (int)e - 25));
+        return sgn ? -f : f;
+      };
+      float worst = 0.f;
+      for (int b = 0; b < B; ++b)
+        for (int t = 0; t < len[(size_t)b]; ++t)
+          for (int n = 0; n < C; ++n) {
+            const size_t i = ((size_t)b * rows + t) * C + n;
+            const float d = fabsf(tof(h0[i]) - tof(h1[i]));
+            if (!(d <= worst)) worst = d;
+          }
+      if (max_diff) *max_diff = worst;
+    }
+    if (iters > 0 && ms_out) {
+      cudaEvent_t e0, e1;
+      CUDA_OK(cudaEventCreate(&e0));
+      CUDA_OK(cudaEventCreate(&e1));
+      for (int i = 0; i < 2; ++i) CUDA_OK(launch_resunit96(rp, g, op, s));
+      CUDA_OK(cudaEventRecord(e0, s));
+      for (int i = 0; i < iters; ++i) CUDA_OK(launch_resunit96(rp, g, op, s));
       CUDA_OK(cudaEventRecord(e1, s));
       CUDA_OK(cudaStreamSynchronize(s));
       float ms = 0;

@@ -459,7 +459,7 @@ void run_microbatch(Model& m, const int32_t* d_codes, const int64_t* d_code_base
     m.arena_cap = need;
   }
   Plan P = make_plan(m, m.arena, B, Tmax);
-  Ctx x{m, BatchGeom{B, Tmax, d_len}, s, valid_frames};
+  Ctx x{m, BatchGeom{B, Tmax, d_len, (long long)valid_frames}, s, valid_frames};
   const int op = m.op_dtype;
   const int64_t R = (int64_t)B * Tmax;
   const int half = c.codebook_dim / 2;
@@ -554,14 +554,38 @@ void run_microbatch(Model& m, const int32_t* d_codes, const int64_t* d_code_base
     // snake(x) was applied by the producer; transposed conv -> X (stream) and A = res1.act1(X)
     { Epi e; e.out_y = P.blk[i].X; e.y_dtype = m.st_dtype; e.out_a = P.blk[i].A; e.snake = &Bk.act_in_next[0]; gemm(x, Bk.tconv, a_in, rate, e); }
     rate *= Bk.rate;
-    for (int j = 0; j < 3; ++j) {
-      { Epi e; e.out_a = P.blk[i].C; e.snake = &Bk.act2[j]; gemm(x, Bk.conv7[j], P.blk[i].A, rate, e); }
-      const SnakeW* next = (j < 2) ? &Bk.act_in_next[j + 1] : (i < 3 ? &m.block_in_snake[i + 1] : &m.out_snake);
-      { Epi e; e.res = P.blk[i].X; e.out_y = P.blk[i].X; e.y_dtype = m.st_dtype; e.out_a = P.blk[i].A; e.snake = next; gemm(x, Bk.conv1[j], P.blk[i].C, rate, e); }
+    const SnakeW* block_out = i < 3 ? &m.block_in_snake[i + 1] : &m.out_snake;
+    ResUnitParams rp{};
+    rp.C = Bk.cout; rp.rows_per_frame = rate; rp.dil = 1;
+    const bool fused = !taps && op != DT_F32 && m.st_dtype == op && Bk.conv7[0].taps == 7 && resunit96_supported(rp, op);
+    if (fused) {
+      // One kernel per residual unit (kernels_res96.cu): X is read once and written once.  The stream ping-pongs between
+      // the block's X and A buffers (a unit must not overwrite rows whose halo another CTA still reads); the last unit
+      // writes only the next consumer's operand snake(X').
+      void* bufs[4] = {P.blk[i].X, P.blk[i].A, P.blk[i].X, P.blk[i].C};
+      for (int j = 0; j < 3; ++j) {
+        rp.x_in = bufs[j]; rp.out = bufs[j + 1];
+        rp.w7 = Bk.conv7[j].w16; rp.w1 = Bk.conv1[j].w16; rp.b7 = Bk.conv7[j].bias; rp.b1 = Bk.conv1[j].bias;
+        rp.ea1 = Bk.act_in_next[j].ea; rp.ib1 = Bk.act_in_next[j].ib; rp.ea2 = Bk.act2[j].ea; rp.ib2 = Bk.act2[j].ib;
+        rp.ea3 = j == 2 ? block_out->ea : nullptr; rp.ib3 = j == 2 ? block_out->ib : nullptr;
+        rp.dil = Bk.conv7[j].dil;
+        cudaError_t err = launch_resunit96(rp, x.g, op, s);
+        if (err != cudaSuccess) throw Error(Q3TTS_ECUDA, std::string("fused residual unit launch: ") + cudaGetErrorString(err));
+        count_launch(x);
+        const double rows = (double)valid_frames * rate, C = (double)Bk.cout;
+        account(x, 2.0 * rows * 8.0 * C * C, rows * C * 2.0 * (2.0 + 6.0 * rp.dil / 128.0) + 8.0 * C * C * 2.0);
+      }
+      a_in = P.blk[i].C;
+    } else {
+      for (int j = 0; j < 3; ++j) {
+        { Epi e; e.out_a = P.blk[i].C; e.snake = &Bk.act2[j]; gemm(x, Bk.conv7[j], P.blk[i].A, rate, e); }
+        const SnakeW* next = (j < 2) ? &Bk.act_in_next[j + 1] : block_out;
+        { Epi e; e.res = P.blk[i].X; e.out_y = P.blk[i].X; e.y_dtype = m.st_dtype; e.out_a = P.blk[i].A; e.snake = next; gemm(x, Bk.conv1[j], P.blk[i].C, rate, e); }
+      }
+      a_in = P.blk[i].A;
     }
     static const char* kNames[4] = {"block0", "block1", "block2", "block3"};
     tap(x, kNames[i], P.blk[i].X, m.st_dtype, rate, Bk.cout, Bk.cout);
-    a_in = P.blk[i].A;
     stage_end(x);
   }
 

@@ -18,6 +18,7 @@ struct BatchGeom {
   int B;                   // utterances in this micro-batch
   int Tmax;                // frames per utterance slot (row stride at rate 1)
   const int* len_frames;   // [B] device: valid frames per utterance
+  long long valid_frames;  // host copy of sum(len_frames) (work-list sizing of the strip-walking kernels)
 };
 
 // Generic "multi-tap GEMM": out[b,t,n] = epi( sum_{j<taps} sum_c A[b, t-(taps-1-j)*dil, c] * W[j,n,c] ).
@@ -102,5 +103,19 @@ cudaError_t launch_conv_gemm_tc(const ConvGemmParams& p, const BatchGeom& g, int
 bool tc2_supported(const ConvGemmParams& p, int op_dtype);
 cudaError_t launch_conv_gemm_tc2(const ConvGemmParams& p, const BatchGeom& g, int op_dtype, int y_dtype,
                                  cudaStream_t s);
+
+// ---- fused residual unit of the 96-channel block (kernels_res96.cu) ------------------------------------------------
+//   out = X + conv1x1(snake2(conv7_dil(snake1(X)) + b7)) + b1        (ST.swift:430-437), or snake3(that) when ea3 != null.
+// X / out are [B, Tmax*rows_per_frame, C] 16-bit channels-last tensors (out != X: tiles of other CTAs read X's halo rows).
+struct ResUnitParams {
+  const void* x_in; void* out;
+  const void* w7; const void* w1;       // packed [7][C][C] and [1][C][C], 16-bit, Cin contiguous
+  const float *b7, *b1;
+  const float *ea1, *ib1, *ea2, *ib2;   // snake before conv7, between the convs
+  const float *ea3, *ib3;               // optional: activation of the consumer, applied to the output
+  int C, dil, rows_per_frame;
+};
+bool resunit96_supported(const ResUnitParams& p, int op_dtype);
+cudaError_t launch_resunit96(const ResUnitParams& p, const BatchGeom& g, int op_dtype, cudaStream_t s);
 
 }  // namespace q3

@@ -71,66 +71,6 @@ __device__ __forceinline__ void ld4(const float* p, float (&v)[16], int i) {
   v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
 }
 
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr) : "memory");
-}
-
-// Four per-column constants: from smem (32-bit shared address, LDS.128) or from global memory (read-only path).
-template <bool kSmem>
-__device__ __forceinline__ float4 ldc4(const float* gptr, uint32_t saddr, int off) {
-  if (kSmem) {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr + 4u * (uint32_t)off));
-    return v;
-  }
-  return __ldg((const float4*)(gptr + off));
-}
-
-// Block epilogue, one 32-row x 32-column chunk of one warp:
-//   v = acc + bias [+ res16];   y = v (16-bit, kY);   a = v + ib * sin^2(v * ea) (16-bit)
-// Each WARP stages its own 32 rows (64-byte rows, 64B swizzle) and issues its own TMA stores: no cross-warp barrier, no
-// scattered global stores, and no per-element branches.  bias / ea / ib point into smem (staged) or global memory.
-template <typename T16, bool kRes, bool kY, bool kSmem>
-__device__ __forceinline__ void epi_block_chunk(const uint32_t (&r)[32], const float* bias, const float* ea, const float* ib,
-                                                uint32_t s_bias, uint32_t s_ea, uint32_t s_ib,
-                                                const uint4 (&rres)[4], uint8_t* buf_y, uint8_t* buf_a, int lane) {
-  const uint32_t sw = (uint32_t)((lane >> 1) & 3);   // SWIZZLE_64B: 16-byte chunk index ^= address bits [7,9)
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {   // 8 columns per step
-    float v[8];
-    const float4 b0 = ldc4<kSmem>(bias, s_bias, 8 * c), b1 = ldc4<kSmem>(bias, s_bias, 8 * c + 4);
-    v[0] = __uint_as_float(r[8 * c + 0]) + b0.x; v[1] = __uint_as_float(r[8 * c + 1]) + b0.y;
-    v[2] = __uint_as_float(r[8 * c + 2]) + b0.z; v[3] = __uint_as_float(r[8 * c + 3]) + b0.w;
-    v[4] = __uint_as_float(r[8 * c + 4]) + b1.x; v[5] = __uint_as_float(r[8 * c + 5]) + b1.y;
-    v[6] = __uint_as_float(r[8 * c + 6]) + b1.z; v[7] = __uint_as_float(r[8 * c + 7]) + b1.w;
-    if (kRes) {
-      const uint4 u = rres[c];
-      const float2 r0 = Cvt<T16>::unpack(u.x), r1 = Cvt<T16>::unpack(u.y), r2 = Cvt<T16>::unpack(u.z), r3 = Cvt<T16>::unpack(u.w);
-      v[0] += r0.x; v[1] += r0.y; v[2] += r1.x; v[3] += r1.y; v[4] += r2.x; v[5] += r2.y; v[6] += r3.x; v[7] += r3.y;
-    }
-    if (kY)
-      *(uint4*)(buf_y + lane * 64 + ((c ^ sw) << 4)) = make_uint4(Cvt<T16>::pack(v[0], v[1]), Cvt<T16>::pack(v[2], v[3]),
-                                                                  Cvt<T16>::pack(v[4], v[5]), Cvt<T16>::pack(v[6], v[7]));
-    const float4 e0 = ldc4<kSmem>(ea, s_ea, 8 * c), e1 = ldc4<kSmem>(ea, s_ea, 8 * c + 4);
-    const float4 i0 = ldc4<kSmem>(ib, s_ib, 8 * c), i1 = ldc4<kSmem>(ib, s_ib, 8 * c + 4);
-    const float ee[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w}, ii[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const float sn = __sinf(v[e] * ee[e]);
-      v[e] = fmaf(ii[e], sn * sn, v[e]);
-    }
-    *(uint4*)(buf_a + lane * 64 + ((c ^ sw) << 4)) = make_uint4(Cvt<T16>::pack(v[0], v[1]), Cvt<T16>::pack(v[2], v[3]),
-                                                                Cvt<T16>::pack(v[4], v[5]), Cvt<T16>::pack(v[6], v[7]));
-  }
-}
-
 // `ntap` taps x NK k-steps of one W stage.  Descriptors advance by 2 (32 bytes) per k-step and by dA / dW per tap;
 // only the very first MMA of a tile runs with accumulate = 0.
 template <bool kPair, int NK>
@@ -423,7 +363,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
           __syncwarp();
           const int n = n0 + ch * 32;
           const uint32_t sb = cst_u32 + 4u * (uint32_t)n, se = sb + 4u * (uint32_t)p.N, si = se + 4u * (uint32_t)p.N;
-#define Q3_EPI(RES, Y, SM) epi_block_chunk<T16, RES, Y, SM>(r, p.bias + n, p.snake_ea + n, p.snake_ib + n, sb, se, si, rres, buf_y, buf_a, lane)
+#define Q3_EPI(RES, Y, SM) epi_block_chunk<T16, RES, Y, true, SM>(r, p.bias + n, p.snake_ea + n, p.snake_ib + n, sb, se, si, rres, buf_y, buf_a, lane)
           if (p.cst_staged) {
             if (has_res) { if (has_y) Q3_EPI(true, true, true); else Q3_EPI(true, false, true); }
             else { if (has_y) Q3_EPI(false, true, true); else Q3_EPI(false, false, true); }

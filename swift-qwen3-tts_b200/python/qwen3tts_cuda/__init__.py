@@ -116,6 +116,7 @@ def lib() -> C.CDLL:
         "q3tts_profile_enable": (C.c_int, [vp, i32]),
         "q3tts_profile_get": (C.c_int, [vp, C.POINTER(StageTime), i32]),
         "q3tts_launch_count": (i64, [vp]),
+        "q3tts_debug_resunit": (C.c_int, [i32, i32, i32, i32, i32, i32, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
         "q3tts_debug_conv_gemm": (C.c_int, [i32, i32, i32, i32, i32, i32, i32, i32, i32, C.POINTER(C.c_float),
                                             C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     }
@@ -139,6 +140,13 @@ def debug_conv_gemm(B: int, rows: int, Cin: int, N: int, taps: int, dil: int, mo
     ms, dy, da = C.c_float(0), C.c_float(0), C.c_float(0)
     _check(lib().q3tts_debug_conv_gemm(B, rows, Cin, N, taps, dil, mode, precision, iters, C.byref(ms), C.byref(dy), C.byref(da)))
     return float(ms.value), float(dy.value), float(da.value)
+
+
+def debug_resunit(B: int, rows: int, dil: int, out_snake: int = 0, precision: int = PREC_FP16, iters: int = 0) -> Tuple[float, float]:
+    """Kernel-level check of the fused residual unit: (ms per launch, max |fused - composed|)."""
+    ms, d = C.c_float(0), C.c_float(0)
+    _check(lib().q3tts_debug_resunit(B, rows, dil, out_snake, precision, iters, C.byref(ms), C.byref(d)))
+    return float(ms.value), float(d.value)
 
 
 def device_count() -> int:
