@@ -627,8 +627,23 @@ int q3tts_debug_resunit(int32_t B, int32_t rows, int32_t dil, int32_t out_snake,
     if (out_snake) { rp.ea3 = ea[2]; rp.ib3 = ib[2]; }
     rp.C = C; rp.dil = dil; rp.rows_per_frame = 1;
     if (!resunit96_supported(rp, op)) return fail(Q3TTS_EINVAL, "fused residual unit not supported for this shape");
+    long long* d_dbg = nullptr;
+    if (getenv("Q3TTS_RES_DEBUG")) { d_dbg = (long long*)dmalloc(16 * 32 * 8); CUDA_OK(cudaMemsetAsync(d_dbg, 0, 16 * 32 * 8, s)); rp.dbg = d_dbg; }
     CUDA_OK(launch_resunit96(rp, g, op, s));
     CUDA_OK(cudaStreamSynchronize(s));
+    if (d_dbg) {
+      std::vector<long long> h(16 * 32);
+      CUDA_OK(cudaMemcpy(h.data(), d_dbg, h.size() * 8, cudaMemcpyDeviceToHost));
+      static const char* kEv[12] = {"prod:slot_free", "-", "P:t_full", "P:done", "MMA:a_ready", "MMA:c7_issued", "MMA:c_ready", "MMA:c1_issued",
+                                    "E1:acc1_full", "E1:done", "E2:acc2_full", "E2:done"};
+      const long long t0 = h[0 * 32 + 8];
+      for (int tile = 8; tile < 20; ++tile) {
+        std::printf("tile %2d:", tile);
+        for (int ev = 0; ev < 12; ++ev) if (ev != 1) std::printf(" %s=%lld", kEv[ev], h[(size_t)ev * 32 + tile] - t0);
+        std::printf("\n");
+      }
+      rp.dbg = nullptr;
+    }
     {
       std::vector<uint16_t> h0(R * C), h1(R * C);
       CUDA_OK(cudaMemcpy(h0.data(), out_snake ? A3 : Y, R * C * 2, cudaMemcpyDeviceToHost));

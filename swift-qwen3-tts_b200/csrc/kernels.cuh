@@ -114,6 +114,7 @@ struct ResUnitParams {
   const float *ea1, *ib1, *ea2, *ib2;   // snake before conv7, between the convs
   const float *ea3, *ib3;               // optional: activation of the consumer, applied to the output
   int C, dil, rows_per_frame;
+  void* dbg;                            // optional device buffer [16][32] of clock64 stamps (pipeline debugging)
 };
 bool resunit96_supported(const ResUnitParams& p, int op_dtype);
 cudaError_t launch_resunit96(const ResUnitParams& p, const BatchGeom& g, int op_dtype, cudaStream_t s);

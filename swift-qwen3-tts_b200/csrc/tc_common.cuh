@@ -78,10 +78,12 @@ __device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.0f +
 
 template <typename T16> struct Cvt;
 template <> struct Cvt<__half> {
+  static __device__ __forceinline__ uint32_t add2(uint32_t a, uint32_t b) { __half2 h = __hadd2(*(__half2*)&a, *(__half2*)&b); return *(uint32_t*)&h; }
   static __device__ __forceinline__ uint32_t pack(float a, float b) { __half2 h = __floats2half2_rn(a, b); return *(uint32_t*)&h; }
   static __device__ __forceinline__ float2 unpack(uint32_t u) { return __half22float2(*(__half2*)&u); }
 };
 template <> struct Cvt<__nv_bfloat16> {
+  static __device__ __forceinline__ uint32_t add2(uint32_t a, uint32_t b) { __nv_bfloat162 h = __hadd2(*(__nv_bfloat162*)&a, *(__nv_bfloat162*)&b); return *(uint32_t*)&h; }
   static __device__ __forceinline__ uint32_t pack(float a, float b) { __nv_bfloat162 h = __floats2bfloat162_rn(a, b); return *(uint32_t*)&h; }
   static __device__ __forceinline__ float2 unpack(uint32_t u) { return __bfloat1622float2(*(__nv_bfloat162*)&u); }
 };
@@ -189,6 +191,21 @@ __device__ __forceinline__ uint32_t elect_one() {
   uint32_t pred;
   asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
   return pred;
+}
+
+// ---- explicit shared-memory accesses (32-bit shared addresses: guaranteed LDS / STS, no generic-address checks) ---
+__device__ __forceinline__ uint4 lds128(uint32_t saddr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ float4 lds4f(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
 // ---- shared pieces of the fused epilogues ---------------------------------------------------------------------
