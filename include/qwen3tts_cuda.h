@@ -178,6 +178,15 @@ typedef struct q3tts_stage_time {
 } q3tts_stage_time;
 int q3tts_profile_enable(q3tts_model* m, int32_t enable);
 int q3tts_profile_get(q3tts_model* m, q3tts_stage_time* out, int32_t cap);
+/* Per-kernel CUDA-event timing of the most recent profiled decode, aggregated by "stage.op" label
+ * (events bracket each launch on the launch stream); flops / bytes are the algorithmic work.     */
+typedef struct q3tts_kernel_time {
+  char name[48];
+  float ms;            /* sum over the launches of this label                                    */
+  int32_t launches;
+  double flops, bytes; /* summed algorithmic FLOPs / HBM bytes of those launches                 */
+} q3tts_kernel_time;
+int q3tts_profile_kernels(q3tts_model* m, q3tts_kernel_time* out, int32_t cap);
 /* Kernels launched by this model since load (all decodes).                                      */
 int64_t q3tts_launch_count(const q3tts_model* m);
 

@@ -119,8 +119,10 @@ void decode_core(Model& m, const int32_t* d_codes, std::vector<Utt> utts, int64_
   const int* d_len = (const int*)(m.d_meta + o_len);
   const int64_t* d_cb = (const int64_t*)(m.d_meta + o_cb);
   const int64_t* d_pb = (const int64_t*)(m.d_meta + o_pb);
-  if (m.profile_enabled)
+  if (m.profile_enabled) {
     for (auto& sp : m.prof) { sp.used = false; sp.ms_accum = 0; sp.flops = 0; sp.bytes = 0; sp.launches = 0; }
+    m.kernel_totals.clear();
+  }
   for (auto& mb : mbs) {
     int64_t valid = 0;
     for (int i = 0; i < mb.B; ++i) valid += utts[(size_t)(mb.first + i)].frames;
@@ -132,6 +134,16 @@ void decode_core(Model& m, const int32_t* d_codes, std::vector<Utt> utts, int64_
           float ms = 0;
           if (cudaEventElapsedTime(&ms, sp.ev0, sp.ev1) == cudaSuccess) sp.ms_accum += ms;
         }
+      for (auto& lp : m.launch_prof) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, lp.ev0, lp.ev1) == cudaSuccess) {
+          auto& t = m.kernel_totals[lp.label];
+          t[0] += ms; t[1] += 1; t[2] += lp.flops; t[3] += lp.bytes;
+        }
+        m.event_pool.push_back(lp.ev0);
+        m.event_pool.push_back(lp.ev1);
+      }
+      m.launch_prof.clear();
     }
   }
   if (d_lengths) {
@@ -706,6 +718,24 @@ int q3tts_profile_get(q3tts_model* h, q3tts_stage_time* out, int32_t cap) {
       out[n].launches = sp.launches;
       out[n].flops = sp.flops;
       out[n].bytes = sp.bytes;
+    }
+    ++n;
+  }
+  return n;
+}
+
+int q3tts_profile_kernels(q3tts_model* h, q3tts_kernel_time* out, int32_t cap) {
+  if (!h || (!out && cap > 0)) return 0;
+  std::lock_guard<std::mutex> lock(h->m->mu);
+  int n = 0;
+  for (auto& kv : h->m->kernel_totals) {
+    if (n < cap) {
+      std::memset(&out[n], 0, sizeof(out[n]));
+      std::snprintf(out[n].name, sizeof(out[n].name), "%s", kv.first.c_str());
+      out[n].ms = (float)kv.second[0];
+      out[n].launches = (int32_t)kv.second[1];
+      out[n].flops = kv.second[2];
+      out[n].bytes = kv.second[3];
     }
     ++n;
   }

@@ -31,6 +31,8 @@ Model::~Model() {
   if (h_err) cudaFreeHost(h_err);
   for (auto& t : taps) if (t.second.d) cudaFree(t.second.d);
   for (auto& p : prof) { if (p.ev0) cudaEventDestroy(p.ev0); if (p.ev1) cudaEventDestroy(p.ev1); }
+  for (auto& lp : launch_prof) { if (lp.ev0) cudaEventDestroy(lp.ev0); if (lp.ev1) cudaEventDestroy(lp.ev1); }
+  for (cudaEvent_t e : event_pool) cudaEventDestroy(e);
   if (stream) cudaStreamDestroy(stream);
 }
 
@@ -371,6 +373,27 @@ void count_launch(Ctx& x, int n = 1) {
   if (x.m.profile_enabled && x.cur_stage >= 0) x.m.prof[(size_t)x.cur_stage].launches += n;
 }
 
+cudaEvent_t pooled_event(Model& m) {
+  if (!m.event_pool.empty()) { cudaEvent_t e = m.event_pool.back(); m.event_pool.pop_back(); return e; }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+// Per-launch timing (profile mode): events bracket ONE kernel launch on the launch stream.
+void launch_begin(Ctx& x, const char* op, double flops, double bytes) {
+  if (!x.m.profile_enabled || x.cur_stage < 0) return;
+  LaunchProfile lp;
+  lp.label = x.m.prof[(size_t)x.cur_stage].name + "." + op;
+  lp.flops = flops; lp.bytes = bytes;
+  lp.ev0 = pooled_event(x.m); lp.ev1 = pooled_event(x.m);
+  cudaEventRecord(lp.ev0, x.s);
+  x.m.launch_prof.push_back(lp);
+}
+void launch_end(Ctx& x) {
+  if (!x.m.profile_enabled || x.cur_stage < 0 || x.m.launch_prof.empty()) return;
+  cudaEventRecord(x.m.launch_prof.back().ev1, x.s);
+}
+
 float* tap_buffer(Model& m, const std::string& name, int B, int C, int64_t L) {
   TapBuf& t = m.taps[name];
   const size_t need = (size_t)B * C * L * 4;
@@ -402,7 +425,7 @@ struct Epi {
 };
 
 // One multi-tap GEMM over the micro-batch.  A: [B, Tmax*rpf, Cin] operand; outputs have N (or N/2) columns.
-void gemm(Ctx& x, const GemmW& w, const void* A, int rows_per_frame, const Epi& e) {
+void gemm(Ctx& x, const GemmW& w, const void* A, int rows_per_frame, const Epi& e, const char* op = "gemm") {
   Model& m = x.m;
   ConvGemmParams p{};
   const int64_t slot = (int64_t)x.g.Tmax * rows_per_frame;
@@ -430,6 +453,7 @@ void gemm(Ctx& x, const GemmW& w, const void* A, int rows_per_frame, const Epi& 
     if (e.out_y) bytes += rows * outN * dt_size(y_dtype);
     if (e.out_a) bytes += rows * outN * ops;
     account(x, 2.0 * rows * w.taps * w.N * w.Cin, bytes);
+    launch_begin(x, op, 2.0 * rows * w.taps * w.N * w.Cin, bytes);
   }
   if (m.op_dtype != DT_F32 && tc2_supported(p, m.op_dtype)) {
     cudaError_t err = launch_conv_gemm_tc2(p, x.g, m.op_dtype, y_dtype, x.s);
@@ -440,6 +464,7 @@ void gemm(Ctx& x, const GemmW& w, const void* A, int rows_per_frame, const Epi& 
   } else {
     launch_conv_gemm_simt(p, x.g, m.op_dtype, y_dtype, x.s);
   }
+  launch_end(x);
   count_launch(x);
 }
 
@@ -485,39 +510,45 @@ void run_microbatch(Model& m, const int32_t* d_codes, const int64_t* d_code_base
       count_launch(x, 2);
     }
     Epi e; e.out_a = P.QP;
-    gemm(x, m.rvq_proj, P.Q, 1, e);
+    gemm(x, m.rvq_proj, P.Q, 1, e, "proj");
     tap(x, "quantized", P.QP, op, 1, c.codebook_dim, c.codebook_dim);
   }
   stage_end(x);
 
   // 2. pre_conv (ST.swift:724-728, 759)
   stage_begin(x, 1);
-  { Epi e; e.out_a = P.PC; gemm(x, m.pre_conv, P.QP, 1, e); }
+  { Epi e; e.out_a = P.PC; gemm(x, m.pre_conv, P.QP, 1, e, "conv3"); }
   tap(x, "pre_conv", P.PC, op, 1, c.latent_dim, c.latent_dim);
   stage_end(x);
 
   // 3. pre_transformer (ST.swift:629-643)
   stage_begin(x, 2);
-  { Epi e; e.out_y = P.H; e.y_dtype = DT_F32; gemm(x, m.in_proj, P.PC, 1, e); }
+  { Epi e; e.out_y = P.H; e.y_dtype = DT_F32; gemm(x, m.in_proj, P.PC, 1, e, "in_proj"); }
   const float scale = 1.0f / sqrtf((float)c.head_dim);   // ST.swift:502
   const int window = (m.opts.attn_mode == Q3TTS_ATTN_CAUSAL_SW) ? c.sliding_window : 0;
   for (auto& L : m.layers) {
     launch_rmsnorm(P.H, L.ln1, c.rms_norm_eps, P.NB, op, R, c.hidden_size, s); count_launch(x);
-    { Epi e; e.out_a = P.QKV; gemm(x, L.qkv, P.NB, 1, e); }
+    { Epi e; e.out_a = P.QKV; gemm(x, L.qkv, P.NB, 1, e, "qkv"); }
+    {
+      const double tkv0 = window > 0 ? std::min<double>(window, (double)valid_frames / B) : (double)valid_frames / B;
+      launch_begin(x, "attention", 4.0 * c.num_attention_heads * c.head_dim * tkv0 * valid_frames,
+                   (double)valid_frames * ((double)(c.num_attention_heads + 2 * c.num_key_value_heads) * c.head_dim + (double)c.num_attention_heads * c.head_dim) * dt_size(op));
+    }
     launch_attention(P.QKV, op, P.AO, op, x.g, c.num_attention_heads, c.num_key_value_heads, c.head_dim, scale, window, s);
+    launch_end(x);
     count_launch(x);
     {  // 4*nh*hd*T_kv FLOP per query frame; keys = own utterance (approximated by the mean valid length)
       const double tkv = window > 0 ? std::min<double>(window, (double)valid_frames / B) : (double)valid_frames / B;
       account(x, 4.0 * c.num_attention_heads * c.head_dim * tkv * valid_frames,
               (double)valid_frames * ((double)(c.num_attention_heads + 2 * c.num_key_value_heads) * c.head_dim + (double)c.num_attention_heads * c.head_dim) * dt_size(op));
     }
-    { Epi e; e.res = P.H; e.scale = L.ls_attn; e.out_y = P.H; e.y_dtype = DT_F32; gemm(x, L.o, P.AO, 1, e); }
+    { Epi e; e.res = P.H; e.scale = L.ls_attn; e.out_y = P.H; e.y_dtype = DT_F32; gemm(x, L.o, P.AO, 1, e, "o_proj"); }
     launch_rmsnorm(P.H, L.ln2, c.rms_norm_eps, P.NB, op, R, c.hidden_size, s); count_launch(x);
-    { Epi e; e.act = ACT_SWIGLU; e.out_a = P.GU; gemm(x, L.gate_up, P.NB, 1, e); }
-    { Epi e; e.res = P.H; e.scale = L.ls_mlp; e.out_y = P.H; e.y_dtype = DT_F32; gemm(x, L.down, P.GU, 1, e); }
+    { Epi e; e.act = ACT_SWIGLU; e.out_a = P.GU; gemm(x, L.gate_up, P.NB, 1, e, "gate_up"); }
+    { Epi e; e.res = P.H; e.scale = L.ls_mlp; e.out_y = P.H; e.y_dtype = DT_F32; gemm(x, L.down, P.GU, 1, e, "down"); }
   }
   launch_rmsnorm(P.H, m.final_norm, c.rms_norm_eps, P.NB, op, R, c.hidden_size, s); count_launch(x);
-  { Epi e; e.out_a = P.TO; gemm(x, m.out_proj, P.NB, 1, e); }
+  { Epi e; e.out_a = P.TO; gemm(x, m.out_proj, P.NB, 1, e, "out_proj"); }
   tap(x, "pre_transformer", P.TO, op, 1, c.latent_dim, c.latent_dim);
   stage_end(x);
 
@@ -527,12 +558,14 @@ void run_microbatch(Model& m, const int32_t* d_codes, const int64_t* d_code_base
   int rate = 1;
   for (size_t i = 0; i < m.ups.size(); ++i) {
     UpsampleW& U = m.ups[i];
-    { Epi e; e.out_y = P.up[i].X; e.y_dtype = DT_F32; gemm(x, U.tconv, cur, rate, e); }   // [T*rate, r*L] == [T*rate*r, L]
+    { Epi e; e.out_y = P.up[i].X; e.y_dtype = DT_F32; gemm(x, U.tconv, cur, rate, e, "convT"); }   // [T*rate, r*L] == [T*rate*r, L]
     rate *= U.ratio;
+    launch_begin(x, "dwconv_ln", 2.0 * 7 * c.latent_dim * (double)valid_frames * rate, (double)valid_frames * rate * c.latent_dim * (4.0 + dt_size(op)));
     launch_dwconv_ln(P.up[i].X, U.dw_w, U.dw_b, U.ln_w, U.ln_b, 1e-6f, P.up[i].N, op, x.g, rate, c.latent_dim, s);
+    launch_end(x);
     count_launch(x);
-    { Epi e; e.act = ACT_GELU; e.out_a = P.up[i].G; gemm(x, U.pw1, P.up[i].N, rate, e); }
-    { Epi e; e.res = P.up[i].X; e.scale = U.gamma; e.y_dtype = DT_F32; e.out_a = P.up[i].XO; gemm(x, U.pw2, P.up[i].G, rate, e); }
+    { Epi e; e.act = ACT_GELU; e.out_a = P.up[i].G; gemm(x, U.pw1, P.up[i].N, rate, e, "pw1"); }
+    { Epi e; e.res = P.up[i].X; e.scale = U.gamma; e.y_dtype = DT_F32; e.out_a = P.up[i].XO; gemm(x, U.pw2, P.up[i].G, rate, e, "pw2"); }
     cur = P.up[i].XO;
     tap(x, i == 0 ? "upsample0" : "upsample1", cur, op, rate, c.latent_dim, c.latent_dim);
   }
@@ -543,7 +576,7 @@ void run_microbatch(Model& m, const int32_t* d_codes, const int64_t* d_code_base
   {
     Epi e; e.out_a = P.A0; e.snake = &m.block_in_snake[0];
     if (taps) e.out_tap = tap_buffer(m, "init_conv_cl", B, c.decoder_dim, (int64_t)Tmax * rate);
-    gemm(x, m.init_conv, cur, rate, e);
+    gemm(x, m.init_conv, cur, rate, e, "conv7");
     if (taps) tap(x, "init_conv", m.taps["init_conv_cl"].d, DT_F32, rate, c.decoder_dim, c.decoder_dim);
   }
   stage_end(x);
@@ -552,12 +585,16 @@ void run_microbatch(Model& m, const int32_t* d_codes, const int64_t* d_code_base
     stage_begin(x, 5 + i);
     BlockW& Bk = m.blocks[i];
     // snake(x) was applied by the producer; transposed conv -> X (stream) and A = res1.act1(X)
-    { Epi e; e.out_y = P.blk[i].X; e.y_dtype = m.st_dtype; e.out_a = P.blk[i].A; e.snake = &Bk.act_in_next[0]; gemm(x, Bk.tconv, a_in, rate, e); }
-    rate *= Bk.rate;
     const SnakeW* block_out = i < 3 ? &m.block_in_snake[i + 1] : &m.out_snake;
     ResUnitParams rp{};
-    rp.C = Bk.cout; rp.rows_per_frame = rate; rp.dil = 1;
+    rp.C = Bk.cout; rp.rows_per_frame = rate * Bk.rate; rp.dil = 1;
     const bool fused = !taps && op != DT_F32 && m.st_dtype == op && Bk.conv7[0].taps == 7 && resunit96_supported(rp, op);
+    {
+      Epi e; e.out_y = P.blk[i].X; e.y_dtype = m.st_dtype;
+      if (!fused) { e.out_a = P.blk[i].A; e.snake = &Bk.act_in_next[0]; }   // the fused units activate their own input
+      gemm(x, Bk.tconv, a_in, rate, e, "convT");
+    }
+    rate *= Bk.rate;
     if (fused) {
       // One kernel per residual unit (kernels_res96.cu): X is read once and written once.  The stream ping-pongs between
       // the block's X and A buffers (a unit must not overwrite rows whose halo another CTA still reads); the last unit
@@ -569,18 +606,21 @@ void run_microbatch(Model& m, const int32_t* d_codes, const int64_t* d_code_base
         rp.ea1 = Bk.act_in_next[j].ea; rp.ib1 = Bk.act_in_next[j].ib; rp.ea2 = Bk.act2[j].ea; rp.ib2 = Bk.act2[j].ib;
         rp.ea3 = j == 2 ? block_out->ea : nullptr; rp.ib3 = j == 2 ? block_out->ib : nullptr;
         rp.dil = Bk.conv7[j].dil;
+        const double rows = (double)valid_frames * rate, C = (double)Bk.cout;
+        const double fl = 2.0 * rows * 8.0 * C * C, by = rows * C * 2.0 * 2.0 + 8.0 * C * C * 2.0;   // X in, X' out (the halo stays on chip), weights once
+        launch_begin(x, "resunit", fl, by);
         cudaError_t err = launch_resunit96(rp, x.g, op, s);
         if (err != cudaSuccess) throw Error(Q3TTS_ECUDA, std::string("fused residual unit launch: ") + cudaGetErrorString(err));
+        launch_end(x);
         count_launch(x);
-        const double rows = (double)valid_frames * rate, C = (double)Bk.cout;
-        account(x, 2.0 * rows * 8.0 * C * C, rows * C * 2.0 * (2.0 + 6.0 * rp.dil / 128.0) + 8.0 * C * C * 2.0);
+        account(x, fl, by);
       }
       a_in = P.blk[i].C;
     } else {
       for (int j = 0; j < 3; ++j) {
-        { Epi e; e.out_a = P.blk[i].C; e.snake = &Bk.act2[j]; gemm(x, Bk.conv7[j], P.blk[i].A, rate, e); }
+        { Epi e; e.out_a = P.blk[i].C; e.snake = &Bk.act2[j]; gemm(x, Bk.conv7[j], P.blk[i].A, rate, e, "conv7"); }
         const SnakeW* next = (j < 2) ? &Bk.act_in_next[j + 1] : block_out;
-        { Epi e; e.res = P.blk[i].X; e.out_y = P.blk[i].X; e.y_dtype = m.st_dtype; e.out_a = P.blk[i].A; e.snake = next; gemm(x, Bk.conv1[j], P.blk[i].C, rate, e); }
+        { Epi e; e.res = P.blk[i].X; e.out_y = P.blk[i].X; e.y_dtype = m.st_dtype; e.out_a = P.blk[i].A; e.snake = next; gemm(x, Bk.conv1[j], P.blk[i].C, rate, e, "conv1"); }
       }
       a_in = P.blk[i].A;
     }
@@ -594,7 +634,9 @@ void run_microbatch(Model& m, const int32_t* d_codes, const int64_t* d_code_base
   {
     const int C = m.blocks[3].cout;
     float* tp = taps ? tap_buffer(m, "out_conv", B, 1, (int64_t)Tmax * rate) : nullptr;
+    launch_begin(x, "conv7_clip", 2.0 * 7 * C * (double)valid_frames * rate, (double)valid_frames * rate * (C * (double)dt_size(op) + 4.0));
     launch_tail(a_in, op, (int64_t)Tmax * rate * C, m.tail_w, m.tail_bias, C, d_pcm, d_pcm_base, tp, (int64_t)Tmax * rate, x.g, rate, s);
+    launch_end(x);
     count_launch(x);
     account(x, 2.0 * 7 * C * (double)valid_frames * rate, (double)valid_frames * rate * (C * (double)dt_size(op) + 4.0));
   }

@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <array>
 #include <map>
 #include <mutex>
 #include <string>
@@ -50,6 +51,9 @@ struct StageProfile {
   float ms_accum = 0;
 };
 
+// One launch of the most recent profiled decode (profile mode only): label = stage.op, events on the launch stream.
+struct LaunchProfile { std::string label; cudaEvent_t ev0 = nullptr, ev1 = nullptr; double flops = 0, bytes = 0; };
+
 struct TapBuf { float* d = nullptr; int B = 0, C = 0; int64_t L = 0; size_t cap = 0; };
 
 struct Model {
@@ -95,6 +99,9 @@ struct Model {
   std::map<std::string, TapBuf> taps;
   bool profile_enabled = false;
   std::vector<StageProfile> prof;
+  std::vector<LaunchProfile> launch_prof;   // per-launch records of the current profiled decode
+  std::vector<cudaEvent_t> event_pool;      // recycled events
+  std::map<std::string, std::array<double, 4>> kernel_totals;   // label -> {ms, launches, flops, bytes}
   int64_t launches = 0;
 
   ~Model();

@@ -145,8 +145,8 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   if (kBlockEpi && p.cst_staged && warp >= 4) {
     for (int i = (int)threadIdx.x - 128; i < p.N; i += kEpiWarps * 32) {
       cst[i] = __ldg(p.bias + i);
-      cst[p.N + i] = __ldg(p.snake_ea + i);
-      cst[2 * p.N + i] = __ldg(p.snake_ib + i);
+      cst[p.N + i] = p.snake_ea ? __ldg(p.snake_ea + i) : 0.f;
+      cst[2 * p.N + i] = p.snake_ib ? __ldg(p.snake_ib + i) : 0.f;
     }
   }
   tc_fence_before();
@@ -331,7 +331,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     // ================= block epilogue (12 warps) =================
     const int ew = warp - 4, quarter = warp & 3, grp = ew >> 2;          // grp 0..2 takes chunks grp, grp+3, ...
     const int nch = p.BN / 32;
-    const bool has_res = p.res != nullptr, has_y = p.out_y != nullptr;
+    const bool has_res = p.res != nullptr, has_y = p.out_y != nullptr, has_a = p.out_a != nullptr;
     uint8_t* buf_a = staging + (size_t)ew * (has_y ? 4096 : 2048);       // this warp's 32 rows x 64 B: a, then y
     uint8_t* buf_y = buf_a + 2048;
     const int slot_rows = p.Tmax * p.rows_per_frame;
@@ -364,7 +364,10 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
           const int n = n0 + ch * 32;
           const uint32_t sb = cst_u32 + 4u * (uint32_t)n, se = sb + 4u * (uint32_t)p.N, si = se + 4u * (uint32_t)p.N;
 #define Q3_EPI(RES, Y, SM) epi_block_chunk<T16, RES, Y, true, SM>(r, p.bias + n, p.snake_ea + n, p.snake_ib + n, sb, se, si, rres, buf_y, buf_a, lane)
-          if (p.cst_staged) {
+#define Q3_EPI_Y(SM) epi_block_chunk<T16, false, true, false, SM>(r, p.bias + n, nullptr, nullptr, sb, se, si, rres, buf_y, buf_a, lane)
+          if (!has_a) {   // stream output only (the consumer applies its own activation)
+            if (p.cst_staged) Q3_EPI_Y(true); else Q3_EPI_Y(false);
+          } else if (p.cst_staged) {
             if (has_res) { if (has_y) Q3_EPI(true, true, true); else Q3_EPI(true, false, true); }
             else { if (has_y) Q3_EPI(false, true, true); else Q3_EPI(false, false, true); }
           } else {
@@ -372,11 +375,12 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             else { if (has_y) Q3_EPI(false, true, false); else Q3_EPI(false, false, false); }
           }
 #undef Q3_EPI
+#undef Q3_EPI_Y
           fence_async_smem();
           __syncwarp();
           if (lane == 0) {
             if (has_y) tma_store_3d(&map_y, buf_y, n, t0 + quarter * 32, b);
-            tma_store_3d(&map_o, buf_a, n, t0 + quarter * 32, b);
+            if (has_a) tma_store_3d(&map_o, buf_a, n, t0 + quarter * 32, b);
             tma_store_commit();
           }
         }
@@ -570,7 +574,8 @@ int pick_bn2(int N, bool prefer32 = false) {
 }
 // The block epilogue: bias + [16-bit residual] + [16-bit stream out] + SnakeBeta operand out, nothing else.
 bool block_epilogue_ok(const ConvGemmParams& p, int y_dtype) {
-  return p.out_a && p.snake_ea && p.bias && p.act == ACT_NONE && !p.out_tap && !p.scale &&
+  const bool with_a = p.out_a && p.snake_ea, y_only = !p.out_a && !p.snake_ea && p.out_y && !p.res;
+  return (with_a || y_only) && p.bias && p.act == ACT_NONE && !p.out_tap && !p.scale &&
          (!p.res || (p.out_y && p.res == p.out_y)) && (!p.out_y || y_dtype != DT_F32) && pick_bn2(p.N, true) % 32 == 0 &&
          pick_bn2(p.N, true) >= 64;
 }

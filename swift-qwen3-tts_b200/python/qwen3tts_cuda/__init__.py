@@ -61,6 +61,11 @@ class Config(C.Structure):
         ("num_parameters", C.c_int64)]
 
 
+class KernelTime(C.Structure):
+    _fields_ = [("name", C.c_char * 48), ("ms", C.c_float), ("launches", C.c_int32),
+                ("flops", C.c_double), ("bytes", C.c_double)]
+
+
 class StageTime(C.Structure):
     _fields_ = [("name", C.c_char * 32), ("ms", C.c_float), ("launches", C.c_int32),
                 ("flops", C.c_double), ("bytes", C.c_double)]
@@ -115,6 +120,7 @@ def lib() -> C.CDLL:
         "q3tts_write_wav": (C.c_int, [cp, vp, i64, i32]),
         "q3tts_profile_enable": (C.c_int, [vp, i32]),
         "q3tts_profile_get": (C.c_int, [vp, C.POINTER(StageTime), i32]),
+        "q3tts_profile_kernels": (C.c_int, [vp, C.POINTER(KernelTime), i32]),
         "q3tts_launch_count": (i64, [vp]),
         "q3tts_debug_resunit": (C.c_int, [i32, i32, i32, i32, i32, i32, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
         "q3tts_debug_conv_gemm": (C.c_int, [i32, i32, i32, i32, i32, i32, i32, i32, i32, C.POINTER(C.c_float),
@@ -313,6 +319,13 @@ class Qwen3TTSSpeechTokenizer:
         n = lib().q3tts_profile_get(self._h, arr, 32)
         return [dict(name=arr[i].name.decode(), ms=float(arr[i].ms), launches=int(arr[i].launches),
                      flops=float(arr[i].flops), bytes=float(arr[i].bytes)) for i in range(min(n, 32))]
+
+    def profile_kernels(self):
+        """Per-kernel timing of the last profiled decode, aggregated by "stage.op"."""
+        arr = (KernelTime * 128)()
+        n = lib().q3tts_profile_kernels(self._h, arr, 128)
+        return [dict(name=arr[i].name.decode(), ms=float(arr[i].ms), launches=int(arr[i].launches),
+                     flops=float(arr[i].flops), bytes=float(arr[i].bytes)) for i in range(min(n, 128))]
 
     def launch_count(self) -> int:
         return int(lib().q3tts_launch_count(self._h))
