@@ -143,13 +143,17 @@ int q3tts_weight_shape(const q3tts_model* m, const char* swift_key, int32_t* ndi
 /* ---- streaming (chunked decode with causal state carry; Q3TTS_ATTN_CAUSAL_SW only) ------------
  * The reference has no chunked PCM streaming (Qwen3+Streaming.swift:19-120 emits one final
  * .audio); correctness here is chunk-invariance: concatenated chunk PCM == one-shot decode in
- * the same mode.  A stream is pinned to the model's GPU for life.                              */
+ * the same mode.  A stream is pinned to the model's GPU for life.  State per stream (device): the last 2
+ * pre_conv inputs, K/V of the last sliding_window-1 frames per transformer layer, and the last 10
+ * pre-transformer outputs (the conv stack is re-run over its 10-frame receptive field per chunk).   */
 int q3tts_stream_open(q3tts_model* m, q3tts_stream** out);
 /* codes: int32 [n_frames,16]; pcm_out: float [n_frames*total_upsample].                        */
 int q3tts_stream_push(q3tts_stream* s, const int32_t* codes, int32_t n_frames, float* pcm_out);
 /* Push one chunk for each of n streams in ONE batched launch chain (config 5).                 */
 int q3tts_stream_push_batch(q3tts_stream* const* streams, int32_t n_streams,
                             const int32_t* const* codes, const int32_t* n_frames, float* const* pcm_out);
+/* Frames pushed so far (-1 for a NULL / closed stream). */
+int64_t q3tts_stream_frames(const q3tts_stream* s);
 void q3tts_stream_close(q3tts_stream* s);
 
 /* ---- batch scheduler (host-only, no CUDA) ------------------------------------------------------

@@ -166,7 +166,7 @@ void check_device_errors(Model& m, cudaStream_t s) {
 }  // namespace
 
 struct q3tts_model { Model* m; };
-struct q3tts_stream { q3tts_model* owner; };
+struct q3tts_stream { q3tts_model* owner; StreamState state; };
 
 extern "C" {
 
@@ -389,18 +389,94 @@ int q3tts_weight_shape(const q3tts_model* h, const char* key, int32_t* ndim, int
   return Q3TTS_OK;
 }
 
-// ---- streaming (implemented in a later milestone) ------------------------------------------------------
-int q3tts_stream_open(q3tts_model*, q3tts_stream** out) {
-  if (out) *out = nullptr;
-  return fail(Q3TTS_ESTATE, "chunked streaming is not available in this build");
+// ---- streaming: chunked decode with causal state carry (no counterpart in the reference) -------------------
+static int stream_push_common(q3tts_stream* const* streams, int32_t n_streams, const int32_t* const* codes, const int32_t* n_frames,
+                              float* const* pcm_out) {
+  return guarded([&]() {
+    if (n_streams < 0) return fail(Q3TTS_EINVAL, "negative stream count");
+    if (n_streams == 0) return (int)Q3TTS_OK;
+    if (!streams || !codes || !n_frames || !pcm_out) return fail(Q3TTS_EINVAL, "NULL argument");
+    q3tts_model* owner = nullptr;
+    int64_t total = 0;
+    for (int i = 0; i < n_streams; ++i) {
+      if (!streams[i] || !streams[i]->owner) return fail(Q3TTS_ESTATE, "push on a closed or NULL stream");
+      if (!owner) owner = streams[i]->owner;
+      if (streams[i]->owner != owner) return fail(Q3TTS_EINVAL, "all streams of one batched push must belong to the same model (one GPU)");
+      if (n_frames[i] < 0) return fail(Q3TTS_EINVAL, "negative frame count");
+      if (n_frames[i] > 0 && (!codes[i] || !pcm_out[i])) return fail(Q3TTS_EINVAL, "NULL buffer");
+      for (int j = 0; j < i; ++j)
+        if (streams[j] == streams[i]) return fail(Q3TTS_EINVAL, "a stream appears twice in one batched push");
+      total += n_frames[i];
+    }
+    if (total == 0) return (int)Q3TTS_OK;
+    Model& m = *owner->m;
+    std::lock_guard<std::mutex> lock(m.mu);
+    CUDA_OK(cudaSetDevice(m.device));
+    const int Q = m.cfg.num_quantizers;
+    const int64_t up = m.cfg.total_upsample;
+    cudaStream_t s = m.stream;
+    ensure_dev(&m.d_codes, &m.d_codes_cap, (size_t)total * Q * 4);
+    ensure_dev(&m.d_pcm, &m.d_pcm_cap, (size_t)total * up * 4);
+    std::vector<StreamState*> st((size_t)n_streams);
+    int64_t off = 0;
+    for (int i = 0; i < n_streams; ++i) {
+      st[(size_t)i] = &streams[i]->state;
+      if (n_frames[i] > 0)
+        CUDA_OK(cudaMemcpyAsync(m.d_codes + off * Q, codes[i], (size_t)n_frames[i] * Q * 4, cudaMemcpyHostToDevice, s));
+      off += n_frames[i];
+    }
+    run_stream_batch(m, st.data(), n_streams, m.d_codes, n_frames, m.d_pcm, s);
+    off = 0;
+    for (int i = 0; i < n_streams; ++i) {
+      if (n_frames[i] > 0)
+        CUDA_OK(cudaMemcpyAsync(pcm_out[i], m.d_pcm + off * up, (size_t)n_frames[i] * up * 4, cudaMemcpyDeviceToHost, s));
+      off += n_frames[i];
+    }
+    check_device_errors(m, s);
+    return (int)Q3TTS_OK;
+  });
 }
-int q3tts_stream_push(q3tts_stream*, const int32_t*, int32_t, float*) {
-  return fail(Q3TTS_ESTATE, "chunked streaming is not available in this build");
+
+int q3tts_stream_open(q3tts_model* h, q3tts_stream** out) {
+  return guarded([&]() {
+    if (out) *out = nullptr;
+    if (!h || !out) return fail(Q3TTS_EINVAL, "NULL argument");
+    Model& m = *h->m;
+    if (m.opts.attn_mode != Q3TTS_ATTN_CAUSAL_SW)
+      return fail(Q3TTS_ESTATE, "chunked streaming needs Q3TTS_ATTN_CAUSAL_SW: the reference's full bidirectional attention (ST.swift:512-528, 763) makes every sample depend on the whole utterance");
+    if (m.cfg.sliding_window < 1) return fail(Q3TTS_EFORMAT, "sliding_window must be >= 1 for streaming");
+    std::lock_guard<std::mutex> lock(m.mu);
+    CUDA_OK(cudaSetDevice(m.device));
+    std::unique_ptr<q3tts_stream> st(new q3tts_stream{h, StreamState{}});
+    stream_state_alloc(m, st->state);
+    *out = st.release();
+    return (int)Q3TTS_OK;
+  });
 }
-int q3tts_stream_push_batch(q3tts_stream* const*, int32_t, const int32_t* const*, const int32_t*, float* const*) {
-  return fail(Q3TTS_ESTATE, "chunked streaming is not available in this build");
+
+int q3tts_stream_push(q3tts_stream* s, const int32_t* codes, int32_t n_frames, float* pcm_out) {
+  q3tts_stream* one[1] = {s};
+  const int32_t* c1[1] = {codes};
+  float* p1[1] = {pcm_out};
+  return stream_push_common(one, 1, c1, &n_frames, p1);
 }
-void q3tts_stream_close(q3tts_stream*) {}
+
+int q3tts_stream_push_batch(q3tts_stream* const* streams, int32_t n_streams, const int32_t* const* codes, const int32_t* n_frames,
+                            float* const* pcm_out) {
+  return stream_push_common(streams, n_streams, codes, n_frames, pcm_out);
+}
+
+int64_t q3tts_stream_frames(const q3tts_stream* s) { return s && s->owner ? s->state.frames_done : -1; }
+
+void q3tts_stream_close(q3tts_stream* s) {
+  if (!s) return;
+  if (s->owner) {
+    std::lock_guard<std::mutex> lock(s->owner->m->mu);
+    cudaStreamSynchronize(s->owner->m->stream);
+    stream_state_free(*s->owner->m, s->state);
+  }
+  delete s;
+}
 
 // ---- scheduler ------------------------------------------------------------------------------------------
 int q3tts_partition_lpt(const int64_t* frames, int32_t n, int32_t parts, int32_t* part_out) {

@@ -27,6 +27,8 @@ Model::~Model() {
   if (d_lengths) cudaFree(d_lengths);
   if (d_meta) cudaFree(d_meta);
   if (h_meta) cudaFreeHost(h_meta);
+  if (stream_ws) cudaFree(stream_ws);
+  if (stream_meta_h) cudaFreeHost(stream_meta_h);
   if (d_err) cudaFree(d_err);
   if (h_err) cudaFreeHost(h_err);
   for (auto& t : taps) if (t.second.d) cudaFree(t.second.d);
@@ -416,6 +418,7 @@ void tap(Ctx& x, const char* name, const void* src, int dtype, int rows_per_fram
 }
 
 struct Epi {
+  int64_t a_bstride = -1, out_bstride = -1;   // elements between slots of A / of every output; -1 = dense [B, Tmax*rpf, C]
   int act = ACT_NONE;
   const void* res = nullptr; const float* scale = nullptr;
   void* out_y = nullptr; int y_dtype = DT_F32;
@@ -429,22 +432,23 @@ void gemm(Ctx& x, const GemmW& w, const void* A, int rows_per_frame, const Epi& 
   Model& m = x.m;
   ConvGemmParams p{};
   const int64_t slot = (int64_t)x.g.Tmax * rows_per_frame;
-  p.A = A; p.lda = w.Cin; p.a_bstride = slot * w.Cin;
+  p.A = A; p.lda = w.Cin; p.a_bstride = e.a_bstride >= 0 ? e.a_bstride : slot * w.Cin;
   p.W = (m.op_dtype == DT_F32) ? (const void*)w.w32 : (const void*)w.w16;
   p.rows_per_frame = rows_per_frame;
   p.N = w.N; p.Cin = w.Cin; p.taps = w.taps; p.dil = w.dil;
   p.bias = w.bias;
   p.act = e.act;
   const int outN = (e.act == ACT_SWIGLU) ? w.N / 2 : w.N;
-  p.res = e.res; p.ldres = outN; p.res_bstride = slot * outN;
+  const int64_t obs = e.out_bstride >= 0 ? e.out_bstride : slot * outN;
+  p.res = e.res; p.ldres = outN; p.res_bstride = obs;
   p.scale = e.scale;
-  p.out_y = e.out_y; p.ldy = outN; p.y_bstride = slot * outN;
-  p.out_a = e.out_a; p.lda_out = outN; p.ao_bstride = slot * outN;
+  p.out_y = e.out_y; p.ldy = outN; p.y_bstride = obs;
+  p.out_a = e.out_a; p.lda_out = outN; p.ao_bstride = obs;
   if (e.snake) {
     if (e.snake->n != w.N) throw Error(Q3TTS_EINVAL, "internal: snake width does not match GEMM N");
     p.snake_ea = e.snake->ea; p.snake_ib = e.snake->ib;
   }
-  p.out_tap = e.out_tap; p.ldt = outN; p.tap_bstride = slot * outN;
+  p.out_tap = e.out_tap; p.ldt = outN; p.tap_bstride = obs;
   const int y_dtype = (m.op_dtype == DT_F32) ? DT_F32 : e.y_dtype;
   {
     const double rows = (double)x.valid_frames * rows_per_frame, ops = (double)dt_size(m.op_dtype);
@@ -470,91 +474,17 @@ void gemm(Ctx& x, const GemmW& w, const void* A, int rows_per_frame, const Epi& 
 
 }  // namespace
 
-void run_microbatch(Model& m, const int32_t* d_codes, const int64_t* d_code_base, int64_t sq, int64_t st,
-                    const int* d_len, const int64_t* d_pcm_base, float* d_pcm, int B, int Tmax, int64_t valid_frames,
-                    cudaStream_t s) {
+// Stages 4-6: upsample, main decoder, outConv + clip, from the pre-transformer output `to` [B, Tmax, latent] (operand dtype).
+static void run_back(Ctx& x, Plan& P, const void* to, const int64_t* d_pcm_base, float* d_pcm) {
+  Model& m = x.m;
   const q3tts_config& c = m.cfg;
-  const size_t need = plan_bytes(m, B, Tmax);
-  if (need > m.arena_cap) {
-    CUDA_OK(cudaStreamSynchronize(s));
-    if (m.arena) cudaFree(m.arena);
-    m.arena = nullptr;
-    m.arena_cap = 0;
-    CUDA_OK(cudaMalloc(&m.arena, need));
-    m.arena_cap = need;
-  }
-  Plan P = make_plan(m, m.arena, B, Tmax);
-  Ctx x{m, BatchGeom{B, Tmax, d_len, (long long)valid_frames}, s, valid_frames};
-  const int op = m.op_dtype;
-  const int64_t R = (int64_t)B * Tmax;
-  const int half = c.codebook_dim / 2;
+  cudaStream_t s = x.s;
+  const int op = m.op_dtype, B = x.g.B, Tmax = x.g.Tmax;
+  const int64_t valid_frames = x.valid_frames;
   const bool taps = m.taps_enabled;
-
-  // 1. RVQ dequantise (ST.swift:214-226)
-  stage_begin(x, 0);
-  {
-    RvqParams rp{};
-    rp.codes = d_codes; rp.code_base = d_code_base; rp.sq = sq; rp.st = st;
-    rp.tables = m.d_tables; rp.table_sizes = m.d_table_sizes;
-    rp.num_q = c.num_quantizers; rp.num_sem = c.num_semantic_quantizers; rp.half = half;
-    rp.out = P.Q; rp.out_dtype = op; rp.err_flag = m.d_err;
-    launch_rvq(rp, x.g, s);
-    count_launch(x);
-    account(x, (double)valid_frames * (c.num_quantizers - 2) * half,
-            (double)valid_frames * (c.num_quantizers * (4.0 + half * 4.0) + 2.0 * half * dt_size(op)));
-    if (taps) {
-      const int64_t L = Tmax;
-      launch_tap_copy(P.Q, op, L * 2 * half, 2 * half, tap_buffer(m, "rvq_sum_first", B, half, L), B, half, L, s);
-      launch_tap_copy((const char*)P.Q + (size_t)half * dt_size(op), op, L * 2 * half, 2 * half,
-                      tap_buffer(m, "rvq_sum_rest", B, half, L), B, half, L, s);
-      count_launch(x, 2);
-    }
-    Epi e; e.out_a = P.QP;
-    gemm(x, m.rvq_proj, P.Q, 1, e, "proj");
-    tap(x, "quantized", P.QP, op, 1, c.codebook_dim, c.codebook_dim);
-  }
-  stage_end(x);
-
-  // 2. pre_conv (ST.swift:724-728, 759)
-  stage_begin(x, 1);
-  { Epi e; e.out_a = P.PC; gemm(x, m.pre_conv, P.QP, 1, e, "conv3"); }
-  tap(x, "pre_conv", P.PC, op, 1, c.latent_dim, c.latent_dim);
-  stage_end(x);
-
-  // 3. pre_transformer (ST.swift:629-643)
-  stage_begin(x, 2);
-  { Epi e; e.out_y = P.H; e.y_dtype = DT_F32; gemm(x, m.in_proj, P.PC, 1, e, "in_proj"); }
-  const float scale = 1.0f / sqrtf((float)c.head_dim);   // ST.swift:502
-  const int window = (m.opts.attn_mode == Q3TTS_ATTN_CAUSAL_SW) ? c.sliding_window : 0;
-  for (auto& L : m.layers) {
-    launch_rmsnorm(P.H, L.ln1, c.rms_norm_eps, P.NB, op, R, c.hidden_size, s); count_launch(x);
-    { Epi e; e.out_a = P.QKV; gemm(x, L.qkv, P.NB, 1, e, "qkv"); }
-    {
-      const double tkv0 = window > 0 ? std::min<double>(window, (double)valid_frames / B) : (double)valid_frames / B;
-      launch_begin(x, "attention", 4.0 * c.num_attention_heads * c.head_dim * tkv0 * valid_frames,
-                   (double)valid_frames * ((double)(c.num_attention_heads + 2 * c.num_key_value_heads) * c.head_dim + (double)c.num_attention_heads * c.head_dim) * dt_size(op));
-    }
-    launch_attention(P.QKV, op, P.AO, op, x.g, c.num_attention_heads, c.num_key_value_heads, c.head_dim, scale, window, s);
-    launch_end(x);
-    count_launch(x);
-    {  // 4*nh*hd*T_kv FLOP per query frame; keys = own utterance (approximated by the mean valid length)
-      const double tkv = window > 0 ? std::min<double>(window, (double)valid_frames / B) : (double)valid_frames / B;
-      account(x, 4.0 * c.num_attention_heads * c.head_dim * tkv * valid_frames,
-              (double)valid_frames * ((double)(c.num_attention_heads + 2 * c.num_key_value_heads) * c.head_dim + (double)c.num_attention_heads * c.head_dim) * dt_size(op));
-    }
-    { Epi e; e.res = P.H; e.scale = L.ls_attn; e.out_y = P.H; e.y_dtype = DT_F32; gemm(x, L.o, P.AO, 1, e, "o_proj"); }
-    launch_rmsnorm(P.H, L.ln2, c.rms_norm_eps, P.NB, op, R, c.hidden_size, s); count_launch(x);
-    { Epi e; e.act = ACT_SWIGLU; e.out_a = P.GU; gemm(x, L.gate_up, P.NB, 1, e, "gate_up"); }
-    { Epi e; e.res = P.H; e.scale = L.ls_mlp; e.out_y = P.H; e.y_dtype = DT_F32; gemm(x, L.down, P.GU, 1, e, "down"); }
-  }
-  launch_rmsnorm(P.H, m.final_norm, c.rms_norm_eps, P.NB, op, R, c.hidden_size, s); count_launch(x);
-  { Epi e; e.out_a = P.TO; gemm(x, m.out_proj, P.NB, 1, e, "out_proj"); }
-  tap(x, "pre_transformer", P.TO, op, 1, c.latent_dim, c.latent_dim);
-  stage_end(x);
-
   // 4. upsample: (transposed conv k=s=r, ConvNeXt) x2 (ST.swift:766-775, 385-401)
   stage_begin(x, 3);
-  const void* cur = P.TO;
+  const void* cur = to;
   int rate = 1;
   for (size_t i = 0; i < m.ups.size(); ++i) {
     UpsampleW& U = m.ups[i];
@@ -641,8 +571,306 @@ void run_microbatch(Model& m, const int32_t* d_codes, const int64_t* d_code_base
     account(x, 2.0 * 7 * C * (double)valid_frames * rate, (double)valid_frames * rate * (C * (double)dt_size(op) + 4.0));
   }
   stage_end(x);
+}
+
+void run_microbatch(Model& m, const int32_t* d_codes, const int64_t* d_code_base, int64_t sq, int64_t st,
+                    const int* d_len, const int64_t* d_pcm_base, float* d_pcm, int B, int Tmax, int64_t valid_frames,
+                    cudaStream_t s) {
+  const q3tts_config& c = m.cfg;
+  const size_t need = plan_bytes(m, B, Tmax);
+  if (need > m.arena_cap) {
+    CUDA_OK(cudaStreamSynchronize(s));
+    if (m.arena) cudaFree(m.arena);
+    m.arena = nullptr;
+    m.arena_cap = 0;
+    CUDA_OK(cudaMalloc(&m.arena, need));
+    m.arena_cap = need;
+  }
+  Plan P = make_plan(m, m.arena, B, Tmax);
+  Ctx x{m, BatchGeom{B, Tmax, d_len, (long long)valid_frames}, s, valid_frames};
+  const int op = m.op_dtype;
+  const int64_t R = (int64_t)B * Tmax;
+  const int half = c.codebook_dim / 2;
+  const bool taps = m.taps_enabled;
+
+  // 1. RVQ dequantise (ST.swift:214-226)
+  stage_begin(x, 0);
+  {
+    RvqParams rp{};
+    rp.codes = d_codes; rp.code_base = d_code_base; rp.sq = sq; rp.st = st;
+    rp.tables = m.d_tables; rp.table_sizes = m.d_table_sizes;
+    rp.num_q = c.num_quantizers; rp.num_sem = c.num_semantic_quantizers; rp.half = half;
+    rp.out = P.Q; rp.out_dtype = op; rp.err_flag = m.d_err;
+    launch_rvq(rp, x.g, s);
+    count_launch(x);
+    account(x, (double)valid_frames * (c.num_quantizers - 2) * half,
+            (double)valid_frames * (c.num_quantizers * (4.0 + half * 4.0) + 2.0 * half * dt_size(op)));
+    if (taps) {
+      const int64_t L = Tmax;
+      launch_tap_copy(P.Q, op, L * 2 * half, 2 * half, tap_buffer(m, "rvq_sum_first", B, half, L), B, half, L, s);
+      launch_tap_copy((const char*)P.Q + (size_t)half * dt_size(op), op, L * 2 * half, 2 * half,
+                      tap_buffer(m, "rvq_sum_rest", B, half, L), B, half, L, s);
+      count_launch(x, 2);
+    }
+    Epi e; e.out_a = P.QP;
+    gemm(x, m.rvq_proj, P.Q, 1, e, "proj");
+    tap(x, "quantized", P.QP, op, 1, c.codebook_dim, c.codebook_dim);
+  }
+  stage_end(x);
+
+  // 2. pre_conv (ST.swift:724-728, 759)
+  stage_begin(x, 1);
+  { Epi e; e.out_a = P.PC; gemm(x, m.pre_conv, P.QP, 1, e, "conv3"); }
+  tap(x, "pre_conv", P.PC, op, 1, c.latent_dim, c.latent_dim);
+  stage_end(x);
+
+  // 3. pre_transformer (ST.swift:629-643)
+  stage_begin(x, 2);
+  { Epi e; e.out_y = P.H; e.y_dtype = DT_F32; gemm(x, m.in_proj, P.PC, 1, e, "in_proj"); }
+  const float scale = 1.0f / sqrtf((float)c.head_dim);   // ST.swift:502
+  const int window = (m.opts.attn_mode == Q3TTS_ATTN_CAUSAL_SW) ? c.sliding_window : 0;
+  for (auto& L : m.layers) {
+    launch_rmsnorm(P.H, L.ln1, c.rms_norm_eps, P.NB, op, R, c.hidden_size, s); count_launch(x);
+    { Epi e; e.out_a = P.QKV; gemm(x, L.qkv, P.NB, 1, e, "qkv"); }
+    {
+      const double tkv0 = window > 0 ? std::min<double>(window, (double)valid_frames / B) : (double)valid_frames / B;
+      launch_begin(x, "attention", 4.0 * c.num_attention_heads * c.head_dim * tkv0 * valid_frames,
+                   (double)valid_frames * ((double)(c.num_attention_heads + 2 * c.num_key_value_heads) * c.head_dim + (double)c.num_attention_heads * c.head_dim) * dt_size(op));
+    }
+    launch_attention(P.QKV, op, P.AO, op, x.g, c.num_attention_heads, c.num_key_value_heads, c.head_dim, scale, window, s);
+    launch_end(x);
+    count_launch(x);
+    {  // 4*nh*hd*T_kv FLOP per query frame; keys = own utterance (approximated by the mean valid length)
+      const double tkv = window > 0 ? std::min<double>(window, (double)valid_frames / B) : (double)valid_frames / B;
+      account(x, 4.0 * c.num_attention_heads * c.head_dim * tkv * valid_frames,
+              (double)valid_frames * ((double)(c.num_attention_heads + 2 * c.num_key_value_heads) * c.head_dim + (double)c.num_attention_heads * c.head_dim) * dt_size(op));
+    }
+    { Epi e; e.res = P.H; e.scale = L.ls_attn; e.out_y = P.H; e.y_dtype = DT_F32; gemm(x, L.o, P.AO, 1, e, "o_proj"); }
+    launch_rmsnorm(P.H, L.ln2, c.rms_norm_eps, P.NB, op, R, c.hidden_size, s); count_launch(x);
+    { Epi e; e.act = ACT_SWIGLU; e.out_a = P.GU; gemm(x, L.gate_up, P.NB, 1, e, "gate_up"); }
+    { Epi e; e.res = P.H; e.scale = L.ls_mlp; e.out_y = P.H; e.y_dtype = DT_F32; gemm(x, L.down, P.GU, 1, e, "down"); }
+  }
+  launch_rmsnorm(P.H, m.final_norm, c.rms_norm_eps, P.NB, op, R, c.hidden_size, s); count_launch(x);
+  { Epi e; e.out_a = P.TO; gemm(x, m.out_proj, P.NB, 1, e, "out_proj"); }
+  tap(x, "pre_transformer", P.TO, op, 1, c.latent_dim, c.latent_dim);
+  stage_end(x);
+
+  run_back(x, P, P.TO, d_pcm_base, d_pcm);
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) throw Error(Q3TTS_ECUDA, std::string("kernel launch: ") + cudaGetErrorString(err));
+}
+
+
+
+// ---- chunked streaming ------------------------------------------------------------------------------------------------
+int stream_context_frames(const q3tts_config& c) {
+  // causal receptive field of stages 4-6, walked from the PCM sample back to the pre-transformer output (rows at each rate)
+  int64_t rows = 6;                                              // outConv k = 7
+  for (int i = 3; i >= 0; --i) {
+    rows += 6 * (1 + 3 + 9);                                     // three residual units, conv7 with dilation 1, 3, 9
+    const int r = c.upsample_rates[i];
+    rows = (rows + r - 1) / r + 1;                               // transposed conv k = 2r, s = r: y[t*r+p] needs x[t], x[t-1]
+  }
+  rows += 6;                                                     // initConv k = 7
+  for (int i = c.num_upsampling_ratios - 1; i >= 0; --i) {
+    rows += 6;                                                   // ConvNeXt depthwise k = 7
+    const int r = c.upsampling_ratios[i];
+    rows = (rows + r - 1) / r;                                   // transposed conv k = s = r: y[t*r+p] needs x[t] only
+  }
+  return (int)rows;
+}
+
+void stream_state_alloc(Model& m, StreamState& st) {
+  const q3tts_config& c = m.cfg;
+  const size_t op = dt_size(m.op_dtype);
+  const size_t ld = (size_t)(c.num_attention_heads + 2 * c.num_key_value_heads) * c.head_dim;
+  const int Hc = stream_context_frames(c), W1 = std::max(c.sliding_window - 1, 0);
+  CUDA_OK(cudaMalloc(&st.q_hist, 2 * (size_t)c.codebook_dim * op));
+  CUDA_OK(cudaMalloc(&st.kv, std::max<size_t>((size_t)c.num_hidden_layers * W1 * ld * op, 16)));
+  CUDA_OK(cudaMalloc(&st.to_hist, (size_t)Hc * c.latent_dim * op));
+  st.frames_done = 0;
+}
+void stream_state_free(Model& m, StreamState& st) {
+  cudaSetDevice(m.device);
+  if (st.q_hist) cudaFree(st.q_hist);
+  if (st.kv) cudaFree(st.kv);
+  if (st.to_hist) cudaFree(st.to_hist);
+  st = StreamState{};
+}
+
+void run_stream_batch(Model& m, StreamState* const* streams, int S, const int32_t* d_codes, const int* n_frames,
+                      float* d_pcm_out, cudaStream_t s) {
+  const q3tts_config& c = m.cfg;
+  const int op = m.op_dtype;
+  const size_t ops = dt_size(op);
+  const int Hc = stream_context_frames(c), W1 = c.sliding_window - 1, Q = c.num_quantizers;
+  const int cb = c.codebook_dim, lat = c.latent_dim, hid = c.hidden_size, inter = c.intermediate_size;
+  const int A = c.num_attention_heads * c.head_dim, ld = (c.num_attention_heads + 2 * c.num_key_value_heads) * c.head_dim;
+  const int64_t up = c.total_upsample;
+  int nmax = 0;
+  int64_t total = 0;
+  for (int i = 0; i < S; ++i) { nmax = std::max(nmax, n_frames[i]); total += n_frames[i]; }
+  if (nmax == 0) return;
+  const int Tq = 2 + nmax, Tkv = W1 + nmax, Tc = Hc + nmax;
+
+  // ---- workspace: back-stage plan (arena) + streaming front buffers (stream_ws) ----
+  const size_t need = plan_bytes(m, S, Tc);
+  if (need > m.arena_cap) {
+    CUDA_OK(cudaStreamSynchronize(s));
+    if (m.arena) cudaFree(m.arena);
+    m.arena = nullptr; m.arena_cap = 0;
+    CUDA_OK(cudaMalloc(&m.arena, need));
+    m.arena_cap = need;
+  }
+  Plan P = make_plan(m, m.arena, S, Tc);
+  const int n_items_max = S * (8 + 2 * c.num_hidden_layers);
+  Arena a{nullptr};
+  auto carve = [&](Arena& ar) {
+    struct { int *len_new, *len_q, *len_kv, *beg_kv, *len_c; int64_t *code_base, *pcm_base; CopyItem* items;
+             void *Qsum, *QPin, *PC, *NB, *QKV, *AO, *GU, *TO, *Cin; float *H, *pcm; } w;
+    w.len_new = ar.take<int>((size_t)S * 4); w.len_q = ar.take<int>((size_t)S * 4); w.len_kv = ar.take<int>((size_t)S * 4);
+    w.beg_kv = ar.take<int>((size_t)S * 4); w.len_c = ar.take<int>((size_t)S * 4);
+    w.code_base = ar.take<int64_t>((size_t)S * 8); w.pcm_base = ar.take<int64_t>((size_t)S * 8);
+    w.items = ar.take<CopyItem>((size_t)n_items_max * sizeof(CopyItem));
+    w.Qsum = ar.take((size_t)S * nmax * cb * ops); w.QPin = ar.take((size_t)S * Tq * cb * ops); w.PC = ar.take((size_t)S * Tq * lat * ops);
+    w.H = ar.take<float>((size_t)S * nmax * hid * 4); w.NB = ar.take((size_t)S * nmax * hid * ops);
+    w.QKV = ar.take((size_t)S * Tkv * ld * ops); w.AO = ar.take((size_t)S * Tkv * A * ops); w.GU = ar.take((size_t)S * nmax * inter * ops);
+    w.TO = ar.take((size_t)S * nmax * lat * ops); w.Cin = ar.take((size_t)S * Tc * lat * ops);
+    w.pcm = ar.take<float>((size_t)S * Tc * up * 4);
+    return w;
+  };
+  carve(a);
+  const size_t ws_need = a.off + 256;
+  if (ws_need > m.stream_ws_cap) {
+    CUDA_OK(cudaStreamSynchronize(s));
+    if (m.stream_ws) cudaFree(m.stream_ws);
+    m.stream_ws = nullptr; m.stream_ws_cap = 0;
+    CUDA_OK(cudaMalloc(&m.stream_ws, ws_need));
+    m.stream_ws_cap = ws_need;
+  }
+  Arena b{m.stream_ws};
+  auto w = carve(b);
+
+  // ---- metadata + copy lists (host), one pinned upload ----
+  const size_t meta_bytes = (size_t)((char*)w.Qsum - (char*)w.len_new);     // everything before the activation buffers
+  if (meta_bytes > m.stream_meta_cap) {
+    CUDA_OK(cudaStreamSynchronize(s));
+    if (m.stream_meta_h) cudaFreeHost(m.stream_meta_h);
+    m.stream_meta_h = nullptr; m.stream_meta_cap = 0;
+    CUDA_OK(cudaMallocHost(&m.stream_meta_h, meta_bytes));
+    m.stream_meta_cap = meta_bytes;
+  } else {
+    CUDA_OK(cudaStreamSynchronize(s));   // the previous push may still be reading the staging block
+  }
+  char* hm = m.stream_meta_h;
+  auto host = [&](const void* dev) { return hm + ((const char*)dev - (const char*)w.len_new); };
+  int *h_len_new = (int*)host(w.len_new), *h_len_q = (int*)host(w.len_q), *h_len_kv = (int*)host(w.len_kv), *h_beg_kv = (int*)host(w.beg_kv),
+      *h_len_c = (int*)host(w.len_c);
+  int64_t *h_code_base = (int64_t*)host(w.code_base), *h_pcm_base = (int64_t*)host(w.pcm_base);
+  CopyItem* h_items = (CopyItem*)host(w.items);
+  // copy lists, grouped by when they run: [pre] histories -> slots; [layer l] cache -> qkv rows, then qkv rows -> cache;
+  // [mid] TO -> Cin and history updates; [post] PCM out
+  std::vector<CopyItem> pre, mid, post;
+  std::vector<std::vector<CopyItem>> kv_in((size_t)c.num_hidden_layers), kv_out((size_t)c.num_hidden_layers);
+  int64_t frame_off = 0;
+  std::vector<int> ctxc((size_t)S);
+  for (int i = 0; i < S; ++i) {
+    StreamState& st = *streams[i];
+    const int n = n_frames[i];
+    const int cq = (int)std::min<int64_t>(2, st.frames_done), ckv = (int)std::min<int64_t>(W1, st.frames_done),
+              cc = (int)std::min<int64_t>(Hc, st.frames_done);
+    ctxc[(size_t)i] = cc;
+    h_len_new[i] = n; h_len_q[i] = n > 0 ? 2 + n : 0; h_len_kv[i] = n > 0 ? W1 + n : 0; h_beg_kv[i] = W1 - ckv; h_len_c[i] = n > 0 ? cc + n : 0;
+    h_code_base[i] = frame_off * Q; h_pcm_base[i] = (int64_t)i * Tc * up;
+    if (n == 0) continue;
+    char* qpin = (char*)w.QPin + (size_t)i * Tq * cb * ops;
+    if (cq < 2) pre.push_back({nullptr, qpin, (long long)((2 - cq) * cb * ops)});                                   // causal zero padding
+    if (cq > 0) pre.push_back({(char*)st.q_hist + (size_t)(2 - cq) * cb * ops, qpin + (size_t)(2 - cq) * cb * ops, (long long)(cq * cb * ops)});
+    // new q history = last two rows of [hist | new] (n + 2 rows in the slot)
+    mid.push_back({qpin + (size_t)n * cb * ops, st.q_hist, (long long)(2 * cb * ops)});
+    for (int l = 0; l < c.num_hidden_layers; ++l) {
+      char* cache = (char*)st.kv + (size_t)l * W1 * ld * ops;
+      char* slot = (char*)w.QKV + (size_t)i * Tkv * ld * ops;
+      if (ckv > 0) kv_in[(size_t)l].push_back({cache + (size_t)(W1 - ckv) * ld * ops, slot + (size_t)(W1 - ckv) * ld * ops, (long long)((size_t)ckv * ld * ops)});
+      if (W1 > 0) kv_out[(size_t)l].push_back({slot + (size_t)n * ld * ops, cache, (long long)((size_t)W1 * ld * ops)});   // rows n .. n+W1-1
+    }
+    char* cin = (char*)w.Cin + (size_t)i * Tc * lat * ops;
+    if (cc > 0) mid.push_back({(char*)st.to_hist + (size_t)(Hc - cc) * lat * ops, cin, (long long)((size_t)cc * lat * ops)});
+    mid.push_back({(char*)w.TO + (size_t)i * nmax * lat * ops, cin + (size_t)cc * lat * ops, (long long)((size_t)n * lat * ops)});
+    post.push_back({(char*)w.pcm + ((size_t)i * Tc + cc) * up * 4, (char*)d_pcm_out + (size_t)frame_off * up * 4, (long long)((size_t)n * up * 4)});
+    frame_off += n;
+  }
+  // the to_hist update reads Cin after it is complete: a second list run after `mid`
+  std::vector<CopyItem> mid2;
+  for (int i = 0; i < S; ++i) {
+    const int n = n_frames[i];
+    if (n == 0) continue;
+    StreamState& st = *streams[i];
+    const int cc = ctxc[(size_t)i], keep = std::min(Hc, cc + n);
+    char* cin = (char*)w.Cin + (size_t)i * Tc * lat * ops;
+    mid2.push_back({cin + (size_t)(cc + n - keep) * lat * ops, (char*)st.to_hist + (size_t)(Hc - keep) * lat * ops, (long long)((size_t)keep * lat * ops)});
+  }
+  size_t cursor = 0;
+  auto place = [&](const std::vector<CopyItem>& v) {
+    const size_t at = cursor;
+    if (cursor + v.size() > (size_t)n_items_max) throw Error(Q3TTS_EINVAL, "internal: streaming copy list overflow");
+    for (const CopyItem& it : v) h_items[cursor++] = it;
+    return at;
+  };
+  const size_t at_pre = place(pre), at_mid = place(mid), at_mid2 = place(mid2), at_post = place(post);
+  std::vector<size_t> at_in((size_t)c.num_hidden_layers), at_out((size_t)c.num_hidden_layers);
+  for (int l = 0; l < c.num_hidden_layers; ++l) { at_in[(size_t)l] = place(kv_in[(size_t)l]); at_out[(size_t)l] = place(kv_out[(size_t)l]); }
+  CUDA_OK(cudaMemcpyAsync(w.len_new, hm, meta_bytes, cudaMemcpyHostToDevice, s));
+  auto run_copies = [&](size_t at, size_t n) { launch_block_copy(w.items + at, (int)n, s); if (n) m.launches += 1; };
+
+  // ---- front: RVQ -> pre_conv -> transformer with the KV history ----
+  const float scale = 1.0f / sqrtf((float)c.head_dim);
+  Ctx xn{m, BatchGeom{S, nmax, w.len_new, (long long)total, nullptr}, s, total};          // the new frames
+  Ctx xq{m, BatchGeom{S, Tq, w.len_q, (long long)(total + 2 * S), nullptr}, s, total};       // pre_conv slots: [2 history | new]
+  run_copies(at_pre, pre.size());
+  {
+    RvqParams rp{};
+    rp.codes = d_codes; rp.code_base = w.code_base; rp.sq = 1; rp.st = Q;
+    rp.tables = m.d_tables; rp.table_sizes = m.d_table_sizes;
+    rp.num_q = c.num_quantizers; rp.num_sem = c.num_semantic_quantizers; rp.half = cb / 2;
+    rp.out = w.Qsum; rp.out_dtype = op; rp.err_flag = m.d_err;
+    launch_rvq(rp, xn.g, s);
+    m.launches += 1;
+    Epi e; e.out_a = (char*)w.QPin + (size_t)2 * cb * ops; e.out_bstride = (int64_t)Tq * cb;
+    gemm(xn, m.rvq_proj, w.Qsum, 1, e, "proj");
+  }
+  { Epi e; e.out_a = w.PC; gemm(xq, m.pre_conv, w.QPin, 1, e, "conv3"); }
+  { Epi e; e.a_bstride = (int64_t)Tq * lat; e.out_y = w.H; e.y_dtype = DT_F32; gemm(xn, m.in_proj, (char*)w.PC + (size_t)2 * lat * ops, 1, e, "in_proj"); }
+  BatchGeom gkv{S, Tkv, w.len_kv, (long long)(total + (int64_t)W1 * S), w.beg_kv};
+  const int64_t Rn = (int64_t)S * nmax;
+  for (int l = 0; l < c.num_hidden_layers; ++l) {
+    LayerW& L = m.layers[(size_t)l];
+    launch_rmsnorm(w.H, L.ln1, c.rms_norm_eps, w.NB, op, Rn, hid, s); m.launches += 1;
+    { Epi e; e.out_a = (char*)w.QKV + (size_t)W1 * ld * ops; e.out_bstride = (int64_t)Tkv * ld; gemm(xn, L.qkv, w.NB, 1, e, "qkv"); }
+    run_copies(at_in[(size_t)l], kv_in[(size_t)l].size());
+    launch_attention(w.QKV, op, w.AO, op, gkv, c.num_attention_heads, c.num_key_value_heads, c.head_dim, scale, c.sliding_window, s);
+    m.launches += 1;
+    run_copies(at_out[(size_t)l], kv_out[(size_t)l].size());
+    { Epi e; e.a_bstride = (int64_t)Tkv * A; e.res = w.H; e.scale = L.ls_attn; e.out_y = w.H; e.y_dtype = DT_F32;
+      gemm(xn, L.o, (char*)w.AO + (size_t)W1 * A * ops, 1, e, "o_proj"); }
+    launch_rmsnorm(w.H, L.ln2, c.rms_norm_eps, w.NB, op, Rn, hid, s); m.launches += 1;
+    { Epi e; e.act = ACT_SWIGLU; e.out_a = w.GU; gemm(xn, L.gate_up, w.NB, 1, e, "gate_up"); }
+    { Epi e; e.res = w.H; e.scale = L.ls_mlp; e.out_y = w.H; e.y_dtype = DT_F32; gemm(xn, L.down, w.GU, 1, e, "down"); }
+  }
+  launch_rmsnorm(w.H, m.final_norm, c.rms_norm_eps, w.NB, op, Rn, hid, s); m.launches += 1;
+  { Epi e; e.out_a = w.TO; gemm(xn, m.out_proj, w.NB, 1, e, "out_proj"); }
+  run_copies(at_mid, mid.size());
+  run_copies(at_mid2, mid2.size());
+
+  // ---- back: the conv stack over [context | new] frames; only the new frames' PCM is kept ----
+  int64_t valid_c = 0;
+  for (int i = 0; i < S; ++i) valid_c += n_frames[i] > 0 ? ctxc[(size_t)i] + n_frames[i] : 0;
+  Ctx xc{m, BatchGeom{S, Tc, w.len_c, (long long)valid_c, nullptr}, s, valid_c};
+  run_back(xc, P, w.Cin, w.pcm_base, w.pcm);
+  run_copies(at_post, post.size());
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) throw Error(Q3TTS_ECUDA, std::string("kernel launch: ") + cudaGetErrorString(err));
+  for (int i = 0; i < S; ++i) streams[i]->frames_done += n_frames[i];
 }
 
 }  // namespace q3

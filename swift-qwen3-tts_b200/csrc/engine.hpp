@@ -94,6 +94,10 @@ struct Model {
   int* d_err = nullptr;
   int* h_err = nullptr;                                  // pinned
 
+  // streaming workspace (grow-only) + pinned staging for its metadata
+  char* stream_ws = nullptr;  size_t stream_ws_cap = 0;
+  char* stream_meta_h = nullptr; size_t stream_meta_cap = 0;
+
   // taps / profiling
   bool taps_enabled = false;
   std::map<std::string, TapBuf> taps;
@@ -106,6 +110,26 @@ struct Model {
 
   ~Model();
 };
+
+// Chunked streaming (Q3TTS_ATTN_CAUSAL_SW only).  Per stream, on the device, right-aligned histories:
+//   q_hist  [2][codebook_dim]            last inputs of pre_conv (k = 3)
+//   kv      [layers][W-1][qkv width]     K and V of the last W-1 frames of every transformer layer (W = sliding_window)
+//   to_hist [Hc][latent_dim]             last pre-transformer outputs: the conv stack (stages 4-6) is re-run over Hc context
+//                                        frames per chunk (overlap-save; Hc = its causal receptive field, 10 frames for
+//                                        the 12 Hz decoder) -- exact, at (Hc + n) / n times the conv work of a chunk of n.
+struct StreamState {
+  int64_t frames_done = 0;
+  void* q_hist = nullptr;
+  void* kv = nullptr;
+  void* to_hist = nullptr;
+};
+int stream_context_frames(const q3tts_config& c);      // Hc
+void stream_state_alloc(Model& m, StreamState& st);
+void stream_state_free(Model& m, StreamState& st);
+// One chunk for each of S streams in one launch chain.  d_codes: packed [sum n, Q] frame-major; n_frames: host [S];
+// d_pcm_out: packed [sum n * total_upsample].  Advances frames_done.
+void run_stream_batch(Model& m, StreamState* const* streams, int S, const int32_t* d_codes, const int* n_frames,
+                      float* d_pcm_out, cudaStream_t s);
 
 struct MicroBatch { int first = 0, B = 0, Tmax = 0; };   // utterances [first, first+B) of the sorted order
 

@@ -19,6 +19,8 @@ struct BatchGeom {
   int Tmax;                // frames per utterance slot (row stride at rate 1)
   const int* len_frames;   // [B] device: valid frames per utterance
   long long valid_frames;  // host copy of sum(len_frames) (work-list sizing of the strip-walking kernels)
+  const int* row_begin;    // [B] device or null: first valid row of a slot (attention only: streaming keeps its KV history
+                           //   right-aligned in front of the new frames, so a young stream's slot starts late)
 };
 
 // Generic "multi-tap GEMM": out[b,t,n] = epi( sum_{j<taps} sum_c A[b, t-(taps-1-j)*dil, c] * W[j,n,c] ).
@@ -90,6 +92,10 @@ void launch_lengths(const int32_t* codes, const int64_t* code_base, int64_t st, 
 // Stage tap: [B, rows(stride), C] (any dtype) -> fp32 NCT [B, C, L].
 void launch_tap_copy(const void* src, int dtype, int64_t bstride, int ld, float* dst, int B, int C, int64_t L,
                      cudaStream_t s);
+
+// Batched block copy (streaming state shuffles): item i copies `bytes` (multiple of 16) from src to dst; a null src zero-fills.
+struct CopyItem { const void* src; void* dst; long long bytes; };
+void launch_block_copy(const CopyItem* d_items, int n_items, cudaStream_t s);
 
 // float <-> 16-bit conversion of packed weights.
 void launch_convert(const float* src, void* dst, int dtype, int64_t n, cudaStream_t s);

@@ -44,18 +44,18 @@ attention_mma_kernel(const T16* __restrict__ qkv, T16* __restrict__ out, BatchGe
   __shared__ __align__(16) T16 Ks[AK * APAD];
   __shared__ __align__(16) T16 Vs[AK * APAD];
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * AQ;
-  const int len = g.len_frames[b];
+  const int len = g.len_frames[b], beg = g.row_begin ? g.row_begin[b] : 0;
   if (q0 >= len) return;
   const int hk = h / (nh / nkv), ld = (nh + 2 * nkv) * AD;
   const T16* base = qkv + (int64_t)b * g.Tmax * ld;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-  auto load_tile = [&](T16* dst, int row0, int col0) {   // 64 rows x 64 halves, 16-byte loads, zero beyond len
+  auto load_tile = [&](T16* dst, int row0, int col0) {   // 64 rows x 64 halves, 16-byte loads, zero outside [beg, len)
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int idx = tid + i * 128, r = idx >> 3, c8 = idx & 7;
       uint4 v = make_uint4(0, 0, 0, 0);
-      if (row0 + r < len) v = __ldg((const uint4*)(base + (int64_t)(row0 + r) * ld + col0 + c8 * 8));
+      if (row0 + r < len && row0 + r >= beg) v = __ldg((const uint4*)(base + (int64_t)(row0 + r) * ld + col0 + c8 * 8));
       *(uint4*)&dst[r * APAD + c8 * 8] = v;
     }
   };
@@ -74,7 +74,8 @@ attention_mma_kernel(const T16* __restrict__ qkv, T16* __restrict__ out, BatchGe
   const int r0 = q0 + warp * 16 + (lane >> 2), r1 = r0 + 8;        // the two query rows this thread holds
 
   int k_begin = 0, k_end = len;
-  if (window > 0) { k_begin = max(0, q0 - window + 1) / AK * AK; k_end = min(len, q0 + AQ); }
+  if (window > 0) { k_begin = max(beg, max(0, q0 - window + 1)) / AK * AK; k_end = min(len, q0 + AQ); }
+  else k_begin = beg / AK * AK;
   for (int kt = k_begin; kt < k_end; kt += AK) {
     __syncthreads();                       // previous tile fully consumed
     load_tile(Ks, kt, (nh + hk) * AD);
@@ -100,7 +101,7 @@ attention_mma_kernel(const T16* __restrict__ qkv, T16* __restrict__ out, BatchGe
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int key = kt + j * 8 + 2 * (lane & 3) + (e & 1), tq = (e < 2) ? r0 : r1;
-        bool ok = key < len;
+        bool ok = key < len && key >= beg;
         if (window > 0) ok = ok && key <= tq && (tq - key) < window;
         s[j][e] = ok ? s[j][e] * scale_log2e : -INFINITY;
       }

@@ -311,7 +311,7 @@ attention_kernel(const TI* qkv, TO* out, BatchGeom g, int nh, int nkv, float sca
   __shared__ float Vs[32][HD + 1];
   __shared__ float Qs[ATT_QB][HD];
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * ATT_QB;
-  const int len = g.len_frames[b];
+  const int len = g.len_frames[b], beg = g.row_begin ? g.row_begin[b] : 0;
   if (q0 >= len) return;
   const int hk = h / (nh / nkv);
   const int ld = (nh + 2 * nkv) * HD;
@@ -331,12 +331,12 @@ attention_kernel(const TI* qkv, TO* out, BatchGeom g, int nh, int nkv, float sca
   const int qlast = min(q0 + ATT_QB, len) - 1;
   int k_begin = 0, k_end = len;
   if (window > 0) { k_begin = max(0, q0 - window + 1); k_end = qlast + 1; }
-  k_begin &= ~31;
+  k_begin = max(k_begin, beg) & ~31;
   for (int kc = k_begin; kc < k_end; kc += 32) {
     __syncthreads();
     for (int i = threadIdx.x; i < 32 * HD; i += 128) {
       const int kj = i / HD, d = i % HD;
-      const bool ok = kc + kj < len;
+      const bool ok = kc + kj < len && kc + kj >= beg;
       Ks[kj][d] = ok ? ldf(base, (int64_t)(kc + kj) * ld + (nh + hk) * HD + d) : 0.f;
       Vs[kj][d] = ok ? ldf(base, (int64_t)(kc + kj) * ld + (nh + nkv + hk) * HD + d) : 0.f;
     }
@@ -349,7 +349,7 @@ attention_kernel(const TI* qkv, TO* out, BatchGeom g, int nh, int nkv, float sca
       float sc = 0.f;
 #pragma unroll 16
       for (int d = 0; d < HD; ++d) sc = fmaf(Qs[qi][d], Ks[lane][d], sc);
-      bool ok = kj < len;
+      bool ok = kj < len && kj >= beg;
       if (window > 0) ok = ok && kj <= tq && (tq - kj) < window;
       sc = ok ? sc : -INFINITY;
       float cm = sc;
@@ -508,6 +508,20 @@ void launch_tail(const void* a, int a_dtype, int64_t a_bstride, const float* w, 
   const int64_t warps = (int64_t)g.B * g.Tmax * rows_per_frame;
   const unsigned blocks = (unsigned)((warps * 32 + 255) / 256);
   Q3_DISPATCH_DT(a_dtype, T, (tail_kernel<T><<<blocks, 256, 0, s>>>((const T*)a, a_bstride, w, bias, C, pcm, pcm_base, tap, tap_bstride, g, rows_per_frame)));
+}
+
+// ================================================================================================
+// Batched block copy: one CTA per item, 16-byte chunks (the streaming API's state shuffles).
+// ================================================================================================
+__global__ void __launch_bounds__(256) block_copy_kernel(const CopyItem* items) {
+  const CopyItem it = items[blockIdx.x];
+  const long long n = it.bytes >> 4;
+  uint4* d = (uint4*)it.dst;
+  const uint4* sp = (const uint4*)it.src;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) d[i] = sp ? sp[i] : make_uint4(0, 0, 0, 0);
+}
+void launch_block_copy(const CopyItem* d_items, int n_items, cudaStream_t s) {
+  if (n_items > 0) block_copy_kernel<<<(unsigned)n_items, 256, 0, s>>>(d_items);
 }
 
 // ================================================================================================

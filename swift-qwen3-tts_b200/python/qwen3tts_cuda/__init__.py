@@ -22,7 +22,7 @@ from typing import Optional, Sequence, Tuple
 
 import numpy as np
 
-__all__ = ["Qwen3TTSSpeechTokenizer", "Qwen3TTSSpeechTokenizerDecoder", "AudioDecodingFailed", "lib",
+__all__ = ["Qwen3TTSSpeechTokenizer", "DecodeStream", "Qwen3TTSSpeechTokenizerDecoder", "AudioDecodingFailed", "lib",
            "partition_lpt", "PREC_FP32", "PREC_FP16", "PREC_BF16", "ATTN_REFERENCE", "ATTN_CAUSAL_SW",
            "library_path", "checkpoint_inspect", "pcm_to_int16", "write_wav", "trim_length",
            "voice_clone_cut", "device_count"]
@@ -112,6 +112,7 @@ def lib() -> C.CDLL:
         "q3tts_stream_open": (C.c_int, [vp, C.POINTER(vp)]),
         "q3tts_stream_push": (C.c_int, [vp, vp, i32, vp]),
         "q3tts_stream_push_batch": (C.c_int, [vp, i32, vp, vp, vp]),
+        "q3tts_stream_frames": (i64, [vp]),
         "q3tts_stream_close": (None, [vp]),
         "q3tts_partition_lpt": (C.c_int, [vp, i32, i32, vp]),
         "q3tts_trim_length": (i64, [i64, i64]),
@@ -133,6 +134,29 @@ def lib() -> C.CDLL:
     L._q3_symbols = tuple(sigs)
     _lib = L
     return L
+
+
+class DecodeStream:
+    """One chunked-decode stream (causal state lives on the model's GPU)."""
+
+    def __init__(self, owner, handle):
+        self._owner, self._h = owner, handle
+
+    def push(self, codes: np.ndarray) -> np.ndarray:
+        """codes [n,16] int32 -> PCM [n*1920] float32 for exactly these frames."""
+        ac = np.ascontiguousarray(codes, dtype=np.int32).reshape(-1, self._owner.config.num_quantizers)
+        out = np.empty(ac.shape[0] * self._owner.config.total_upsample, dtype=np.float32)
+        _check(lib().q3tts_stream_push(self._h, ac.ctypes.data, ac.shape[0], out.ctypes.data))
+        return out
+
+    @property
+    def frames(self) -> int:
+        return int(lib().q3tts_stream_frames(self._h))
+
+    def close(self) -> None:
+        if self._h:
+            lib().q3tts_stream_close(self._h)
+            self._h = None
 
 
 def _check(status: int) -> None:
@@ -283,6 +307,27 @@ class Qwen3TTSSpeechTokenizer:
         _check(lib().q3tts_decode_varlen(self._h, packed.ctypes.data, offs.ctypes.data, n, pcm.ctypes.data,
                                          lengths.ctypes.data))
         return [pcm[offs[i] * up: offs[i + 1] * up] for i in range(n)], lengths
+
+    # ---- chunked streaming (Q3TTS_ATTN_CAUSAL_SW; the reference only streams token ids, Qwen3+Streaming.swift) ----
+    def open_stream(self) -> "DecodeStream":
+        h = C.c_void_p()
+        _check(lib().q3tts_stream_open(self._h, C.byref(h)))
+        return DecodeStream(self, h)
+
+    def push_streams(self, streams: Sequence["DecodeStream"], chunks: Sequence[np.ndarray]):
+        """One chunk [n_i,16] for each stream, decoded in ONE batched launch chain; returns the list of PCM chunks."""
+        n = len(streams)
+        if n != len(chunks):
+            raise AudioDecodingFailed(1, "streams and chunks differ in length")
+        up = self.config.total_upsample
+        arrs = [np.ascontiguousarray(ch, dtype=np.int32).reshape(-1, self.config.num_quantizers) for ch in chunks]
+        outs = [np.empty(a.shape[0] * up, dtype=np.float32) for a in arrs]
+        hs = (C.c_void_p * n)(*[s._h for s in streams])
+        cs = (C.c_void_p * n)(*[a.ctypes.data for a in arrs])
+        ps = (C.c_void_p * n)(*[o.ctypes.data for o in outs])
+        ns = (C.c_int32 * n)(*[a.shape[0] for a in arrs])
+        _check(lib().q3tts_stream_push_batch(hs, n, cs, ns, ps))
+        return outs
 
     # ---- device-pointer path (used by bench.py: inputs already resident in HBM) ----
     def decode_device(self, d_codes_ptr: int, B: int, T: int, d_pcm_ptr: int, d_lengths_ptr: int = 0,
