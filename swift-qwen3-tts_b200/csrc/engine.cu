@@ -461,9 +461,6 @@ void gemm(Ctx& x, const GemmW& w, const void* A, int rows_per_frame, const Epi& 
   }
   if (m.op_dtype != DT_F32 && tc2_supported(p, m.op_dtype)) {
     cudaError_t err = launch_conv_gemm_tc2(p, x.g, m.op_dtype, y_dtype, x.s);
-    if (err != cudaSuccess) throw Error(Q3TTS_ECUDA, std::string("tcgen05 GEMM (v2) launch: ") + cudaGetErrorString(err));
-  } else if (m.op_dtype != DT_F32 && tc_supported(p, m.op_dtype)) {
-    cudaError_t err = launch_conv_gemm_tc(p, x.g, m.op_dtype, y_dtype, x.s);
     if (err != cudaSuccess) throw Error(Q3TTS_ECUDA, std::string("tcgen05 GEMM launch: ") + cudaGetErrorString(err));
   } else {
     launch_conv_gemm_simt(p, x.g, m.op_dtype, y_dtype, x.s);

@@ -100,12 +100,9 @@ void launch_block_copy(const CopyItem* d_items, int n_items, cudaStream_t s);
 // float <-> 16-bit conversion of packed weights.
 void launch_convert(const float* src, void* dst, int dtype, int64_t n, cudaStream_t s);
 
-// ---- tcgen05 tensor-core path (kernels_tc.cu) -------------------------------------------------
-bool tc_supported(const ConvGemmParams& p, int op_dtype);
+// ---- tcgen05 tensor-core path (kernels_tc2.cu) -------------------------------------------------
 // A/W/out_a are `op_dtype` (F16/BF16) operands, fp32 accumulate in TMEM; res/out_y are `y_dtype`.
-cudaError_t launch_conv_gemm_tc(const ConvGemmParams& p, const BatchGeom& g, int op_dtype, int y_dtype,
-                                cudaStream_t s);
-// Second generation (kernels_tc2.cu): halo tiles (one TMA box serves every tap) + cluster-multicast weights.
+// Halo tiles (one TMA box serves every tap of a 64-channel block), CTA-pair MMA, smem-resident weights, fused epilogues.
 bool tc2_supported(const ConvGemmParams& p, int op_dtype);
 cudaError_t launch_conv_gemm_tc2(const ConvGemmParams& p, const BatchGeom& g, int op_dtype, int y_dtype,
                                  cudaStream_t s);

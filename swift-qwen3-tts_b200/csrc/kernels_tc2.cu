@@ -1,7 +1,8 @@
-// tcgen05 multi-tap GEMM, second generation: HALO tiles + CTA-pair MMA + lean issue loops.
+// tcgen05 multi-tap GEMM: HALO tiles + CTA-pair MMA + lean issue loops -- the tensor-core engine behind every conv, linear and
+// transposed conv of the decoder in the 16-bit modes (see kernels.cuh for the multi-tap GEMM definition).
 //
-// v1 (kernels_tc.cu) re-reads the activation tile once per tap and the weight tile once per 128-row tile; ncu showed
-// block3's conv7 moving 18 GB L2->SM for 1.1 GB of input (profiles/r1_v1_*).  Here:
+// The first version of this kernel re-read the activation tile once per tap and the weight tile once per 128-row tile; ncu
+// showed block3's conv7 moving 18 GB L2->SM for 1.1 GB of input (profiles/r1_v1_*).  Here:
 //  * the A operand of ALL taps of a 64-channel block comes from ONE TMA box of 128 + (taps-1)*dil rows (the halo
 //    tile).  Tap j is the same smem tile viewed from row j*dil: its UMMA descriptor simply starts j*dil*128 bytes
 //    later (the 128B swizzle is a function of the absolute smem address, which TMA and the MMA unit share);
@@ -46,7 +47,6 @@ struct Tc2Params {
   int N, BN, Cin, taps, dil, ncb, halo;          // halo = (taps-1)*dil rows in front of every tile
   int tiles_per_utt, n_tiles, m_tiles_total, cs; // cs = cluster size (1 or 2)
   uint32_t idesc, a_stage_bytes, a_tx_bytes, w_stage_bytes;
-  int desc_mode;                                 // 1: base_offset 0, 2: base_offset = (addr >> 7) & 7
   int na, nw;                                    // ring depths (A halo tiles, W stages)
   int wg, ngroups;                               // taps per W stage; W stages per 64-channel block
   uint32_t w_tap_bytes;                          // bytes of one tap's weight tile in this CTA (BN/cs rows x 128 B)
@@ -603,7 +603,7 @@ cudaError_t launch_variant(const cudaLaunchConfig_t& cfg, bool pair, bool block,
 }
 }  // namespace
 
-// 0 = v1 (per-tap loads), 1 = v2 with base_offset 0 (default), 2 = v2 with base_offset from the start address
+// Q3TTS_TC_HALO=0 disables the tensor-core path (CUDA-core 16-bit GEMM everywhere: a debugging aid)
 int tc2_mode() {
   static const int m = env_int("Q3TTS_TC_HALO", 1);
   return m;
@@ -676,7 +676,6 @@ cudaError_t launch_conv_gemm_tc2(const ConvGemmParams& p, const BatchGeom& g, in
     q.ngroups = (p.taps + q.wg - 1) / q.wg;
   }
   q.w_stage_bytes = q.w_tap_bytes * (uint32_t)q.wg;
-  q.desc_mode = tc2_mode();
   q.bias = p.bias; q.act = p.act;
   q.res = p.res; q.ldres = p.ldres; q.res_bstride = p.res_bstride; q.scale = p.scale;
   q.out_y = p.out_y; q.ldy = p.ldy; q.y_bstride = p.y_bstride;

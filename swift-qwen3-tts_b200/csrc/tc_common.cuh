@@ -136,13 +136,6 @@ __device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
-// Descriptor for a K-major SW128 tile whose first row is NOT at a 1024-byte boundary (row-shifted view of a halo
-// tile).  base_offset (bits [49,52)) = (start address >> 7) & 7 when `with_base_offset`.
-__device__ __forceinline__ uint64_t make_smem_desc_shifted(uint32_t saddr, bool with_base_offset) {
-  uint64_t d = make_smem_desc(saddr);
-  if (with_base_offset) d |= (uint64_t)((saddr >> 7) & 7) << 49;
-  return d;
-}
 
 // ---- TMA store (smem -> global) and sub-CTA named barriers -------------------------------------------------
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
