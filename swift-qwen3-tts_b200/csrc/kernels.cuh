@@ -85,6 +85,11 @@ void launch_tail(const void* a, int a_dtype, int64_t a_bstride, const float* w /
                  float* pcm, const int64_t* pcm_base, float* tap, int64_t tap_bstride, const BatchGeom& g,
                  int rows_per_frame, cudaStream_t s);
 
+// Same op on the warp-level tensor path for 16-bit operands (kernels_attn.cu): [rows x C] . [C x 8] with HMMA, then the 7-tap diagonal sum.
+bool tail_mma_supported(int dtype, int C);
+void launch_tail_mma(const void* a, int dtype, int64_t a_bstride, const float* w, float bias, int C, float* pcm,
+                     const int64_t* pcm_base, float* tap, int64_t tap_bstride, const BatchGeom& g, int rows_per_frame, cudaStream_t s);
+
 // audioLengths = count(code[b,t,0] > 0) * rate (ST.swift:831-833).
 void launch_lengths(const int32_t* codes, const int64_t* code_base, int64_t st, const int* len_frames, int B,
                     int rate, int32_t* out, cudaStream_t s);

@@ -1,3 +1,5 @@
+// Warp-level mma.sync kernels for the two small ops that are not worth a tcgen05 pipeline: attention and the tail conv.
+//
 // Tensor-core attention for the decoder's pre-transformer (ST.swift:512-528): softmax(scale * Q K^T [+ mask]) V per
 // (utterance, head), head_dim 64, 16-bit operands, fp32 softmax statistics and output accumulators.
 // Attention is 0.1-0.25 % of the decoder's FLOPs and T <= a few thousand, so this is a compact
@@ -6,6 +8,8 @@
 // Keys are limited to the utterance's own frames, so padded batch slots never leak into valid frames.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+
+#include <type_traits>
 
 #include "kernels.cuh"
 
@@ -154,6 +158,81 @@ attention_mma_kernel(const T16* __restrict__ qkv, T16* __restrict__ out, BatchGe
   }
 }
 
+
+// ---- tail: outConv (C -> 1, k = 7, causal) + bias + clip (ST.swift:674-678, 688, 781) -------------------------------------
+// out[t] = b + sum_j sum_c w[j][c] a[t-6+j][c] = sum_j P[t-6+j][j] with P = A[rows x C] . W^T[C x 8] (7 taps + one zero
+// column): a GEMM with N = 8, i.e. exactly one HMMA m16n8k16 n-tile.  The scalar version spent ~1400 instructions per output
+// sample (672 conversions + 672 FMAs) and ran at 1.7 TB/s; here a 16-row group costs C/16 ldmatrix + 2*C/16 HMMA.  The fp32
+// weights are split into hi + lo 16-bit halves (two MMAs) so the result keeps fp32-weight accuracy.
+constexpr int TT_ROWS = 128, TT_HALO = 6, TT_IN = 144;   // outputs per CTA; input rows = 134 rounded up to 9 groups of 16
+
+template <typename T16, int C>
+__global__ void __launch_bounds__(128)
+tail_mma_kernel(const T16* __restrict__ a, int64_t a_bstride, const float* __restrict__ w /*[7][C]*/, float bias, float* __restrict__ pcm,
+                const int64_t* __restrict__ pcm_base, float* __restrict__ tap, int64_t tap_bstride, BatchGeom g, int rows_per_frame,
+                int tiles_per_utt) {
+  constexpr int STRIDE = C + 8, V = C / 8, KS = C / 16;
+  __shared__ __align__(16) T16 tile[TT_IN * STRIDE];
+  __shared__ float P[TT_IN][8];
+  const int b = blockIdx.x / tiles_per_utt;
+  const int64_t t0 = (int64_t)(blockIdx.x % tiles_per_utt) * TT_ROWS;
+  const int64_t slot_rows = (int64_t)g.Tmax * rows_per_frame, valid = (int64_t)g.len_frames[b] * rows_per_frame;
+  if (t0 >= valid) return;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tg = lane & 3;
+  const T16* ab = a + (int64_t)b * a_bstride;
+  // all of a thread's 16-byte loads are issued before the first store: one HBM round trip per CTA instead of one per chunk
+  constexpr int NLD = (TT_IN * V + 127) / 128;
+  uint4 ld[NLD];
+#pragma unroll
+  for (int i = 0; i < NLD; ++i) {
+    const int idx = tid + i * 128, row = idx / V, c8 = idx % V;
+    const int64_t tin = t0 - TT_HALO + row;
+    ld[i] = make_uint4(0, 0, 0, 0);
+    if (idx < TT_IN * V && tin >= 0 && tin < slot_rows && row < TT_ROWS + TT_HALO) ld[i] = __ldg((const uint4*)(ab + tin * C + c8 * 8));
+  }
+#pragma unroll
+  for (int i = 0; i < NLD; ++i) {
+    const int idx = tid + i * 128, row = idx / V, c8 = idx % V;
+    if (idx < TT_IN * V) *(uint4*)&tile[row * STRIDE + c8 * 8] = ld[i];
+  }
+  // B fragments (col-major [K][8]): b0 = W[k = 2tg, 2tg+1][n = gq], b1 = W[k = 2tg+8, +9][n = gq]; tap 7 is a zero column
+  uint32_t bh[KS][2], bl[KS][2];
+#pragma unroll
+  for (int kk = 0; kk < KS; ++kk)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int c = kk * 16 + 2 * tg + 8 * h;
+      const float w0 = gq < 7 ? __ldg(w + gq * C + c) : 0.f, w1 = gq < 7 ? __ldg(w + gq * C + c + 1) : 0.f;
+      const uint32_t hi = Mma<T16>::pack(w0, w1);
+      float2 hf;
+      if (sizeof(T16) == 2 && std::is_same<T16, __half>::value) hf = __half22float2(*(const __half2*)&hi);
+      else hf = __bfloat1622float2(*(const __nv_bfloat162*)&hi);
+      bh[kk][h] = hi;
+      bl[kk][h] = Mma<T16>::pack(w0 - hf.x, w1 - hf.y);
+    }
+  __syncthreads();
+  for (int grp = warp; grp < TT_IN / 16; grp += 4) {
+    float c4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int kk = 0; kk < KS; ++kk) {
+      uint32_t af[4];
+      ldsm_x4(af, smem_addr(&tile[(grp * 16 + (lane & 15)) * STRIDE + kk * 16 + (lane >> 4) * 8]));
+      Mma<T16>::run(c4, af, bh[kk][0], bh[kk][1]);
+      Mma<T16>::run(c4, af, bl[kk][0], bl[kk][1]);
+    }
+    *(float2*)&P[grp * 16 + gq][2 * tg] = make_float2(c4[0], c4[1]);
+    *(float2*)&P[grp * 16 + gq + 8][2 * tg] = make_float2(c4[2], c4[3]);
+  }
+  __syncthreads();
+  const int64_t t = t0 + tid;
+  if (t < valid) {
+    float v = bias;
+#pragma unroll
+    for (int j = 0; j < 7; ++j) v += P[tid + j][j];      // input row t-6+j sits at tile row (t - t0) + j
+    if (tap) tap[(int64_t)b * tap_bstride + t] = v;
+    pcm[pcm_base[b] + t] = fminf(fmaxf(v, -1.0f), 1.0f);
+  }
+}
 }  // namespace
 
 bool attention_mma_supported(int dtype, int hd) { return (dtype == DT_F16 || dtype == DT_BF16) && hd == 64; }
@@ -164,6 +243,18 @@ void launch_attention_mma(const void* qkv, int dtype, void* out, const BatchGeom
   const float sl2 = scale * 1.4426950408889634f;
   if (dtype == DT_F16) attention_mma_kernel<__half><<<grid, 128, 0, s>>>((const __half*)qkv, (__half*)out, g, nh, nkv, sl2, causal_window);
   else attention_mma_kernel<__nv_bfloat16><<<grid, 128, 0, s>>>((const __nv_bfloat16*)qkv, (__nv_bfloat16*)out, g, nh, nkv, sl2, causal_window);
+}
+
+bool tail_mma_supported(int dtype, int C) { return (dtype == DT_F16 || dtype == DT_BF16) && (C == 96 || C == 64 || C == 128); }
+
+void launch_tail_mma(const void* a, int dtype, int64_t a_bstride, const float* w, float bias, int C, float* pcm, const int64_t* pcm_base,
+                     float* tap, int64_t tap_bstride, const BatchGeom& g, int rows_per_frame, cudaStream_t s) {
+  const int tiles = (int)(((int64_t)g.Tmax * rows_per_frame + TT_ROWS - 1) / TT_ROWS);
+  const unsigned blocks = (unsigned)(g.B * tiles);
+#define Q3_TAILM(T, CC) tail_mma_kernel<T, CC><<<blocks, 128, 0, s>>>((const T*)a, a_bstride, w, bias, pcm, pcm_base, tap, tap_bstride, g, rows_per_frame, tiles)
+  if (dtype == DT_F16) { if (C == 96) Q3_TAILM(__half, 96); else if (C == 64) Q3_TAILM(__half, 64); else Q3_TAILM(__half, 128); }
+  else { if (C == 96) Q3_TAILM(__nv_bfloat16, 96); else if (C == 64) Q3_TAILM(__nv_bfloat16, 64); else Q3_TAILM(__nv_bfloat16, 128); }
+#undef Q3_TAILM
 }
 
 }  // namespace q3

@@ -495,6 +495,11 @@ tail16_kernel(const T16* a, int64_t a_bstride, float bias, float* pcm, const int
 void launch_tail(const void* a, int a_dtype, int64_t a_bstride, const float* w, float bias, int C, float* pcm,
                  const int64_t* pcm_base, float* tap, int64_t tap_bstride, const BatchGeom& g, int rows_per_frame,
                  cudaStream_t s) {
+  static const bool no_mma_tail = [] { const char* e = getenv("Q3TTS_NO_MMA_TAIL"); return e && e[0] == '1'; }();
+  if (!no_mma_tail && tail_mma_supported(a_dtype, C)) {
+    launch_tail_mma(a, a_dtype, a_bstride, w, bias, C, pcm, pcm_base, tap, tap_bstride, g, rows_per_frame, s);
+    return;
+  }
   if (a_dtype != DT_F32 && (C == 96 || C == 72)) {
     cudaMemcpyToSymbolAsync(c_tail_w, w, (size_t)7 * C * sizeof(float), 0, cudaMemcpyDeviceToDevice, s);
     const int tiles = (int)(((int64_t)g.Tmax * rows_per_frame + TAIL_TILE - 1) / TAIL_TILE);
