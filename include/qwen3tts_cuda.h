@@ -206,6 +206,10 @@ int q3tts_debug_conv_gemm(int32_t B, int32_t rows, int32_t Cin, int32_t N, int32
  * the same unit composed from three CUDA-core GEMM launches; out_snake = apply the consumer's SnakeBeta. */
 int q3tts_debug_resunit(int32_t B, int32_t rows, int32_t dil, int32_t out_snake, int32_t precision,
                         int32_t iters, float* ms_out, float* max_diff);
+/* The residual unit fused into the tcgen05 GEMM (C = 128 or 192: conv7 + snake -> smem operand tile -> conv1 +
+ * residual [+ snake]) against two CUDA-core GEMM launches.                                                          */
+int q3tts_debug_fused_unit(int32_t B, int32_t rows, int32_t C, int32_t dil, int32_t with_operand, int32_t precision,
+                           int32_t iters, float* ms_out, float* max_diff_y, float* max_diff_a);
 
 #ifdef __cplusplus
 }

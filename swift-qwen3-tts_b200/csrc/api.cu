@@ -773,6 +773,119 @@ int q3tts_debug_resunit(int32_t B, int32_t rows, int32_t dil, int32_t out_snake,
   });
 }
 
+// The residual unit fused into the tcgen05 GEMM (conv7 + snake -> smem operand tile -> conv1 + residual [+ snake], kernels_tc2.cu)
+// against the same unit as two CUDA-core GEMM launches, on seeded random data; then `iters` timed launches.
+int q3tts_debug_fused_unit(int32_t B, int32_t rows, int32_t C, int32_t dil, int32_t with_operand, int32_t precision, int32_t iters,
+                           float* ms_out, float* max_diff_y, float* max_diff_a) {
+  return guarded([&]() {
+    if (B < 1 || rows < 1 || C < 64 || dil < 1) return fail(Q3TTS_EINVAL, "bad shape");
+    const int op = precision == Q3TTS_PREC_BF16 ? DT_BF16 : DT_F16;
+    cudaStream_t s = nullptr;
+    CUDA_OK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    std::vector<void*> allocs;
+    auto dmalloc = [&](size_t bytes) { void* d = nullptr; CUDA_OK(cudaMalloc(&d, bytes)); allocs.push_back(d); return d; };
+    uint64_t seed = 0xA0761D6478BD642Full ^ ((uint64_t)C << 20) ^ (uint64_t)dil;
+    auto rnd = [&]() { seed = seed * 6364136223846793005ull + 1442695040888963407ull; return (float)((seed >> 40) & 0xFFFFFF) / 8388608.0f - 1.0f; };
+    auto upload16 = [&](size_t n, float scale) {
+      std::vector<float> h(n);
+      for (auto& v : h) v = rnd() * scale;
+      float* d32 = (float*)dmalloc(n * 4);
+      void* d16 = dmalloc(n * 2);
+      CUDA_OK(cudaMemcpyAsync(d32, h.data(), n * 4, cudaMemcpyHostToDevice, s));
+      CUDA_OK(cudaStreamSynchronize(s));
+      launch_convert(d32, d16, op, (int64_t)n, s);
+      return d16;
+    };
+    auto upload32 = [&](size_t n, float scale, float offset) {
+      std::vector<float> h(n);
+      for (auto& v : h) v = offset + rnd() * scale;
+      float* d = (float*)dmalloc(n * 4);
+      CUDA_OK(cudaMemcpyAsync(d, h.data(), n * 4, cudaMemcpyHostToDevice, s));
+      CUDA_OK(cudaStreamSynchronize(s));
+      return d;
+    };
+    const size_t R = (size_t)B * rows;
+    void* A = upload16(R * C, 1.5f);
+    void* X = upload16(R * C, 1.5f);
+    void* W7 = upload16((size_t)7 * C * C, 1.0f / sqrtf(7.0f * C));
+    void* W1 = upload16((size_t)C * C, 1.0f / sqrtf((float)C));
+    float* b7 = upload32((size_t)C, 0.1f, 0.f);
+    float* b1 = upload32((size_t)C, 0.1f, 0.f);
+    float *ea[2], *ib[2];
+    for (int i = 0; i < 2; ++i) { ea[i] = upload32((size_t)C, 0.3f, 1.0f); ib[i] = upload32((size_t)C, 0.3f, 1.0f); }
+    std::vector<int> len((size_t)B);
+    long long valid_rows = 0;
+    for (int b = 0; b < B; ++b) { len[(size_t)b] = std::max(1, rows - 211 * b); valid_rows += len[(size_t)b]; }
+    int* d_len = (int*)dmalloc((size_t)B * 4);
+    CUDA_OK(cudaMemcpyAsync(d_len, len.data(), (size_t)B * 4, cudaMemcpyHostToDevice, s));
+    void* Cb = dmalloc(R * C * 2);
+    void* y[2] = {dmalloc(R * C * 2), dmalloc(R * C * 2)};
+    void* a[2] = {dmalloc(R * C * 2), dmalloc(R * C * 2)};
+    for (int w = 0; w < 2; ++w) {
+      CUDA_OK(cudaMemcpyAsync(y[w], X, R * C * 2, cudaMemcpyDeviceToDevice, s));
+      CUDA_OK(cudaMemsetAsync(a[w], 0, R * C * 2, s));
+    }
+    BatchGeom g{B, rows, d_len, valid_rows};
+    auto base = [&](const void* in, const void* w, int taps, int d, const float* bias) {
+      ConvGemmParams p{};
+      p.A = in; p.lda = C; p.a_bstride = (int64_t)rows * C; p.W = w; p.rows_per_frame = 1; p.N = C; p.Cin = C; p.taps = taps; p.dil = d;
+      p.bias = bias; p.act = ACT_NONE; p.lda_out = C; p.ao_bstride = (int64_t)rows * C; p.ldy = C; p.y_bstride = (int64_t)rows * C;
+      p.ldres = C; p.res_bstride = (int64_t)rows * C;
+      return p;
+    };
+    { ConvGemmParams p = base(A, W7, 7, dil, b7); p.out_a = Cb; p.snake_ea = ea[0]; p.snake_ib = ib[0]; launch_conv_gemm_simt(p, g, op, op, s); }
+    { ConvGemmParams p = base(Cb, W1, 1, 1, b1); p.res = y[0]; p.out_y = y[0];
+      if (with_operand) { p.out_a = a[0]; p.snake_ea = ea[1]; p.snake_ib = ib[1]; }
+      launch_conv_gemm_simt(p, g, op, op, s); }
+    ConvGemmParams pf = base(A, W7, 7, dil, b7);
+    pf.snake_ea = ea[0]; pf.snake_ib = ib[0];
+    FusedConv1 f{W1, b1, y[1], y[1], with_operand ? a[1] : nullptr, with_operand ? ea[1] : nullptr, with_operand ? ib[1] : nullptr};
+    if (!tc2_fuse_supported(pf, op)) return fail(Q3TTS_EINVAL, "shape not supported by the fused unit");
+    CUDA_OK(launch_conv_gemm_tc2(pf, g, op, op, s, &f));
+    CUDA_OK(cudaStreamSynchronize(s));
+    auto max_diff = [&](void* d0, void* d1) {
+      std::vector<uint16_t> h0(R * C), h1(R * C);
+      CUDA_OK(cudaMemcpy(h0.data(), d0, R * C * 2, cudaMemcpyDeviceToHost));
+      CUDA_OK(cudaMemcpy(h1.data(), d1, R * C * 2, cudaMemcpyDeviceToHost));
+      auto tof = [&](uint16_t u) {
+        if (op == DT_BF16) { uint32_t v = (uint32_t)u << 16; float f; std::memcpy(&f, &v, 4); return f; }
+        const uint32_t sgn = (u >> 15) & 1, e = (u >> 10) & 31, m = u & 1023;
+        float f = e == 0 ? ldexpf((float)m, -24) : (e == 31 ? INFINITY : ldexpf((float)(m | 1024), (int)e - 25));
+        return sgn ? -f : f;
+      };
+      float worst = 0.f;
+      for (int b = 0; b < B; ++b)
+        for (int t = 0; t < len[(size_t)b]; ++t)
+          for (int n = 0; n < C; ++n) {
+            const size_t i = ((size_t)b * rows + t) * C + n;
+            const float d = fabsf(tof(h0[i]) - tof(h1[i]));
+            if (!(d <= worst)) worst = d;
+          }
+      return worst;
+    };
+    if (max_diff_y) *max_diff_y = max_diff(y[0], y[1]);
+    if (max_diff_a) *max_diff_a = with_operand ? max_diff(a[0], a[1]) : 0.f;
+    if (iters > 0 && ms_out) {
+      cudaEvent_t e0, e1;
+      CUDA_OK(cudaEventCreate(&e0));
+      CUDA_OK(cudaEventCreate(&e1));
+      for (int i = 0; i < 2; ++i) CUDA_OK(launch_conv_gemm_tc2(pf, g, op, op, s, &f));
+      CUDA_OK(cudaEventRecord(e0, s));
+      for (int i = 0; i < iters; ++i) CUDA_OK(launch_conv_gemm_tc2(pf, g, op, op, s, &f));
+      CUDA_OK(cudaEventRecord(e1, s));
+      CUDA_OK(cudaStreamSynchronize(s));
+      float ms = 0;
+      CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+      *ms_out = ms / iters;
+      cudaEventDestroy(e0);
+      cudaEventDestroy(e1);
+    }
+    for (void* d : allocs) cudaFree(d);
+    cudaStreamDestroy(s);
+    return (int)Q3TTS_OK;
+  });
+}
+
 // ---- measurement --------------------------------------------------------------------------------------------
 int q3tts_profile_enable(q3tts_model* h, int32_t enable) {
   if (!h) return fail(Q3TTS_EINVAL, "model is NULL");

@@ -544,12 +544,39 @@ static void run_back(Ctx& x, Plan& P, const void* to, const int64_t* d_pcm_base,
       }
       a_in = P.blk[i].C;
     } else {
+      // conv7 + conv1 of a unit as ONE tcgen05 kernel when the 1x1 conv's operand tile and weights fit in smem (C <= 192):
+      // the conv7 output never goes to HBM.  The operand ping-pongs between the A and C buffers (a unit's output operand
+      // must not overwrite halo rows its later tiles still read).
+      ConvGemmParams probe{};
+      probe.N = Bk.conv7[0].N; probe.Cin = Bk.conv7[0].Cin; probe.lda = probe.Cin; probe.taps = Bk.conv7[0].taps; probe.dil = 9;
+      probe.bias = Bk.conv7[0].bias; probe.snake_ea = Bk.act2[0].ea; probe.act = ACT_NONE;
+      const bool fuse1 = !taps && op != DT_F32 && m.st_dtype == op && Bk.conv1[0].taps == 1 && tc2_fuse_supported(probe, op);
+      void* abuf[2] = {P.blk[i].A, P.blk[i].C};
       for (int j = 0; j < 3; ++j) {
-        { Epi e; e.out_a = P.blk[i].C; e.snake = &Bk.act2[j]; gemm(x, Bk.conv7[j], P.blk[i].A, rate, e, "conv7"); }
         const SnakeW* next = (j < 2) ? &Bk.act_in_next[j + 1] : block_out;
-        { Epi e; e.res = P.blk[i].X; e.out_y = P.blk[i].X; e.y_dtype = m.st_dtype; e.out_a = P.blk[i].A; e.snake = next; gemm(x, Bk.conv1[j], P.blk[i].C, rate, e, "conv1"); }
+        if (fuse1) {
+          const GemmW& w7 = Bk.conv7[j];
+          const GemmW& w1 = Bk.conv1[j];
+          const int64_t slot = (int64_t)x.g.Tmax * rate;
+          ConvGemmParams p{};
+          p.A = abuf[j & 1]; p.lda = w7.Cin; p.a_bstride = slot * w7.Cin; p.W = w7.w16; p.rows_per_frame = rate;
+          p.N = w7.N; p.Cin = w7.Cin; p.taps = w7.taps; p.dil = w7.dil; p.bias = w7.bias; p.act = ACT_NONE;
+          p.snake_ea = Bk.act2[j].ea; p.snake_ib = Bk.act2[j].ib;
+          FusedConv1 f{w1.w16, w1.bias, P.blk[i].X, P.blk[i].X, abuf[(j + 1) & 1], next->ea, next->ib};
+          const double rows = (double)valid_frames * rate, C = (double)w7.N;
+          const double fl = 2.0 * rows * 8.0 * C * C, by = rows * C * 2.0 * 4.0 + 8.0 * C * C * 2.0;   // A in, X in, X' out, A' out
+          launch_begin(x, "conv7+conv1", fl, by);
+          cudaError_t err = launch_conv_gemm_tc2(p, x.g, op, op, s, &f);
+          if (err != cudaSuccess) throw Error(Q3TTS_ECUDA, std::string("fused residual GEMM launch: ") + cudaGetErrorString(err));
+          launch_end(x);
+          count_launch(x);
+          account(x, fl, by);
+        } else {
+          { Epi e; e.out_a = P.blk[i].C; e.snake = &Bk.act2[j]; gemm(x, Bk.conv7[j], P.blk[i].A, rate, e, "conv7"); }
+          { Epi e; e.res = P.blk[i].X; e.out_y = P.blk[i].X; e.y_dtype = m.st_dtype; e.out_a = P.blk[i].A; e.snake = next; gemm(x, Bk.conv1[j], P.blk[i].C, rate, e, "conv1"); }
+        }
       }
-      a_in = P.blk[i].A;
+      a_in = fuse1 ? abuf[1] : P.blk[i].A;        // three units: A -> C -> A -> C
     }
     static const char* kNames[4] = {"block0", "block1", "block2", "block3"};
     tap(x, kNames[i], P.blk[i].X, m.st_dtype, rate, Bk.cout, Bk.cout);

@@ -109,8 +109,18 @@ void launch_convert(const float* src, void* dst, int dtype, int64_t n, cudaStrea
 // A/W/out_a are `op_dtype` (F16/BF16) operands, fp32 accumulate in TMEM; res/out_y are `y_dtype`.
 // Halo tiles (one TMA box serves every tap of a 64-channel block), CTA-pair MMA, smem-resident weights, fused epilogues.
 bool tc2_supported(const ConvGemmParams& p, int op_dtype);
+// Optional second stage fused into the same kernel (residual unit, ST.swift:430-437): `p` is the unit's k=7 conv with bias + SnakeBeta
+// (p.out_a is not written: the activated result stays in smem as the operand of the 1x1 conv W1 [N][N]), then
+//   v = W1 . that + bias + res;   out_y = v;   out_a = v + ib * sin^2(v * ea)   (out_a / ea / ib may be null: stream only).
+// out_a must not alias p.A (later tiles still read halo rows of p.A); res == out_y (in place) is fine.
+struct FusedConv1 {
+  const void* W1; const float* bias;
+  const void* res; void* out_y; void* out_a;
+  const float* ea; const float* ib;
+};
+bool tc2_fuse_supported(const ConvGemmParams& p, int op_dtype);
 cudaError_t launch_conv_gemm_tc2(const ConvGemmParams& p, const BatchGeom& g, int op_dtype, int y_dtype,
-                                 cudaStream_t s);
+                                 cudaStream_t s, const FusedConv1* fuse = nullptr);
 
 // ---- fused residual unit of the 96-channel block (kernels_res96.cu) ------------------------------------------------
 //   out = X + conv1x1(snake2(conv7_dil(snake1(X)) + b7)) + b1        (ST.swift:430-437), or snake3(that) when ea3 != null.

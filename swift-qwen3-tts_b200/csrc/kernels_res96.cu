@@ -184,7 +184,7 @@ resunit96_kernel(const __grid_constant__ CUtensorMap map_main, const __grid_cons
     w.init(p, g0);
     for (int j = 0; j < q; ++j) {
       const int slot = j % R_SLOTS;
-      if (j >= R_SLOTS) mbar_wait(&slot_free[slot], (uint32_t)(((j - R_SLOTS) / R_SLOTS) & 1));   // conv7 and conv1 of the slot's previous tile are over
+      if (j >= R_SLOTS) mbar_wait_sleep(&slot_free[slot], (uint32_t)(((j - R_SLOTS) / R_SLOTS) & 1));   // conv7 and conv1 of the slot's previous tile are over
       R_STAMP(0, j);
       if (elect_one()) {
         if (w.live(p)) {
@@ -209,11 +209,11 @@ resunit96_kernel(const __grid_constant__ CUtensorMap map_main, const __grid_cons
       const uint32_t idesc = p.idesc7;
       const uint64_t dTap = (uint64_t)(p.dil * 4);             // dil rows x 64 B, in 16-byte units
       const uint32_t tsub16 = p.tsub_bytes >> 4;
-      mbar_wait(w_full, 0);
+      mbar_wait_sleep(w_full, 0);
       for (int i = 0; i <= q; ++i) {
         if (i < q) {
           const int slot = i % R_SLOTS;
-          mbar_wait(&a_ready[slot], (uint32_t)((i / R_SLOTS) & 1));
+          mbar_wait_sleep(&a_ready[slot], (uint32_t)((i / R_SLOTS) & 1));
           tc_fence_after();
           R_STAMP(4, i);
           if (elect_one()) {
@@ -241,8 +241,8 @@ resunit96_kernel(const __grid_constant__ CUtensorMap map_main, const __grid_cons
         }
         if (i >= 1) {
           const int t = i - 1;
-          mbar_wait(&c_ready[t & 1], (uint32_t)((t >> 1) & 1));
-          if (t >= 2) mbar_wait(&acc2_free[t & 1], (uint32_t)(((t - 2) >> 1) & 1));
+          mbar_wait_sleep(&c_ready[t & 1], (uint32_t)((t >> 1) & 1));
+          if (t >= 2) mbar_wait_sleep(&acc2_free[t & 1], (uint32_t)(((t - 2) >> 1) & 1));
           tc_fence_after();
           R_STAMP(6, t);
           if (elect_one()) {
@@ -282,7 +282,7 @@ resunit96_kernel(const __grid_constant__ CUtensorMap map_main, const __grid_cons
       const bool live = w.live(p), first = w.first;
       w.next(p);                                                  // now describes tile j+1
       const bool copy_tail = live && j + 1 < q && w.live(p) && !w.first;
-      mbar_wait(&t_full[slot], (uint32_t)((j / R_SLOTS) & 1));
+      mbar_wait_sleep(&t_full[slot], (uint32_t)((j / R_SLOTS) & 1));
       if (pw == 0) R_STAMP(2, j);
       bool tail_ok = !(copy_tail && j >= R_SLOTS - 1);          // else: conv7 of the next slot's previous tile may still read its halo rows
       if (live) {
@@ -290,7 +290,7 @@ resunit96_kernel(const __grid_constant__ CUtensorMap map_main, const __grid_cons
           const int G2 = G + 2;
           const bool two = G2 < ngroups;
           if (!tail_ok && (two ? G2 : G) * 8 >= R_BM) {            // first iteration that touches the tail (groups ascend)
-            mbar_wait(&c7_done[nslot], (uint32_t)(((j - (R_SLOTS - 1)) / R_SLOTS) & 1));
+            mbar_wait_sleep(&c7_done[nslot], (uint32_t)(((j - (R_SLOTS - 1)) / R_SLOTS) & 1));
             tail_ok = true;
           }
           uint32_t addr[2], naddr[2];
@@ -340,7 +340,7 @@ resunit96_kernel(const __grid_constant__ CUtensorMap map_main, const __grid_cons
     w.init(p, g0);
     for (int t = 0; t < q; ++t) {
       const bool live = w.live(p);
-      mbar_wait(&acc1_full[t & 1], (uint32_t)((t >> 1) & 1));
+      mbar_wait_sleep(&acc1_full[t & 1], (uint32_t)((t >> 1) & 1));
       tc_fence_after();
       if (warp == R_CTRL + R_PW) R_STAMP(8, t);
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((t & 1) * 128 + col_base);
@@ -401,7 +401,7 @@ resunit96_kernel(const __grid_constant__ CUtensorMap map_main, const __grid_cons
       uint4 rr[6];
 #pragma unroll
       for (int c = 0; c < 6; ++c) rr[c] = row_ok ? __ldg(res_row + c) : make_uint4(0, 0, 0, 0);
-      mbar_wait(&acc2_full[u & 1], (uint32_t)((u >> 1) & 1));
+      mbar_wait_sleep(&acc2_full[u & 1], (uint32_t)((u >> 1) & 1));
       tc_fence_after();
       if (warp == R_CTRL + R_PW + R_E1W) R_STAMP(10, u);
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(256 + (u & 1) * 128 + col_base);

@@ -64,6 +64,12 @@ struct Tc2Params {
   void* out_a; int lda_out; long long ao_bstride;
   const float* snake_ea; const float* snake_ib;
   float* out_tap; int ldt; long long tap_bstride;
+  // fused residual unit (block epilogue kernel only): this GEMM is conv7 (+ bias + snake -> a 128B-swizzled operand tile in
+  // smem), followed by the unit's 1x1 conv from that tile (W1 resident in smem) with the usual residual epilogue
+  int fuse, ncb2;
+  uint32_t w1_blk_bytes;                         // one 64-channel block of this CTA's half of W1: (BN/2) rows x 128 B
+  const float* bias2; const float* ea2; const float* ib2;
+  const void* res2; void* out_y2; void* out_a2; long long o2_bstride;
 };
 
 __device__ __forceinline__ void ld4(const float* p, float (&v)[16], int i) {
@@ -94,23 +100,28 @@ __device__ __forceinline__ void issue_taps(uint32_t d_tmem, uint64_t ad, uint64_
 template <typename T16, bool kPair, bool kBlockEpi>
 __global__ void __launch_bounds__(kBlockEpi ? T2_THREADS_BLOCK : T2_THREADS_GENERIC, 1)
 conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
-                     const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_o, Tc2Params p,
-                     int y_is_f32) {
+                     const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_o,
+                     const __grid_constant__ CUtensorMap map_w2, Tc2Params p, int y_is_f32) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* a_ring = smem;
   const int T2_NA = p.na, T2_NW = p.nw;
   uint8_t* w_ring = smem + (size_t)T2_NA * p.a_stage_bytes;
   uint8_t* staging = w_ring + (size_t)T2_NW * p.w_stage_bytes;          // 1024-aligned (all stage sizes are)
-  float* cst = (float*)(staging + p.staging_bytes);   // [bias | ea | ib] x N when staged
-  uint64_t* bars = (uint64_t*)((uint8_t*)cst + (p.cst_staged ? (size_t)3 * p.N * 4 : 0));
+  uint8_t* c_tile = staging + p.staging_bytes;                          // fused unit: conv1's operand, [ncb2][128 rows][128 B]
+  uint8_t* w1s = c_tile + (p.fuse ? (size_t)p.ncb2 * 16384 : 0);        // fused unit: [ncb2][BN/2 rows][128 B]
+  float* cst = (float*)(w1s + (p.fuse ? (size_t)p.ncb2 * p.w1_blk_bytes : 0));   // [bias | ea | ib] x N when staged (x2 when fused)
+  uint64_t* bars = (uint64_t*)((uint8_t*)cst + (p.cst_staged ? (size_t)(p.fuse ? 6 : 3) * p.N * 4 : 0));
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + T2_MAX_NA;
   uint64_t* w_full = a_empty + T2_MAX_NA;
   uint64_t* w_empty = w_full + T2_MAX_NW;
   uint64_t* tmem_full = w_empty + T2_MAX_NW;
   uint64_t* tmem_empty = tmem_full + T2_MAX_ACC;
-  uint32_t* tmem_ptr = (uint32_t*)(tmem_empty + T2_MAX_ACC);
+  uint64_t* tmem_full2 = tmem_empty + T2_MAX_ACC;   // [2] fused unit: conv1 has completed (operand tile free, accumulator = conv1)
+  uint64_t* c_ready = tmem_full2 + 2;               // fused unit: the operand tile of conv1 is written (both CTAs)
+  uint64_t* w1_full = c_ready + 1;
+  uint32_t* tmem_ptr = (uint32_t*)(w1_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cs = p.cs;
@@ -131,6 +142,9 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     for (int i = 0; i < T2_NA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < T2_NW; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], kPair ? 1u : (uint32_t)cs); }
     for (int i = 0; i < p.nacc; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], (uint32_t)((kPair ? 2 : 1) * kEpiWarps)); }
+    for (int i = 0; i < 2; ++i) mbar_init(&tmem_full2[i], 1);
+    mbar_init(c_ready, (uint32_t)((kPair ? 2 : 1) * kEpiWarps));
+    mbar_init(w1_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -147,6 +161,11 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
       cst[i] = __ldg(p.bias + i);
       cst[p.N + i] = p.snake_ea ? __ldg(p.snake_ea + i) : 0.f;
       cst[2 * p.N + i] = p.snake_ib ? __ldg(p.snake_ib + i) : 0.f;
+      if (p.fuse) {
+        cst[3 * p.N + i] = __ldg(p.bias2 + i);
+        cst[4 * p.N + i] = p.ea2 ? __ldg(p.ea2 + i) : 0.f;
+        cst[5 * p.N + i] = p.ib2 ? __ldg(p.ib2 + i) : 0.f;
+      }
     }
   }
   tc_fence_before();
@@ -192,15 +211,24 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     const int wrows = p.BN / cs;
     const int res_es = y_is_f32 ? 4 : 2;
     const int stages_per_tile = p.ncb * p.ngroups;
+    if (kBlockEpi && kPair && p.fuse && elect_one()) {   // the 1x1 conv's weights: resident for the whole kernel
+      if (rank == 0) mbar_expect_tx(w1_full, 2u * (uint32_t)p.ncb2 * p.w1_blk_bytes);
+      for (int cb = 0; cb < p.ncb2; ++cb)
+        tma_load_2d_2sm(w1s + (size_t)cb * p.w1_blk_bytes, &map_w2, w1_full, cb * T2_BK, (int)rank * (p.BN / 2));
+    }
+    __syncwarp();
     for (int item = cid; item < items; item += ncl) {
       int b, t0, n0; bool mine;
       if (!coords(item, b, t0, n0, mine)) continue;
-      if (p.res != nullptr && mine) {
+      const void* res_any = (kBlockEpi && p.fuse) ? p.res2 : p.res;       // fused unit: the residual belongs to the 1x1 stage
+      if (res_any != nullptr && mine) {
         const int valid = __ldg(p.len_frames + b) * p.rows_per_frame;
         const int line_cnt = (p.BN * res_es + 127) / 128;
+        const long long rb = (kBlockEpi && p.fuse) ? p.o2_bstride : p.res_bstride;
+        const int rl = (kBlockEpi && p.fuse) ? p.N : p.ldres;
         for (int r = lane; r < T2_BM; r += 32) {
           if (t0 + r >= valid) break;
-          const char* ptr = (const char*)p.res + ((long long)b * p.res_bstride + (long long)(t0 + r) * p.ldres + n0) * res_es;
+          const char* ptr = (const char*)res_any + ((long long)b * rb + (long long)(t0 + r) * rl + n0) * res_es;
           for (int l = 0; l < line_cnt; ++l) asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr + l * 128));
         }
         __syncwarp();
@@ -266,6 +294,27 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
       uint32_t w_seen = 0;                       // resident weights: bit s = stage s has been waited for once (it never changes again)
       const int which = warp == 1 ? 0 : 1;
       int turn = 0;
+      // fused unit: conv1 of tile k is issued after conv7 of tile k+1 (the tensor pipe stays busy while epilogue 1 of tile k
+      // writes the operand tile); it accumulates into the tile's own accumulator slot, which epilogue 1 has drained.
+      int n_done = 0, prev_acc = 0;
+      auto issue_conv1 = [&]() {
+        mbar_wait(c_ready, (uint32_t)((n_done - 1) & 1));
+        if (n_done == 1) mbar_wait(w1_full, 0u);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t d2 = tmem_base + (uint32_t)(prev_acc * p.acc_stride);
+          const uint64_t ad = desc_fixed | (uint64_t)(smem_u32(c_tile) >> 4), wd = desc_fixed | (uint64_t)(smem_u32(w1s) >> 4);
+          for (int cb = 0; cb < p.ncb2; ++cb) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t a2 = ad + (uint64_t)(cb * (16384 >> 4) + 2 * k), w2 = wd + (uint64_t)(cb * (int)(p.w1_blk_bytes >> 4) + 2 * k);
+              if (kPair) tc_mma_f16_2sm(d2, a2, w2, idesc, (uint32_t)(cb | k)); else tc_mma_f16(d2, a2, w2, idesc, (uint32_t)(cb | k));
+            }
+          }
+          if (kPair) tc_commit_2sm(&tmem_full2[prev_acc], mc_mask); else tc_commit(&tmem_full2[prev_acc]);
+        }
+        __syncwarp();
+      };
       for (int item = cid; item < items; item += ncl) {
         int b, t0, n0; bool mine;
         if (!coords(item, b, t0, n0, mine)) continue;
@@ -324,18 +373,97 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
           }
           if (++sa == T2_NA) { sa = 0; pa ^= 1; }
         }
+        if (kBlockEpi && p.fuse) {
+          if (n_done > 0) issue_conv1();
+          prev_acc = acc;
+          ++n_done;
+        }
         if (++acc == nacc) { acc = 0; pacc ^= 1; }
       }
+      if (kBlockEpi && p.fuse && n_done > 0) issue_conv1();
     }
+  } else if (kBlockEpi && warp >= 4 && p.fuse) {
+    // ================= fused residual unit: epilogue 1 (conv7 -> operand tile) and epilogue 2 (conv1 -> stream, operand) =================
+    const int ew = warp - 4, quarter = warp & 3, grp = ew >> 2;
+    const int nch = p.BN / 32;
+    const int slot_rows = p.Tmax * p.rows_per_frame;
+    const uint32_t cst_u32 = smem_u32(cst);
+    const uint32_t sw128 = (uint32_t)(lane & 7);                         // 128B swizzle: chunk ^= row & 7
+    uint8_t* const c_row = c_tile + (size_t)(quarter * 32 + lane) * 128;
+    const bool has_a2 = p.out_a2 != nullptr;
+    int acc = 0, pv_acc = 0, pv_b = 0, pv_t0 = 0;
+    uint32_t pacc = 0, pv_pacc = 0;
+    bool have_prev = false, pv_mine = false;
+    auto epilogue2 = [&]() {   // of the previous tile: acc = conv1(...) ; + b1 + X -> X' [, snake_next(X')], stored from registers
+      const int trow = pv_t0 + quarter * 32 + lane;
+      const bool ok = pv_mine && trow < slot_rows;
+      const long long off = (long long)min(pv_b, p.B - 1) * p.o2_bstride + (long long)min(trow, slot_rows - 1) * p.N;
+      const T16* res_row = (const T16*)p.res2 + off;
+      uint4 rres[4] = {};
+      if (ok && grp < nch) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) rres[c] = __ldg((const uint4*)(res_row + grp * 32 + 8 * c));
+      }
+      mbar_wait(&tmem_full2[pv_acc], pv_pacc);
+      tc_fence_after();
+      for (int ch = grp; ch < nch; ch += 3) {
+        uint32_t r[32];
+        tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(pv_acc * p.acc_stride + ch * 32), r);
+        if (ok && ch != grp) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) rres[c] = __ldg((const uint4*)(res_row + ch * 32 + 8 * c));
+        }
+        tc_wait_ld();
+        const int n = ch * 32;
+        const uint32_t sb = cst_u32 + 4u * (uint32_t)(3 * p.N + n), se = sb + 4u * (uint32_t)p.N, si = se + 4u * (uint32_t)p.N;
+        uint8_t* row_y = (uint8_t*)((T16*)p.out_y2 + off + n);
+        uint8_t* row_a = (uint8_t*)((T16*)p.out_a2 + off + n);
+        if (has_a2) epi_block_chunk<T16, true, true, true, true>(r, nullptr, nullptr, nullptr, sb, se, si, rres, row_y, row_a, 0u, 0u, ok);
+        else epi_block_chunk<T16, true, true, false, true>(r, nullptr, nullptr, nullptr, sb, se, si, rres, row_y, row_a, 0u, 0u, ok);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (kPair && rank != 0) mbar_arrive_remote(&tmem_empty[pv_acc], 0); else mbar_arrive(&tmem_empty[pv_acc]);
+      }
+    };
+    for (int item = cid; item < items; item += ncl) {
+      int b, t0, n0; bool mine;
+      if (!coords(item, b, t0, n0, mine)) continue;
+      if (have_prev) epilogue2();                                        // also: conv1(prev) no longer reads the operand tile
+      // ---- epilogue 1: acc + b7 -> snake -> conv1's operand tile (128B-swizzled, K-major) ----
+      mbar_wait(&tmem_full[acc], pacc);
+      tc_fence_after();
+      for (int ch = grp; ch < nch; ch += 3) {
+        uint32_t r[32];
+        tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.acc_stride + ch * 32), r);
+        tc_wait_ld();
+        const int n = ch * 32;
+        const uint32_t sb = cst_u32 + 4u * (uint32_t)n, se = sb + 4u * (uint32_t)p.N, si = se + 4u * (uint32_t)p.N;
+        const uint4 none[4] = {};
+        uint8_t* row_a = c_row + (size_t)(ch >> 1) * 16384;
+        epi_block_chunk<T16, false, false, true, true>(r, nullptr, nullptr, nullptr, sb, se, si, none, nullptr, row_a, (uint32_t)((ch & 1) * 4), sw128, true);
+      }
+      fence_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (kPair && rank != 0) mbar_arrive_remote(c_ready, 0); else mbar_arrive(c_ready);
+      }
+      have_prev = true; pv_acc = acc; pv_pacc = pacc; pv_b = b; pv_t0 = t0; pv_mine = mine;
+      if (++acc == p.nacc) { acc = 0; pacc ^= 1; }
+    }
+    if (have_prev) epilogue2();
   } else if (kBlockEpi && warp >= 4) {
     // ================= block epilogue (12 warps) =================
     const int ew = warp - 4, quarter = warp & 3, grp = ew >> 2;          // grp 0..2 takes chunks grp, grp+3, ...
     const int nch = p.BN / 32;
     const bool has_res = p.res != nullptr, has_y = p.out_y != nullptr, has_a = p.out_a != nullptr;
-    uint8_t* buf_a = staging + (size_t)ew * (has_y ? 4096 : 2048);       // this warp's 32 rows x 64 B: a, then y
-    uint8_t* buf_y = buf_a + 2048;
+    uint8_t* buf_a = staging + (size_t)ew * ((has_y && has_a) ? 4096 : 2048);   // this warp's 32 rows x 64 B: a, then y
+    uint8_t* buf_y = buf_a + (has_a ? 2048 : 0);
     const int slot_rows = p.Tmax * p.rows_per_frame;
     const uint32_t cst_u32 = smem_u32(cst);
+    const uint32_t sw64 = (uint32_t)((lane >> 1) & 3);                    // SWIZZLE_64B staging rows
     int acc = 0;
     uint32_t pacc = 0;
     for (int item = cid; item < items; item += ncl) {
@@ -363,8 +491,8 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
           __syncwarp();
           const int n = n0 + ch * 32;
           const uint32_t sb = cst_u32 + 4u * (uint32_t)n, se = sb + 4u * (uint32_t)p.N, si = se + 4u * (uint32_t)p.N;
-#define Q3_EPI(RES, Y, SM) epi_block_chunk<T16, RES, Y, true, SM>(r, p.bias + n, p.snake_ea + n, p.snake_ib + n, sb, se, si, rres, buf_y, buf_a, lane)
-#define Q3_EPI_Y(SM) epi_block_chunk<T16, false, true, false, SM>(r, p.bias + n, nullptr, nullptr, sb, se, si, rres, buf_y, buf_a, lane)
+#define Q3_EPI(RES, Y, SM) epi_block_chunk<T16, RES, Y, true, SM>(r, p.bias + n, p.snake_ea + n, p.snake_ib + n, sb, se, si, rres, buf_y + lane * 64, buf_a + lane * 64, 0u, sw64, true)
+#define Q3_EPI_Y(SM) epi_block_chunk<T16, false, true, false, SM>(r, p.bias + n, nullptr, nullptr, sb, se, si, rres, buf_y + lane * 64, buf_a + lane * 64, 0u, sw64, true)
           if (!has_a) {   // stream output only (the consumer applies its own activation)
             if (p.cst_staged) Q3_EPI_Y(true); else Q3_EPI_Y(false);
           } else if (p.cst_staged) {
@@ -586,7 +714,7 @@ int env_int(const char* name, int dflt) {
 
 template <typename T16>
 cudaError_t launch_variant(const cudaLaunchConfig_t& cfg, bool pair, bool block, const CUtensorMap& ma, const CUtensorMap& mw,
-                           const CUtensorMap& my, const CUtensorMap& mo, const Tc2Params& q, int yf) {
+                           const CUtensorMap& my, const CUtensorMap& mo, const CUtensorMap& mw2, const Tc2Params& q, int yf) {
   static std::once_flag once;
   std::call_once(once, []() {
     cudaFuncSetAttribute(conv_gemm_tc2_kernel<T16, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -595,11 +723,11 @@ cudaError_t launch_variant(const cudaLaunchConfig_t& cfg, bool pair, bool block,
     cudaFuncSetAttribute(conv_gemm_tc2_kernel<T16, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   });
   if (pair) {
-    if (block) return cudaLaunchKernelEx(&cfg, conv_gemm_tc2_kernel<T16, true, true>, ma, mw, my, mo, q, yf);
-    return cudaLaunchKernelEx(&cfg, conv_gemm_tc2_kernel<T16, true, false>, ma, mw, my, mo, q, yf);
+    if (block) return cudaLaunchKernelEx(&cfg, conv_gemm_tc2_kernel<T16, true, true>, ma, mw, my, mo, mw2, q, yf);
+    return cudaLaunchKernelEx(&cfg, conv_gemm_tc2_kernel<T16, true, false>, ma, mw, my, mo, mw2, q, yf);
   }
-  if (block) return cudaLaunchKernelEx(&cfg, conv_gemm_tc2_kernel<T16, false, true>, ma, mw, my, mo, q, yf);
-  return cudaLaunchKernelEx(&cfg, conv_gemm_tc2_kernel<T16, false, false>, ma, mw, my, mo, q, yf);
+  if (block) return cudaLaunchKernelEx(&cfg, conv_gemm_tc2_kernel<T16, false, true>, ma, mw, my, mo, mw2, q, yf);
+  return cudaLaunchKernelEx(&cfg, conv_gemm_tc2_kernel<T16, false, false>, ma, mw, my, mo, mw2, q, yf);
 }
 }  // namespace
 
@@ -619,7 +747,18 @@ bool tc2_supported(const ConvGemmParams& p, int op_dtype) {
   return encode_fn2() != nullptr;
 }
 
-cudaError_t launch_conv_gemm_tc2(const ConvGemmParams& p, const BatchGeom& g, int op_dtype, int y_dtype, cudaStream_t s) {
+bool tc2_fuse_supported(const ConvGemmParams& p, int op_dtype) {
+  // Opt-in: with N = 192 TMEM holds two accumulators only, so conv1(i-1) queues behind conv7(i) and epilogue 2 cannot overlap the
+  // next conv7 -- measured 0.84 ms vs 0.68 ms for the two separate kernels (960 k rows).  Pays off only for N <= 128.
+  static const int on = env_int("Q3TTS_TC_FUSE", 0);
+  if (!on || !tc2_supported(p, op_dtype)) return false;
+  // one N tile (the 1x1 conv needs every channel of the row), whole 64-channel blocks, operand tile + W1 half + rings in smem
+  return p.N == p.Cin && p.N % 64 == 0 && p.N <= 192 && pick_bn2(p.N, true) == p.N && p.bias && p.snake_ea && p.act == ACT_NONE &&
+         !p.res && !p.out_y && !p.out_tap && !p.scale;
+}
+
+cudaError_t launch_conv_gemm_tc2(const ConvGemmParams& p, const BatchGeom& g, int op_dtype, int y_dtype, cudaStream_t s,
+                                 const FusedConv1* fuse) {
   EncodeTiledFn enc = encode_fn2();
   if (!enc) return cudaErrorNotSupported;
   static const int cs_env = env_int("Q3TTS_TC_CLUSTER", 2);
@@ -628,7 +767,7 @@ cudaError_t launch_conv_gemm_tc2(const ConvGemmParams& p, const BatchGeom& g, in
   static const int resident_env = env_int("Q3TTS_TC_W_RESIDENT", 1);
   static const int nacc_env = env_int("Q3TTS_TC_NACC", 4);
   static const int cst_env = env_int("Q3TTS_TC_CST", 1);
-  const bool epi_block = block_env && block_epilogue_ok(p, y_dtype);
+  const bool epi_block = fuse != nullptr || (block_env && block_epilogue_ok(p, y_dtype));
   const int BN = pick_bn2(p.N, epi_block);
   const int slot_rows = g.Tmax * p.rows_per_frame;
   const int halo = (p.taps - 1) * p.dil;
@@ -640,8 +779,9 @@ cudaError_t launch_conv_gemm_tc2(const ConvGemmParams& p, const BatchGeom& g, in
   q.m_tiles_total = g.B * q.tiles_per_utt;
   int cs = (cs_env == 2 && BN % 16 == 0 && q.m_tiles_total >= 2) ? 2 : 1;
   const bool pair = pair_env && cs == 2;
+  if (fuse && !pair) return cudaErrorNotSupported;
   q.cs = cs;
-  q.nacc = (BN <= 128 && nacc_env >= 4) ? 4 : 2;
+  q.nacc = (!fuse && BN <= 128 && nacc_env >= 4) ? 4 : 2;   // the fused unit tracks two conv1 accumulators
   q.acc_stride = (int)T2_TMEM_COLS / q.nacc;
   const CUtensorMapDataType dt = op_dtype == DT_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   CUtensorMap map_a, map_w;
@@ -670,7 +810,7 @@ cudaError_t launch_conv_gemm_tc2(const ConvGemmParams& p, const BatchGeom& g, in
   q.w_tap_bytes = (uint32_t)(pair ? BN / 2 : BN) * 128u;     // pair mode: each CTA stages half of the weight tile
   {  // several taps share one W stage when the tiles are small: one barrier wait / commit per wg*nk MMAs
     static const int wg_env = env_int("Q3TTS_TC_WG_KB", 40);
-    const int wg_max = std::max(1, (wg_env * 1024) / (int)q.w_tap_bytes);
+    const int wg_max = fuse ? 1 : std::max(1, (wg_env * 1024) / (int)q.w_tap_bytes);   // fused unit: small stages, deep ring
     q.ngroups = (p.taps + wg_max - 1) / wg_max;
     q.wg = (p.taps + q.ngroups - 1) / q.ngroups;
     q.ngroups = (p.taps + q.wg - 1) / q.wg;
@@ -685,9 +825,22 @@ cudaError_t launch_conv_gemm_tc2(const ConvGemmParams& p, const BatchGeom& g, in
   // 16-bit outputs leave through smem staging + TMA stores
   static const int tma_store_env = env_int("Q3TTS_TC_TMA_STORE", 1);
   const int yf = y_dtype == DT_F32;
-  q.tma_y = (epi_block || tma_store_env) && p.out_y && !yf && p.act != ACT_SWIGLU;
-  q.tma_a = (epi_block || tma_store_env) && p.out_a && p.act != ACT_SWIGLU;
-  q.cst_staged = epi_block && cst_env && p.N <= T2_CST_MAX_N;
+  q.tma_y = !fuse && (epi_block || tma_store_env) && p.out_y && !yf && p.act != ACT_SWIGLU;
+  q.tma_a = !fuse && (epi_block || tma_store_env) && p.out_a && p.act != ACT_SWIGLU;
+  q.cst_staged = epi_block && (cst_env || fuse) && p.N <= T2_CST_MAX_N;
+  CUtensorMap map_w2 = map_w;
+  if (fuse) {
+    q.fuse = 1; q.ncb2 = p.N / T2_BK; q.w1_blk_bytes = (uint32_t)(BN / 2) * 128u;
+    q.bias2 = fuse->bias; q.ea2 = fuse->ea; q.ib2 = fuse->ib;
+    q.res2 = fuse->res; q.out_y2 = fuse->out_y; q.out_a2 = fuse->out_a; q.o2_bstride = (long long)slot_rows * p.N;
+    cuuint64_t dims[2] = {(cuuint64_t)p.N, (cuuint64_t)p.N};
+    cuuint64_t strides[1] = {(cuuint64_t)p.N * 2};
+    cuuint32_t box[2] = {T2_BK, (cuuint32_t)(BN / 2)};
+    cuuint32_t es[2] = {1, 1};
+    if (enc(&map_w2, dt, 2, const_cast<void*>(fuse->W1), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return cudaErrorInvalidValue;
+  }
   CUtensorMap map_y = map_a, map_o = map_a;   // placeholders when unused
   auto out_map = [&](CUtensorMap* m, void* base, int ld, long long bstride) -> bool {
     cuuint64_t dims[3] = {(cuuint64_t)ld, (cuuint64_t)slot_rows, (cuuint64_t)g.B};
@@ -701,8 +854,8 @@ cudaError_t launch_conv_gemm_tc2(const ConvGemmParams& p, const BatchGeom& g, in
   };
   if (q.tma_y && !out_map(&map_y, p.out_y, p.ldy, p.y_bstride)) return cudaErrorInvalidValue;
   if (q.tma_a && !out_map(&map_o, p.out_a, p.lda_out, p.ao_bstride)) return cudaErrorInvalidValue;
-  q.staging_bytes = !(q.tma_y || q.tma_a) ? 0u : (epi_block ? (uint32_t)T2_EPI_WARPS_BLOCK * (q.tma_y ? 4096u : 2048u) : T2_STAGING_BYTES);
-  const size_t fixed = q.staging_bytes + (q.cst_staged ? (size_t)3 * p.N * 4 : 0) + 512 + 1024;
+  q.staging_bytes = !(q.tma_y || q.tma_a) ? 0u : (epi_block ? (uint32_t)T2_EPI_WARPS_BLOCK * ((q.tma_y && q.tma_a) ? 4096u : 2048u) : T2_STAGING_BYTES);
+  const size_t fixed = q.staging_bytes + (fuse ? (size_t)q.ncb2 * (16384 + q.w1_blk_bytes) : 0) + (q.cst_staged ? (size_t)(fuse ? 6 : 3) * p.N * 4 : 0) + 512 + 1024;
   auto magic = [](uint32_t d, uint32_t* m, uint32_t* sh) {   // x / d == umulhi(x, m) >> sh for 0 <= x < 2^31
     uint32_t lg = 0;
     while ((1u << lg) < d) ++lg;
@@ -736,7 +889,7 @@ cudaError_t launch_conv_gemm_tc2(const ConvGemmParams& p, const BatchGeom& g, in
   // Two MMA issuer warps on alternate tiles: a warp then waits on ring slots up to one tile ahead of the other's, and
   // an mbarrier parity wait cannot tell phase n from phase n-2, so both rings must hold more than one tile.
   static const int nmma_env = env_int("Q3TTS_TC_NMMA", 2);
-  q.nmma = (nmma_env == 2 && q.na >= q.ncb + 1 && (q.w_resident || q.nw >= stages_per_tile + 1)) ? 2 : 1;
+  q.nmma = (!fuse && nmma_env == 2 && q.na >= q.ncb + 1 && (q.w_resident || q.nw >= stages_per_tile + 1)) ? 2 : 1;
   if (q.nw < 2 && !q.w_resident) return cudaErrorInvalidConfiguration;
   if (q.na < 2) return cudaErrorInvalidConfiguration;
   size_t smem = (size_t)q.na * q.a_stage_bytes + (size_t)q.nw * q.w_stage_bytes + fixed;
@@ -757,8 +910,8 @@ cudaError_t launch_conv_gemm_tc2(const ConvGemmParams& p, const BatchGeom& g, in
   attr[0].val.clusterDim.x = (unsigned)cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if (op_dtype == DT_F16) return launch_variant<__half>(cfg, pair, epi_block, map_a, map_w, map_y, map_o, q, yf);
-  return launch_variant<__nv_bfloat16>(cfg, pair, epi_block, map_a, map_w, map_y, map_o, q, yf);
+  if (op_dtype == DT_F16) return launch_variant<__half>(cfg, pair, epi_block, map_a, map_w, map_y, map_o, map_w2, q, yf);
+  return launch_variant<__nv_bfloat16>(cfg, pair, epi_block, map_a, map_w, map_y, map_o, map_w2, q, yf);
 }
 
 }  // namespace q3

@@ -33,6 +33,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(done) : "r"(addr), "r"(parity) : "memory");
   } while (!done);
 }
+// Same wait, for roles that expect to wait long: the hardware may suspend the thread up to `hint_ns` per try (it is woken by the
+// barrier's phase flip), so a waiting warp polls a few times per microsecond instead of burning issue slots the working warps need.
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, uint32_t hint_ns = 4000) {
+  uint32_t done;
+  const uint32_t addr = smem_u32(bar);
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(addr), "r"(parity), "r"(hint_ns) : "memory");
+  } while (!done);
+}
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
@@ -224,15 +237,16 @@ __device__ __forceinline__ float4 ldc4(const float* gptr, uint32_t saddr, int of
   return __ldg((const float4*)(gptr + off));
 }
 
-// Block epilogue, one 32-row x 32-column chunk of one warp:
+// Block epilogue, one 32-row x 32-column chunk of one warp (a lane owns one row):
 //   v = acc + bias [+ res16];   y = v (16-bit, kY);   a = v + ib * sin^2(v * ea) (16-bit, kA)
-// Each WARP stages its own 32 rows (64-byte rows, 64B swizzle) and issues its own TMA stores: no cross-warp barrier, no
-// scattered global stores, and no per-element branches.  bias / ea / ib point into smem (staged) or global memory.
+// The four 16-byte pieces of a row go to row_y / row_a + ((chunk_base + c) ^ swz) * 16: a warp-private staging row
+// (64-byte rows, SWIZZLE_64B: swz = (lane >> 1) & 3) that leaves through the warp's own TMA store, a row of a 128B-swizzled
+// operand tile in smem (swz = row & 7, chunk_base = 0 or 4), or the row in global memory itself (swz = 0).
+// bias / ea / ib come from smem (staged constants) or global memory.
 template <typename T16, bool kRes, bool kY, bool kA, bool kSmem>
 __device__ __forceinline__ void epi_block_chunk(const uint32_t (&r)[32], const float* bias, const float* ea, const float* ib,
-                                                uint32_t s_bias, uint32_t s_ea, uint32_t s_ib,
-                                                const uint4 (&rres)[4], uint8_t* buf_y, uint8_t* buf_a, int lane) {
-  const uint32_t sw = (uint32_t)((lane >> 1) & 3);   // SWIZZLE_64B: 16-byte chunk index ^= address bits [7,9)
+                                                uint32_t s_bias, uint32_t s_ea, uint32_t s_ib, const uint4 (&rres)[4],
+                                                uint8_t* row_y, uint8_t* row_a, uint32_t chunk_base, uint32_t swz, bool store_ok) {
 #pragma unroll
   for (int c = 0; c < 4; ++c) {   // 8 columns per step
     float v[8];
@@ -246,9 +260,10 @@ __device__ __forceinline__ void epi_block_chunk(const uint32_t (&r)[32], const f
       const float2 r0 = Cvt<T16>::unpack(u.x), r1 = Cvt<T16>::unpack(u.y), r2 = Cvt<T16>::unpack(u.z), r3 = Cvt<T16>::unpack(u.w);
       v[0] += r0.x; v[1] += r0.y; v[2] += r1.x; v[3] += r1.y; v[4] += r2.x; v[5] += r2.y; v[6] += r3.x; v[7] += r3.y;
     }
-    if (kY)
-      *(uint4*)(buf_y + lane * 64 + ((c ^ sw) << 4)) = make_uint4(Cvt<T16>::pack(v[0], v[1]), Cvt<T16>::pack(v[2], v[3]),
-                                                                  Cvt<T16>::pack(v[4], v[5]), Cvt<T16>::pack(v[6], v[7]));
+    const uint32_t at = ((chunk_base + (uint32_t)c) ^ swz) << 4;
+    if (kY && store_ok)
+      *(uint4*)(row_y + at) = make_uint4(Cvt<T16>::pack(v[0], v[1]), Cvt<T16>::pack(v[2], v[3]),
+                                         Cvt<T16>::pack(v[4], v[5]), Cvt<T16>::pack(v[6], v[7]));
     if (kA) {
       const float4 e0 = ldc4<kSmem>(ea, s_ea, 8 * c), e1 = ldc4<kSmem>(ea, s_ea, 8 * c + 4);
       const float4 i0 = ldc4<kSmem>(ib, s_ib, 8 * c), i1 = ldc4<kSmem>(ib, s_ib, 8 * c + 4);
@@ -258,12 +273,12 @@ __device__ __forceinline__ void epi_block_chunk(const uint32_t (&r)[32], const f
         const float sn = __sinf(v[e] * ee[e]);
         v[e] = fmaf(ii[e], sn * sn, v[e]);
       }
-      *(uint4*)(buf_a + lane * 64 + ((c ^ sw) << 4)) = make_uint4(Cvt<T16>::pack(v[0], v[1]), Cvt<T16>::pack(v[2], v[3]),
-                                                                  Cvt<T16>::pack(v[4], v[5]), Cvt<T16>::pack(v[6], v[7]));
+      if (store_ok)
+        *(uint4*)(row_a + at) = make_uint4(Cvt<T16>::pack(v[0], v[1]), Cvt<T16>::pack(v[2], v[3]),
+                                           Cvt<T16>::pack(v[4], v[5]), Cvt<T16>::pack(v[6], v[7]));
     }
   }
 }
-
 
 }  // namespace tc
 }  // namespace q3

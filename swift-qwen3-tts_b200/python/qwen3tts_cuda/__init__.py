@@ -123,6 +123,8 @@ def lib() -> C.CDLL:
         "q3tts_profile_get": (C.c_int, [vp, C.POINTER(StageTime), i32]),
         "q3tts_profile_kernels": (C.c_int, [vp, C.POINTER(KernelTime), i32]),
         "q3tts_launch_count": (i64, [vp]),
+        "q3tts_debug_fused_unit": (C.c_int, [i32, i32, i32, i32, i32, i32, i32, C.POINTER(C.c_float), C.POINTER(C.c_float),
+                                             C.POINTER(C.c_float)]),
         "q3tts_debug_resunit": (C.c_int, [i32, i32, i32, i32, i32, i32, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
         "q3tts_debug_conv_gemm": (C.c_int, [i32, i32, i32, i32, i32, i32, i32, i32, i32, C.POINTER(C.c_float),
                                             C.POINTER(C.c_float), C.POINTER(C.c_float)]),
@@ -169,6 +171,14 @@ def debug_conv_gemm(B: int, rows: int, Cin: int, N: int, taps: int, dil: int, mo
     """Kernel-level check: (ms per launch, max|tc - simt| stream, max|tc - simt| operand) of one multi-tap GEMM."""
     ms, dy, da = C.c_float(0), C.c_float(0), C.c_float(0)
     _check(lib().q3tts_debug_conv_gemm(B, rows, Cin, N, taps, dil, mode, precision, iters, C.byref(ms), C.byref(dy), C.byref(da)))
+    return float(ms.value), float(dy.value), float(da.value)
+
+
+def debug_fused_unit(B: int, rows: int, Cch: int, dil: int, with_operand: int = 1, precision: int = PREC_FP16,
+                     iters: int = 0) -> Tuple[float, float, float]:
+    """Kernel-level check of the GEMM-fused residual unit: (ms, max|diff| stream, max|diff| operand)."""
+    ms, dy, da = C.c_float(0), C.c_float(0), C.c_float(0)
+    _check(lib().q3tts_debug_fused_unit(B, rows, Cch, dil, with_operand, precision, iters, C.byref(ms), C.byref(dy), C.byref(da)))
     return float(ms.value), float(dy.value), float(da.value)
 
 
