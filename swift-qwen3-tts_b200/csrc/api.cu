@@ -535,11 +535,11 @@ int q3tts_write_wav(const char* path, const float* pcm, int64_t n, int32_t rate)
 // One multi-tap GEMM on seeded random data: the tcgen05 path against the CUDA-core 16-bit path of the same op, then
 // `iters` timed launches (CUDA events).  mode 0: conv7-like (bias, SnakeBeta operand out); 1: conv1-like (bias,
 // in-place 16-bit residual stream, SnakeBeta operand out); 2: transposed-conv-like (bias, stream out, SnakeBeta operand
-// out); 3: plain (bias, operand out).  Utterance b has rows - 37*b valid rows (ragged tiles).
+// out); 3: plain (bias, operand out); 4: stream out only.  Utterance b has rows - 37*b valid rows (ragged tiles).
 int q3tts_debug_conv_gemm(int32_t B, int32_t rows, int32_t Cin, int32_t N, int32_t taps, int32_t dil, int32_t mode,
                           int32_t precision, int32_t iters, float* ms_out, float* max_diff_y, float* max_diff_a) {
   return guarded([&]() {
-    if (B < 1 || rows < 1 || Cin < 16 || N < 16 || taps < 1 || dil < 1 || mode < 0 || mode > 3) return fail(Q3TTS_EINVAL, "bad GEMM shape");
+    if (B < 1 || rows < 1 || Cin < 16 || N < 16 || taps < 1 || dil < 1 || mode < 0 || mode > 4) return fail(Q3TTS_EINVAL, "bad GEMM shape");
     const int op = precision == Q3TTS_PREC_BF16 ? DT_BF16 : DT_F16;
     cudaStream_t s = nullptr;
     CUDA_OK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
@@ -586,9 +586,10 @@ int q3tts_debug_conv_gemm(int32_t B, int32_t rows, int32_t Cin, int32_t N, int32
       p.A = A; p.lda = Cin; p.a_bstride = (int64_t)rows * Cin;
       p.W = W; p.rows_per_frame = 1; p.N = N; p.Cin = Cin; p.taps = taps; p.dil = dil;
       p.bias = bias; p.act = ACT_NONE;
-      p.out_a = a[which]; p.lda_out = N; p.ao_bstride = (int64_t)rows * N;
-      if (mode != 3) { p.snake_ea = ea; p.snake_ib = ib; }
-      if (mode == 1 || mode == 2) { p.out_y = y[which]; p.ldy = N; p.y_bstride = (int64_t)rows * N; }
+      p.lda_out = N; p.ao_bstride = (int64_t)rows * N;
+      if (mode != 4) p.out_a = a[which];
+      if (mode != 3 && mode != 4) { p.snake_ea = ea; p.snake_ib = ib; }
+      if (mode == 1 || mode == 2 || mode == 4) { p.out_y = y[which]; p.ldy = N; p.y_bstride = (int64_t)rows * N; }
       if (mode == 1) { p.res = y[which]; p.ldres = N; p.res_bstride = (int64_t)rows * N; }
       return p;
     };
@@ -621,8 +622,8 @@ int q3tts_debug_conv_gemm(int32_t B, int32_t rows, int32_t Cin, int32_t N, int32
           }
       return worst;
     };
-    if (max_diff_a) *max_diff_a = max_diff(a[0], a[1]);
-    if (max_diff_y) *max_diff_y = (mode == 1 || mode == 2) ? max_diff(y[0], y[1]) : 0.f;
+    if (max_diff_a) *max_diff_a = mode != 4 ? max_diff(a[0], a[1]) : 0.f;
+    if (max_diff_y) *max_diff_y = (mode == 1 || mode == 2 || mode == 4) ? max_diff(y[0], y[1]) : 0.f;
     if (iters > 0 && ms_out) {
       cudaEvent_t e0, e1;
       CUDA_OK(cudaEventCreate(&e0));
