@@ -207,6 +207,7 @@ Model* model_create(const Checkpoint& ck, const q3tts_options& opts) {
     const std::string p = pt + "layers." + std::to_string(n) + ".";
     LayerW& L = m.layers[(size_t)n];
     pack_linear(m, L.qkv, {&T(ck, p + "self_attn.q_proj.weight"), &T(ck, p + "self_attn.k_proj.weight"), &T(ck, p + "self_attn.v_proj.weight")}, nullptr);
+    L.qkv.bias = upload(m, std::vector<float>((size_t)L.qkv.N, 0.f));   // bias-free in the reference (ST.swift:492-494); a zero bias selects the fast epilogue
     pack_linear(m, L.o, {&T(ck, p + "self_attn.o_proj.weight")}, nullptr);
     pack_linear(m, L.gate_up, {&T(ck, p + "mlp.gate_proj.weight"), &T(ck, p + "mlp.up_proj.weight")}, nullptr, true);
     pack_linear(m, L.down, {&T(ck, p + "mlp.down_proj.weight")}, nullptr);
@@ -222,7 +223,13 @@ Model* model_create(const Checkpoint& ck, const q3tts_options& opts) {
     U.ratio = c.upsampling_ratios[i];
     pack_tconv(m, U.tconv, T(ck, u + "0.conv.weight"), T(ck, u + "0.conv.bias"), U.ratio);
     const HostTensor& dw = T(ck, u + "1.dwconv.conv.weight");   // [L,7,1]
-    U.dw_w = upload(m, dw.data);
+    {  // [C][7] -> [7][C]: the row kernel reads four channels of one tap with one 16-byte load
+      const int64_t Cc = dw.shape[0], K = dw.shape[1];
+      std::vector<float> tw((size_t)(Cc * K));
+      for (int64_t cc = 0; cc < Cc; ++cc)
+        for (int64_t k = 0; k < K; ++k) tw[(size_t)(k * Cc + cc)] = dw.data[(size_t)(cc * K + k)];
+      U.dw_w = upload(m, tw);
+    }
     U.dw_b = upload(m, T(ck, u + "1.dwconv.conv.bias").data);
     U.ln_w = upload(m, T(ck, u + "1.norm.weight").data);
     U.ln_b = upload(m, T(ck, u + "1.norm.bias").data);

@@ -66,7 +66,7 @@ void launch_rmsnorm(const float* x, const float* w, float eps, void* out, int ou
                     cudaStream_t s);
 
 // depthwise causal conv k=7 (+bias) followed by LayerNorm(eps) over C (ST.swift:389-393); x fp32 stream.
-void launch_dwconv_ln(const float* x, const float* w7 /*[C][7]*/, const float* wb, const float* ln_w,
+void launch_dwconv_ln(const float* x, const float* w7 /*[7][C]*/, const float* wb, const float* ln_w,
                       const float* ln_b, float eps, void* out, int out_dtype, const BatchGeom& g,
                       int rows_per_frame, int C, cudaStream_t s);
 

@@ -245,6 +245,69 @@ void launch_rmsnorm(const float* x, const float* w, float eps, void* out, int ou
 // Depthwise causal conv k=7 + bias, then LayerNorm over C (ST.swift:389-393, 372-379).
 // One CTA per output row; each thread owns channels tid, tid+256, ...
 // ================================================================================================
+// One WARP per output row (no block barriers): a lane owns channels 4*lane + 128*k .. +3 (k < C/128), so every access is a
+// 16-byte load / store that the warp coalesces into 512 contiguous bytes; the 8 warps of a CTA take 8 consecutive rows, whose
+// 7-row windows overlap in L1.  w7 is [7][C] (tap-major).  C % 128 == 0, C <= 2048; other widths use the generic kernel below.
+__device__ __forceinline__ void st4(float* p, float4 v) { *(float4*)p = v; }
+__device__ __forceinline__ void st4(__half* p, float4 v) {
+  __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+  *(uint2*)p = make_uint2(*(uint32_t*)&a, *(uint32_t*)&b);
+}
+__device__ __forceinline__ void st4(__nv_bfloat16* p, float4 v) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+  *(uint2*)p = make_uint2(*(uint32_t*)&a, *(uint32_t*)&b);
+}
+template <typename TO, int KC>
+__global__ void __launch_bounds__(256)
+dwconv_ln_warp_kernel(const float* __restrict__ x, const float* __restrict__ w7, const float* __restrict__ wb,
+                      const float* __restrict__ ln_w, const float* __restrict__ ln_b, float eps, TO* __restrict__ out, BatchGeom g,
+                      int rows_per_frame) {
+  constexpr int C = KC * 128;
+  const int slot_rows = g.Tmax * rows_per_frame;
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= (int64_t)g.B * slot_rows) return;
+  const int b = (int)(row / slot_rows), t = (int)(row % slot_rows), lane = threadIdx.x & 31;
+  if (t >= g.len_frames[b] * rows_per_frame) return;
+  const float* xb = x + (int64_t)b * slot_rows * C;
+  float4 acc[KC];
+#pragma unroll
+  for (int k = 0; k < KC; ++k) acc[k] = __ldg((const float4*)(wb + 4 * lane + 128 * k));
+#pragma unroll
+  for (int j = 0; j < 7; ++j) {
+    const int tin = t - 6 + j;
+    if (tin < 0) continue;
+#pragma unroll
+    for (int k = 0; k < KC; ++k) {
+      const float4 xv = __ldg((const float4*)(xb + (int64_t)tin * C + 4 * lane + 128 * k));
+      const float4 wv = __ldg((const float4*)(w7 + j * C + 4 * lane + 128 * k));
+      acc[k].x = fmaf(wv.x, xv.x, acc[k].x); acc[k].y = fmaf(wv.y, xv.y, acc[k].y);
+      acc[k].z = fmaf(wv.z, xv.z, acc[k].z); acc[k].w = fmaf(wv.w, xv.w, acc[k].w);
+    }
+  }
+  float sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < KC; ++k) sum += (acc[k].x + acc[k].y) + (acc[k].z + acc[k].w);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / (float)C;
+  float sq = 0.f;
+#pragma unroll
+  for (int k = 0; k < KC; ++k) {
+    const float dx = acc[k].x - mean, dy = acc[k].y - mean, dz = acc[k].z - mean, dw = acc[k].w - mean;
+    sq += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  const float r = rsqrtf(sq / (float)C + eps);
+  TO* orow = out + ((int64_t)b * slot_rows + t) * C;
+#pragma unroll
+  for (int k = 0; k < KC; ++k) {
+    const float4 lw = __ldg((const float4*)(ln_w + 4 * lane + 128 * k)), lb = __ldg((const float4*)(ln_b + 4 * lane + 128 * k));
+    st4(orow + 4 * lane + 128 * k, make_float4((acc[k].x - mean) * r * lw.x + lb.x, (acc[k].y - mean) * r * lw.y + lb.y,
+                                               (acc[k].z - mean) * r * lw.z + lb.z, (acc[k].w - mean) * r * lw.w + lb.w));
+  }
+}
+
 template <typename TO>
 __global__ void __launch_bounds__(256)
 dwconv_ln_kernel(const float* x, const float* w7, const float* wb, const float* ln_w, const float* ln_b, float eps,
@@ -261,13 +324,12 @@ dwconv_ln_kernel(const float* x, const float* w7, const float* wb, const float* 
 #pragma unroll
     for (int j = 0; j < 7; ++j) {
       const int tin = t - 6 + j;
-      if (tin >= 0) a = fmaf(w7[c * 7 + j], xb[(int64_t)tin * C + c], a);
+      if (tin >= 0) a = fmaf(w7[j * C + c], xb[(int64_t)tin * C + c], a);
     }
     vals[cnt] = a;
     sum += a;
   }
   __shared__ float red[8];
-  __shared__ float stat[2];
   auto block_sum = [&](float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -284,7 +346,6 @@ dwconv_ln_kernel(const float* x, const float* w7, const float* wb, const float* 
   for (int i = 0; i < cnt; ++i) { float d = vals[i] - mean; sq = fmaf(d, d, sq); }
   const float var = block_sum(sq) / (float)C;
   const float r = rsqrtf(var + eps);
-  (void)stat;
   TO* orow = out + ((int64_t)b * slot_rows + t) * C;
   cnt = 0;
   for (int c = threadIdx.x; c < C; c += 256, ++cnt) stf(orow, c, (vals[cnt] - mean) * r * ln_w[c] + ln_b[c]);
@@ -292,8 +353,18 @@ dwconv_ln_kernel(const float* x, const float* w7, const float* wb, const float* 
 
 void launch_dwconv_ln(const float* x, const float* w7, const float* wb, const float* ln_w, const float* ln_b, float eps,
                       void* out, int out_dtype, const BatchGeom& g, int rows_per_frame, int C, cudaStream_t s) {
-  const unsigned blocks = (unsigned)((int64_t)g.B * g.Tmax * rows_per_frame);
-  Q3_DISPATCH_DT(out_dtype, T, (dwconv_ln_kernel<T><<<blocks, 256, 0, s>>>(x, w7, wb, ln_w, ln_b, eps, (T*)out, g, rows_per_frame, C)));
+  const int64_t rows = (int64_t)g.B * g.Tmax * rows_per_frame;
+  if (C == 1024) {
+    const unsigned blocks = (unsigned)((rows + 7) / 8);
+    Q3_DISPATCH_DT(out_dtype, T, (dwconv_ln_warp_kernel<T, 8><<<blocks, 256, 0, s>>>(x, w7, wb, ln_w, ln_b, eps, (T*)out, g, rows_per_frame)));
+    return;
+  }
+  if (C == 512) {
+    const unsigned blocks = (unsigned)((rows + 7) / 8);
+    Q3_DISPATCH_DT(out_dtype, T, (dwconv_ln_warp_kernel<T, 4><<<blocks, 256, 0, s>>>(x, w7, wb, ln_w, ln_b, eps, (T*)out, g, rows_per_frame)));
+    return;
+  }
+  Q3_DISPATCH_DT(out_dtype, T, (dwconv_ln_kernel<T><<<(unsigned)rows, 256, 0, s>>>(x, w7, wb, ln_w, ln_b, eps, (T*)out, g, rows_per_frame, C)));
 }
 
 // ================================================================================================

@@ -493,8 +493,10 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
           const uint32_t sb = cst_u32 + 4u * (uint32_t)n, se = sb + 4u * (uint32_t)p.N, si = se + 4u * (uint32_t)p.N;
 #define Q3_EPI(RES, Y, SM) epi_block_chunk<T16, RES, Y, true, SM>(r, p.bias + n, p.snake_ea + n, p.snake_ib + n, sb, se, si, rres, buf_y + lane * 64, buf_a + lane * 64, 0u, sw64, true)
 #define Q3_EPI_Y(SM) epi_block_chunk<T16, false, true, false, SM>(r, p.bias + n, nullptr, nullptr, sb, se, si, rres, buf_y + lane * 64, buf_a + lane * 64, 0u, sw64, true)
-          if (!has_a) {   // stream output only (the consumer applies its own activation)
-            if (p.cst_staged) Q3_EPI_Y(true); else Q3_EPI_Y(false);
+#define Q3_EPI_YG(SM) epi_block_chunk<T16, false, true, false, SM, true>(r, p.bias + n, nullptr, nullptr, sb, se, si, rres, buf_y + lane * 64, buf_a + lane * 64, 0u, sw64, true)
+          if (!has_a) {   // one output: the stream (the consumer applies its own activation), or a plain / GELU operand
+            if (p.act == ACT_GELU) { if (p.cst_staged) Q3_EPI_YG(true); else Q3_EPI_YG(false); }
+            else if (p.cst_staged) Q3_EPI_Y(true); else Q3_EPI_Y(false);
           } else if (p.cst_staged) {
             if (has_res) { if (has_y) Q3_EPI(true, true, true); else Q3_EPI(true, false, true); }
             else { if (has_y) Q3_EPI(false, true, true); else Q3_EPI(false, false, true); }
@@ -504,6 +506,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
           }
 #undef Q3_EPI
 #undef Q3_EPI_Y
+#undef Q3_EPI_YG
           fence_async_smem();
           __syncwarp();
           if (lane == 0) {
@@ -702,8 +705,9 @@ int pick_bn2(int N, bool prefer32 = false) {
 }
 // The block epilogue: bias + [16-bit residual] + [16-bit stream out] + SnakeBeta operand out, nothing else.
 bool block_epilogue_ok(const ConvGemmParams& p, int y_dtype) {
-  const bool with_a = p.out_a && p.snake_ea, y_only = !p.out_a && !p.snake_ea && p.out_y && !p.res;
-  return (with_a || y_only) && p.bias && p.act == ACT_NONE && !p.out_tap && !p.scale &&
+  const bool with_a = p.out_a && p.snake_ea && p.act == ACT_NONE, y_only = !p.out_a && !p.snake_ea && p.out_y && !p.res && p.act == ACT_NONE;
+  const bool plain_a = p.out_a && !p.snake_ea && !p.out_y && !p.res && (p.act == ACT_NONE || p.act == ACT_GELU);   // one 16-bit operand out
+  return (with_a || y_only || plain_a) && p.bias && !p.out_tap && !p.scale &&
          (!p.res || (p.out_y && p.res == p.out_y)) && (!p.out_y || y_dtype != DT_F32) && pick_bn2(p.N, true) % 32 == 0 &&
          pick_bn2(p.N, true) >= 64;
 }
@@ -820,13 +824,15 @@ cudaError_t launch_conv_gemm_tc2(const ConvGemmParams& p, const BatchGeom& g, in
   q.res = p.res; q.ldres = p.ldres; q.res_bstride = p.res_bstride; q.scale = p.scale;
   q.out_y = p.out_y; q.ldy = p.ldy; q.y_bstride = p.y_bstride;
   q.out_a = p.out_a; q.lda_out = p.lda_out; q.ao_bstride = p.ao_bstride;
+  const bool plain_a = epi_block && !fuse && p.out_a && !p.snake_ea;   // block epilogue, single plain / GELU operand: it leaves as "y"
+  if (plain_a) { q.out_y = p.out_a; q.ldy = p.lda_out; q.y_bstride = p.ao_bstride; q.out_a = nullptr; }
   q.snake_ea = p.snake_ea; q.snake_ib = p.snake_ib;
   q.out_tap = (float*)p.out_tap; q.ldt = p.ldt; q.tap_bstride = p.tap_bstride;
   // 16-bit outputs leave through smem staging + TMA stores
   static const int tma_store_env = env_int("Q3TTS_TC_TMA_STORE", 1);
   const int yf = y_dtype == DT_F32;
-  q.tma_y = !fuse && (epi_block || tma_store_env) && p.out_y && !yf && p.act != ACT_SWIGLU;
-  q.tma_a = !fuse && (epi_block || tma_store_env) && p.out_a && p.act != ACT_SWIGLU;
+  q.tma_y = !fuse && (epi_block || tma_store_env) && q.out_y && (!yf || plain_a) && p.act != ACT_SWIGLU;
+  q.tma_a = !fuse && (epi_block || tma_store_env) && q.out_a && p.act != ACT_SWIGLU;
   q.cst_staged = epi_block && (cst_env || fuse) && p.N <= T2_CST_MAX_N;
   CUtensorMap map_w2 = map_w;
   if (fuse) {
@@ -852,8 +858,8 @@ cudaError_t launch_conv_gemm_tc2(const ConvGemmParams& p, const BatchGeom& g, in
                epi_block ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
                CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
   };
-  if (q.tma_y && !out_map(&map_y, p.out_y, p.ldy, p.y_bstride)) return cudaErrorInvalidValue;
-  if (q.tma_a && !out_map(&map_o, p.out_a, p.lda_out, p.ao_bstride)) return cudaErrorInvalidValue;
+  if (q.tma_y && !out_map(&map_y, q.out_y, q.ldy, q.y_bstride)) return cudaErrorInvalidValue;
+  if (q.tma_a && !out_map(&map_o, q.out_a, q.lda_out, q.ao_bstride)) return cudaErrorInvalidValue;
   q.staging_bytes = !(q.tma_y || q.tma_a) ? 0u : (epi_block ? (uint32_t)T2_EPI_WARPS_BLOCK * ((q.tma_y && q.tma_a) ? 4096u : 2048u) : T2_STAGING_BYTES);
   const size_t fixed = q.staging_bytes + (fuse ? (size_t)q.ncb2 * (16384 + q.w1_blk_bytes) : 0) + (q.cst_staged ? (size_t)(fuse ? 6 : 3) * p.N * 4 : 0) + 512 + 1024;
   auto magic = [](uint32_t d, uint32_t* m, uint32_t* sh) {   // x / d == umulhi(x, m) >> sh for 0 <= x < 2^31

@@ -238,12 +238,12 @@ __device__ __forceinline__ float4 ldc4(const float* gptr, uint32_t saddr, int of
 }
 
 // Block epilogue, one 32-row x 32-column chunk of one warp (a lane owns one row):
-//   v = acc + bias [+ res16];   y = v (16-bit, kY);   a = v + ib * sin^2(v * ea) (16-bit, kA)
+//   v = acc + bias [+ res16] [-> exact GELU];   y = v (16-bit, kY);   a = v + ib * sin^2(v * ea) (16-bit, kA)
 // The four 16-byte pieces of a row go to row_y / row_a + ((chunk_base + c) ^ swz) * 16: a warp-private staging row
 // (64-byte rows, SWIZZLE_64B: swz = (lane >> 1) & 3) that leaves through the warp's own TMA store, a row of a 128B-swizzled
 // operand tile in smem (swz = row & 7, chunk_base = 0 or 4), or the row in global memory itself (swz = 0).
 // bias / ea / ib come from smem (staged constants) or global memory.
-template <typename T16, bool kRes, bool kY, bool kA, bool kSmem>
+template <typename T16, bool kRes, bool kY, bool kA, bool kSmem, bool kGelu = false>
 __device__ __forceinline__ void epi_block_chunk(const uint32_t (&r)[32], const float* bias, const float* ea, const float* ib,
                                                 uint32_t s_bias, uint32_t s_ea, uint32_t s_ib, const uint4 (&rres)[4],
                                                 uint8_t* row_y, uint8_t* row_a, uint32_t chunk_base, uint32_t swz, bool store_ok) {
@@ -259,6 +259,10 @@ __device__ __forceinline__ void epi_block_chunk(const uint32_t (&r)[32], const f
       const uint4 u = rres[c];
       const float2 r0 = Cvt<T16>::unpack(u.x), r1 = Cvt<T16>::unpack(u.y), r2 = Cvt<T16>::unpack(u.z), r3 = Cvt<T16>::unpack(u.w);
       v[0] += r0.x; v[1] += r0.y; v[2] += r1.x; v[3] += r1.y; v[4] += r2.x; v[5] += r2.y; v[6] += r3.x; v[7] += r3.y;
+    }
+    if (kGelu) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = gelu_exact(v[e]);
     }
     const uint32_t at = ((chunk_base + (uint32_t)c) ^ swz) << 4;
     if (kY && store_ok)
