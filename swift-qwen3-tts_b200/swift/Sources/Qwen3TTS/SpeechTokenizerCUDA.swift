@@ -87,7 +87,7 @@ public final class Qwen3TTSSpeechTokenizerDecoder {
 public final class Qwen3TTSSpeechTokenizer {
     public let decoder: Qwen3TTSSpeechTokenizerDecoder
     let decodeUpsampleRate: Int
-    private let handle: OpaquePointer
+    let handle: OpaquePointer
 
     /// Replaces the speech-tokenizer half of `postLoadHook(modelDir:)` (Qwen3.swift:1461-1494):
     /// `speechTokenizerDir` = `<modelDir>/speech_tokenizer` (config.json + *.safetensors).
@@ -154,5 +154,44 @@ public final class Qwen3TTSSpeechTokenizer {
         }
         let audio = (0..<utterances.count).map { i in Array(pcm[(Int(offsets[i]) * up)..<(Int(offsets[i + 1]) * up)]) }
         return (audio, lengths)
+    }
+}
+
+/// Chunked streaming decode: feed codec frames as the Talker emits them (Qwen3.swift:640-729 produces one
+/// 16-code vector per step), get the matching 1920·n samples back.  The model must have been loaded with the
+/// causal sliding-window attention mode (`q3tts_options.attn_mode = Q3TTS_ATTN_CAUSAL_SW`); per-stream state is the
+/// transformer KV window plus ten frames of convolution context.  No counterpart in the reference, whose
+/// `generateStream` decodes once at the end (Qwen3+Streaming.swift:19-120).
+public final class Qwen3TTSDecodeStream {
+    private var stream: OpaquePointer
+    private let samplesPerFrame: Int
+    private let numQuantizers: Int
+
+    public init(_ tokenizer: Qwen3TTSSpeechTokenizer) throws {
+        var s: OpaquePointer?
+        try check(q3tts_stream_open(tokenizer.handle, &s))
+        guard let opened = s else { throw Qwen3TTSCUDAError.audioDecodingFailed("q3tts_stream_open returned NULL") }
+        stream = opened
+        samplesPerFrame = tokenizer.decodeUpsampleRate
+        numQuantizers = tokenizer.decoder.numQuantizers
+    }
+
+    deinit { q3tts_stream_close(stream) }
+
+    /// Frames decoded so far on this stream.
+    public var framesDone: Int { Int(q3tts_stream_frames(stream)) }
+
+    /// - Parameter codes: [n_frames, num_quantizers]
+    /// - Returns: n_frames · 1920 samples continuing the stream's waveform
+    public func push(_ codes: Int32Tensor) throws -> [Float] {
+        precondition(codes.shape.count == 2 && codes.shape[1] == numQuantizers)
+        let n = codes.shape[0]
+        var pcm = [Float](repeating: 0, count: n * samplesPerFrame)
+        try codes.data.withUnsafeBufferPointer { c in
+            try pcm.withUnsafeMutableBufferPointer { p in
+                try check(q3tts_stream_push(stream, c.baseAddress, Int32(n), p.baseAddress))
+            }
+        }
+        return pcm
     }
 }
