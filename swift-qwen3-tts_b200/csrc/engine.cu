@@ -561,6 +561,8 @@ static void run_back(Ctx& x, Plan& P, const void* to, const int64_t* d_pcm_base,
       void* abuf[2] = {P.blk[i].A, P.blk[i].C};
       for (int j = 0; j < 3; ++j) {
         const SnakeW* next = (j < 2) ? &Bk.act_in_next[j + 1] : block_out;
+        // the block's last unit feeds only the next consumer's operand: its stream output is never read again
+        void* x_out = (j == 2 && !taps && op != DT_F32) ? nullptr : P.blk[i].X;
         if (fuse1) {
           const GemmW& w7 = Bk.conv7[j];
           const GemmW& w1 = Bk.conv1[j];
@@ -569,9 +571,9 @@ static void run_back(Ctx& x, Plan& P, const void* to, const int64_t* d_pcm_base,
           p.A = abuf[j & 1]; p.lda = w7.Cin; p.a_bstride = slot * w7.Cin; p.W = w7.w16; p.rows_per_frame = rate;
           p.N = w7.N; p.Cin = w7.Cin; p.taps = w7.taps; p.dil = w7.dil; p.bias = w7.bias; p.act = ACT_NONE;
           p.snake_ea = Bk.act2[j].ea; p.snake_ib = Bk.act2[j].ib;
-          FusedConv1 f{w1.w16, w1.bias, P.blk[i].X, P.blk[i].X, abuf[(j + 1) & 1], next->ea, next->ib};
+          FusedConv1 f{w1.w16, w1.bias, P.blk[i].X, x_out, abuf[(j + 1) & 1], next->ea, next->ib};
           const double rows = (double)valid_frames * rate, C = (double)w7.N;
-          const double fl = 2.0 * rows * 8.0 * C * C, by = rows * C * 2.0 * 4.0 + 8.0 * C * C * 2.0;   // A in, X in, X' out, A' out
+          const double fl = 2.0 * rows * 8.0 * C * C, by = rows * C * 2.0 * (x_out ? 4.0 : 3.0) + 8.0 * C * C * 2.0;   // A in, X in, [X' out,] A' out
           launch_begin(x, "conv7+conv1", fl, by);
           cudaError_t err = launch_conv_gemm_tc2(p, x.g, op, op, s, &f);
           if (err != cudaSuccess) throw Error(Q3TTS_ECUDA, std::string("fused residual GEMM launch: ") + cudaGetErrorString(err));
@@ -580,7 +582,7 @@ static void run_back(Ctx& x, Plan& P, const void* to, const int64_t* d_pcm_base,
           account(x, fl, by);
         } else {
           { Epi e; e.out_a = P.blk[i].C; e.snake = &Bk.act2[j]; gemm(x, Bk.conv7[j], P.blk[i].A, rate, e, "conv7"); }
-          { Epi e; e.res = P.blk[i].X; e.out_y = P.blk[i].X; e.y_dtype = m.st_dtype; e.out_a = P.blk[i].A; e.snake = next; gemm(x, Bk.conv1[j], P.blk[i].C, rate, e, "conv1"); }
+          { Epi e; e.res = P.blk[i].X; e.out_y = x_out; e.y_dtype = m.st_dtype; e.out_a = P.blk[i].A; e.snake = next; gemm(x, Bk.conv1[j], P.blk[i].C, rate, e, "conv1"); }
         }
       }
       a_in = fuse1 ? abuf[1] : P.blk[i].A;        // three units: A -> C -> A -> C

@@ -66,8 +66,12 @@ struct Tc2Params {
   float* out_tap; int ldt; long long tap_bstride;
   // fused residual unit (block epilogue kernel only): this GEMM is conv7 (+ bias + snake -> a 128B-swizzled operand tile in
   // smem), followed by the unit's 1x1 conv from that tile (W1 resident in smem) with the usual residual epilogue
-  int fuse, ncb2;
-  uint32_t w1_blk_bytes;                         // one 64-channel block of this CTA's half of W1: (BN/2) rows x 128 B
+  // The 1x1 conv runs as two N halves through ONE extra accumulator of BN/2 columns (TMEM: 2 x BN + BN/2 <= 512), issued
+  // in the middle of the NEXT tile's conv7, so that neither epilogue ever holds up the tensor pipe.
+  int a_tmem;                                    // conv1's operand lives in TENSOR MEMORY, packed over the drained conv7 accumulator
+  int fuse, ncb2, acc2_col, c1_after0, c1_after1, dbg;   // c1_after*: 64-channel block of the next conv7 after which half 0 / 1 of conv1 is issued
+  uint32_t idesc2;                               // N = BN/2
+  uint32_t w1_blk_bytes;                         // one (N half, 64-channel block) of this CTA's part of W1: (BN/4) rows x 128 B
   const float* bias2; const float* ea2; const float* ib2;
   const void* res2; void* out_y2; void* out_a2; long long o2_bstride;
 };
@@ -109,8 +113,8 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   uint8_t* w_ring = smem + (size_t)T2_NA * p.a_stage_bytes;
   uint8_t* staging = w_ring + (size_t)T2_NW * p.w_stage_bytes;          // 1024-aligned (all stage sizes are)
   uint8_t* c_tile = staging + p.staging_bytes;                          // fused unit: conv1's operand, [ncb2][128 rows][128 B]
-  uint8_t* w1s = c_tile + (p.fuse ? (size_t)p.ncb2 * 16384 : 0);        // fused unit: [ncb2][BN/2 rows][128 B]
-  float* cst = (float*)(w1s + (p.fuse ? (size_t)p.ncb2 * p.w1_blk_bytes : 0));   // [bias | ea | ib] x N when staged (x2 when fused)
+  uint8_t* w1s = c_tile + ((p.fuse && !p.a_tmem) ? (size_t)p.ncb2 * 16384 : 0);        // fused unit: [N half][ncb2][BN/4 rows][128 B]
+  float* cst = (float*)(w1s + (p.fuse ? (size_t)2 * p.ncb2 * p.w1_blk_bytes : 0));   // [bias | ea | ib] x N when staged (x2 when fused)
   uint64_t* bars = (uint64_t*)((uint8_t*)cst + (p.cst_staged ? (size_t)(p.fuse ? 6 : 3) * p.N * 4 : 0));
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + T2_MAX_NA;
@@ -118,10 +122,12 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   uint64_t* w_empty = w_full + T2_MAX_NW;
   uint64_t* tmem_full = w_empty + T2_MAX_NW;
   uint64_t* tmem_empty = tmem_full + T2_MAX_ACC;
-  uint64_t* tmem_full2 = tmem_empty + T2_MAX_ACC;   // [2] fused unit: conv1 has completed (operand tile free, accumulator = conv1)
+  uint64_t* tmem_full2 = tmem_empty + T2_MAX_ACC;   // [2] fused unit: N half h of conv1 has completed
   uint64_t* c_ready = tmem_full2 + 2;               // fused unit: the operand tile of conv1 is written (both CTAs)
   uint64_t* w1_full = c_ready + 1;
-  uint32_t* tmem_ptr = (uint32_t*)(w1_full + 1);
+  uint64_t* acc2_empty = w1_full + 1;               // fused unit: the conv1 accumulator has been drained
+  uint64_t* xbar = acc2_empty + 1;                  // [12] fused unit: a warp's residual chunk has landed in its staging buffer
+  uint32_t* tmem_ptr = (uint32_t*)(xbar + T2_EPI_WARPS_BLOCK);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cs = p.cs;
@@ -145,6 +151,8 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     for (int i = 0; i < 2; ++i) mbar_init(&tmem_full2[i], 1);
     mbar_init(c_ready, (uint32_t)((kPair ? 2 : 1) * kEpiWarps));
     mbar_init(w1_full, 1);
+    mbar_init(acc2_empty, (uint32_t)((kPair ? 2 : 1) * kEpiWarps));
+    for (int i = 0; i < T2_EPI_WARPS_BLOCK; ++i) mbar_init(&xbar[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -212,9 +220,11 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     const int res_es = y_is_f32 ? 4 : 2;
     const int stages_per_tile = p.ncb * p.ngroups;
     if (kBlockEpi && kPair && p.fuse && elect_one()) {   // the 1x1 conv's weights: resident for the whole kernel
-      if (rank == 0) mbar_expect_tx(w1_full, 2u * (uint32_t)p.ncb2 * p.w1_blk_bytes);
-      for (int cb = 0; cb < p.ncb2; ++cb)
-        tma_load_2d_2sm(w1s + (size_t)cb * p.w1_blk_bytes, &map_w2, w1_full, cb * T2_BK, (int)rank * (p.BN / 2));
+      if (rank == 0) mbar_expect_tx(w1_full, 4u * (uint32_t)p.ncb2 * p.w1_blk_bytes);
+      for (int h = 0; h < 2; ++h)
+        for (int cb = 0; cb < p.ncb2; ++cb)
+          tma_load_2d_2sm(w1s + (size_t)(h * p.ncb2 + cb) * p.w1_blk_bytes, &map_w2, w1_full, cb * T2_BK,
+                          h * (p.BN / 2) + (int)rank * (p.BN / 4));
     }
     __syncwarp();
     for (int item = cid; item < items; item += ncl) {
@@ -294,24 +304,31 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
       uint32_t w_seen = 0;                       // resident weights: bit s = stage s has been waited for once (it never changes again)
       const int which = warp == 1 ? 0 : 1;
       int turn = 0;
-      // fused unit: conv1 of tile k is issued after conv7 of tile k+1 (the tensor pipe stays busy while epilogue 1 of tile k
-      // writes the operand tile); it accumulates into the tile's own accumulator slot, which epilogue 1 has drained.
-      int n_done = 0, prev_acc = 0;
-      auto issue_conv1 = [&]() {
-        mbar_wait(c_ready, (uint32_t)((n_done - 1) & 1));
-        if (n_done == 1) mbar_wait(w1_full, 0u);
+      // fused unit: the two N halves of conv1 of tile k-1 are issued after the first and second 64-channel block of conv7 of
+      // tile k: by then epilogue 1 of tile k-1 has written the operand tile, and each half's drain overlaps conv7 MMAs.
+      int n_done = 0;
+      auto issue_conv1 = [&](int h) {
+        if (h == 0) {
+          mbar_wait(c_ready, (uint32_t)((n_done - 1) & 1));
+          if (n_done == 1) mbar_wait(w1_full, 0u);
+        }
+        mbar_wait(acc2_empty, (uint32_t)(h ^ 1));      // fill f = 2 (n_done-1) + h needs the drain of fill f-1
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t d2 = tmem_base + (uint32_t)(prev_acc * p.acc_stride);
-          const uint64_t ad = desc_fixed | (uint64_t)(smem_u32(c_tile) >> 4), wd = desc_fixed | (uint64_t)(smem_u32(w1s) >> 4);
+          const uint32_t d2 = tmem_base + (uint32_t)p.acc2_col;
+          const uint64_t ad = desc_fixed | (uint64_t)(smem_u32(c_tile) >> 4);
+          const uint64_t wd = desc_fixed | (uint64_t)((smem_u32(w1s) + (uint32_t)(h * p.ncb2) * p.w1_blk_bytes) >> 4);
+          const uint32_t a_t = tmem_base + (uint32_t)(((n_done - 1) & 1) * p.acc_stride);   // the previous tile's accumulator slot
           for (int cb = 0; cb < p.ncb2; ++cb) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const uint64_t a2 = ad + (uint64_t)(cb * (16384 >> 4) + 2 * k), w2 = wd + (uint64_t)(cb * (int)(p.w1_blk_bytes >> 4) + 2 * k);
-              if (kPair) tc_mma_f16_2sm(d2, a2, w2, idesc, (uint32_t)(cb | k)); else tc_mma_f16(d2, a2, w2, idesc, (uint32_t)(cb | k));
+              if (kPair && p.a_tmem) tc_mma_f16_2sm_ts(d2, a_t + (uint32_t)(cb * 64 + k * 8), w2, p.idesc2, (uint32_t)(cb | k));
+              else if (kPair) tc_mma_f16_2sm(d2, a2, w2, p.idesc2, (uint32_t)(cb | k));
+              else tc_mma_f16(d2, a2, w2, p.idesc2, (uint32_t)(cb | k));
             }
           }
-          if (kPair) tc_commit_2sm(&tmem_full2[prev_acc], mc_mask); else tc_commit(&tmem_full2[prev_acc]);
+          if (kPair) tc_commit_2sm(&tmem_full2[h], mc_mask); else tc_commit(&tmem_full2[h]);
         }
         __syncwarp();
       };
@@ -372,15 +389,15 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             if (++sw == T2_NW) { sw = 0; pw ^= 1; }
           }
           if (++sa == T2_NA) { sa = 0; pa ^= 1; }
+          if (kBlockEpi && p.fuse && n_done > 0) {
+            if (cb == p.c1_after0) issue_conv1(0);
+            if (cb == p.c1_after1) issue_conv1(1);
+          }
         }
-        if (kBlockEpi && p.fuse) {
-          if (n_done > 0) issue_conv1();
-          prev_acc = acc;
-          ++n_done;
-        }
+        if (kBlockEpi && p.fuse) ++n_done;
         if (++acc == nacc) { acc = 0; pacc ^= 1; }
       }
-      if (kBlockEpi && p.fuse && n_done > 0) issue_conv1();
+      if (kBlockEpi && p.fuse && n_done > 0) { issue_conv1(0); issue_conv1(1); }
     }
   } else if (kBlockEpi && warp >= 4 && p.fuse) {
     // ================= fused residual unit: epilogue 1 (conv7 -> operand tile) and epilogue 2 (conv1 -> stream, operand) =================
@@ -390,50 +407,87 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     const uint32_t cst_u32 = smem_u32(cst);
     const uint32_t sw128 = (uint32_t)(lane & 7);                         // 128B swizzle: chunk ^= row & 7
     uint8_t* const c_row = c_tile + (size_t)(quarter * 32 + lane) * 128;
-    const bool has_a2 = p.out_a2 != nullptr;
-    int acc = 0, pv_acc = 0, pv_b = 0, pv_t0 = 0;
-    uint32_t pacc = 0, pv_pacc = 0;
+    const bool has_a2 = p.out_a2 != nullptr, has_y2 = p.out_y2 != nullptr;
+    const int hch = p.BN / 64;                                           // 32-column chunks per N half
+    int acc = 0, pv_b = 0, pv_t0 = 0;
+    uint32_t pacc = 0, ptile = 0;                                        // ptile: parity of the previous tile's conv1 barriers
     bool have_prev = false, pv_mine = false;
-    auto epilogue2 = [&]() {   // of the previous tile: acc = conv1(...) ; + b1 + X -> X' [, snake_next(X')], stored from registers
-      const int trow = pv_t0 + quarter * 32 + lane;
-      const bool ok = pv_mine && trow < slot_rows;
-      const long long off = (long long)min(pv_b, p.B - 1) * p.o2_bstride + (long long)min(trow, slot_rows - 1) * p.N;
-      const T16* res_row = (const T16*)p.res2 + off;
-      uint4 rres[4] = {};
-      if (ok && grp < nch) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c) rres[c] = __ldg((const uint4*)(res_row + grp * 32 + 8 * c));
+    // Epilogue 2 of the previous tile, N half h: acc2 = conv1(...); + b1 + X -> X' [, snake_next(X')].  The residual chunk
+    // (32 rows x 32 columns of X) comes in by TMA into this warp's staging buffer, X' is written over it and leaves by TMA,
+    // then the operand reuses the buffer: no scattered 16-byte global accesses (they cost 32 LSU wavefronts per instruction).
+    const uint32_t buf = smem_u32(staging) + (uint32_t)ew * 2048u, my_row = buf + (uint32_t)lane * 64u;
+    const uint32_t sw64 = (uint32_t)((lane >> 1) & 3);
+    uint32_t xpar = 0;
+    auto epilogue2 = [&](int h) {
+      const int n = h * (p.BN / 2) + grp * 32, trow0 = pv_t0 + quarter * 32;
+      const bool ok = pv_mine && grp < hch && !(p.dbg & 2);              // warp-uniform
+      if (ok && lane == 0) {
+        tma_store_wait_read0();                                          // my previous store has drained the buffer
+        mbar_expect_tx(&xbar[ew], 2048u);
+        tma_load_3d((void*)(staging + (size_t)ew * 2048), &map_y, &xbar[ew], n, trow0, pv_b);
       }
-      mbar_wait(&tmem_full2[pv_acc], pv_pacc);
+      mbar_wait(&tmem_full2[h], ptile);
       tc_fence_after();
-      for (int ch = grp; ch < nch; ch += 3) {
+      if (ok) {
         uint32_t r[32];
-        tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(pv_acc * p.acc_stride + ch * 32), r);
-        if (ok && ch != grp) {
+        tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(p.acc2_col + grp * 32), r);
+        mbar_wait(&xbar[ew], xpar);
+        xpar ^= 1;
+        uint4 rres[4];
 #pragma unroll
-          for (int c = 0; c < 4; ++c) rres[c] = __ldg((const uint4*)(res_row + ch * 32 + 8 * c));
-        }
+        for (int c = 0; c < 4; ++c) rres[c] = lds128(my_row + ((((uint32_t)c) ^ sw64) << 4));
         tc_wait_ld();
-        const int n = ch * 32;
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {                                                 // the accumulator is in registers: conv1's next half may run
+          if (kPair && rank != 0) mbar_arrive_remote(acc2_empty, 0); else mbar_arrive(acc2_empty);
+        }
         const uint32_t sb = cst_u32 + 4u * (uint32_t)(3 * p.N + n), se = sb + 4u * (uint32_t)p.N, si = se + 4u * (uint32_t)p.N;
-        uint8_t* row_y = (uint8_t*)((T16*)p.out_y2 + off + n);
-        uint8_t* row_a = (uint8_t*)((T16*)p.out_a2 + off + n);
-        if (has_a2) epi_block_chunk<T16, true, true, true, true>(r, nullptr, nullptr, nullptr, sb, se, si, rres, row_y, row_a, 0u, 0u, ok);
-        else epi_block_chunk<T16, true, true, false, true>(r, nullptr, nullptr, nullptr, sb, se, si, rres, row_y, row_a, 0u, 0u, ok);
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (kPair && rank != 0) mbar_arrive_remote(&tmem_empty[pv_acc], 0); else mbar_arrive(&tmem_empty[pv_acc]);
+        epi_res_pass1<T16>(r, sb, rres, my_row, sw64);
+        if (has_y2) {
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) { tma_store_3d(&map_y, staging + (size_t)ew * 2048, n, trow0, pv_b); tma_store_commit(); }
+        }
+        if (has_a2) {
+          epi_res_pass2<T16>(r, se, si);
+          if (lane == 0) tma_store_wait_read0();
+          __syncwarp();
+#pragma unroll
+          for (int c = 0; c < 4; ++c) sts128(my_row + ((((uint32_t)c) ^ sw64) << 4), make_uint4(r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]));
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) { tma_store_3d(&map_o, staging + (size_t)ew * 2048, n, trow0, pv_b); tma_store_commit(); }
+        }
+      } else {
+        __syncwarp();
+        if (lane == 0) {
+          if (kPair && rank != 0) mbar_arrive_remote(acc2_empty, 0); else mbar_arrive(acc2_empty);
+        }
       }
     };
     for (int item = cid; item < items; item += ncl) {
       int b, t0, n0; bool mine;
       if (!coords(item, b, t0, n0, mine)) continue;
-      if (have_prev) epilogue2();                                        // also: conv1(prev) no longer reads the operand tile
+      if (have_prev) { epilogue2(0); epilogue2(1); ptile ^= 1; }          // also: conv1(prev) no longer reads the operand tile
       // ---- epilogue 1: acc + b7 -> snake -> conv1's operand tile (128B-swizzled, K-major) ----
       mbar_wait(&tmem_full[acc], pacc);
       tc_fence_after();
+      if (p.a_tmem) {
+        // warp (quarter, grp) owns accumulator columns [64 grp, 64 grp + 64): it reads them as two 32-column chunks and
+        // writes the packed 16-bit operand back over the first 32 of them (a chunk is in registers before its columns are reused)
+        const uint32_t t0a = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.acc_stride + grp * 64);
+        for (int c2 = 0; c2 < 2 && 2 * grp + c2 < nch; ++c2) {
+          uint32_t r[32], pk[16];
+          tc_ld32(t0a + (uint32_t)(c2 * 32), r);
+          tc_wait_ld();
+          const int n = (2 * grp + c2) * 32;
+          const uint32_t sb = cst_u32 + 4u * (uint32_t)n, se = sb + 4u * (uint32_t)p.N, si = se + 4u * (uint32_t)p.N;
+          epi_snake_pack<T16>(r, sb, se, si, !(p.dbg & 1), pk);
+          tc_st16(t0a + (uint32_t)(c2 * 16), pk);
+        }
+        tc_wait_st();
+      } else
       for (int ch = grp; ch < nch; ch += 3) {
         uint32_t r[32];
         tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.acc_stride + ch * 32), r);
@@ -442,18 +496,21 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         const uint32_t sb = cst_u32 + 4u * (uint32_t)n, se = sb + 4u * (uint32_t)p.N, si = se + 4u * (uint32_t)p.N;
         const uint4 none[4] = {};
         uint8_t* row_a = c_row + (size_t)(ch >> 1) * 16384;
-        epi_block_chunk<T16, false, false, true, true>(r, nullptr, nullptr, nullptr, sb, se, si, none, nullptr, row_a, (uint32_t)((ch & 1) * 4), sw128, true);
+        if (p.dbg & 1) epi_block_chunk<T16, false, true, false, true>(r, nullptr, nullptr, nullptr, sb, se, si, none, row_a, nullptr, (uint32_t)((ch & 1) * 4), sw128, true);
+        else epi_block_chunk<T16, false, false, true, true>(r, nullptr, nullptr, nullptr, sb, se, si, none, nullptr, row_a, (uint32_t)((ch & 1) * 4), sw128, true);
       }
       fence_async_smem();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) {
-        if (kPair && rank != 0) mbar_arrive_remote(c_ready, 0); else mbar_arrive(c_ready);
+      if (lane == 0) {   // the conv7 accumulator is drained and this warp's part of the operand tile is written
+        if (kPair && rank != 0) { mbar_arrive_remote(&tmem_empty[acc], 0); mbar_arrive_remote(c_ready, 0); }
+        else { mbar_arrive(&tmem_empty[acc]); mbar_arrive(c_ready); }
       }
-      have_prev = true; pv_acc = acc; pv_pacc = pacc; pv_b = b; pv_t0 = t0; pv_mine = mine;
+      have_prev = true; pv_b = b; pv_t0 = t0; pv_mine = mine;
       if (++acc == p.nacc) { acc = 0; pacc ^= 1; }
     }
-    if (have_prev) epilogue2();
+    if (have_prev) { epilogue2(0); epilogue2(1); }
+    if (lane == 0) tma_store_wait_all();
   } else if (kBlockEpi && warp >= 4) {
     // ================= block epilogue (12 warps) =================
     const int ew = warp - 4, quarter = warp & 3, grp = ew >> 2;          // grp 0..2 takes chunks grp, grp+3, ...
@@ -708,7 +765,7 @@ bool block_epilogue_ok(const ConvGemmParams& p, int y_dtype) {
   const bool with_a = p.out_a && p.snake_ea && p.act == ACT_NONE, y_only = !p.out_a && !p.snake_ea && p.out_y && !p.res && p.act == ACT_NONE;
   const bool plain_a = p.out_a && !p.snake_ea && !p.out_y && !p.res && (p.act == ACT_NONE || p.act == ACT_GELU);   // one 16-bit operand out
   return (with_a || y_only || plain_a) && p.bias && !p.out_tap && !p.scale &&
-         (!p.res || (p.out_y && p.res == p.out_y)) && (!p.out_y || y_dtype != DT_F32) && pick_bn2(p.N, true) % 32 == 0 &&
+         (!p.res || !p.out_y || p.res == p.out_y) && (!p.out_y || y_dtype != DT_F32) && pick_bn2(p.N, true) % 32 == 0 &&
          pick_bn2(p.N, true) >= 64;
 }
 int env_int(const char* name, int dflt) {
@@ -752,9 +809,8 @@ bool tc2_supported(const ConvGemmParams& p, int op_dtype) {
 }
 
 bool tc2_fuse_supported(const ConvGemmParams& p, int op_dtype) {
-  // Opt-in: with N = 192 TMEM holds two accumulators only, so conv1(i-1) queues behind conv7(i) and epilogue 2 cannot overlap the
-  // next conv7 -- measured 0.84 ms vs 0.68 ms for the two separate kernels (960 k rows).  Pays off only for N <= 128.
-  static const int on = env_int("Q3TTS_TC_FUSE", 0);
+  // conv7 + conv1 of a residual unit in one kernel: 0.48 ms vs 0.36 + 0.34 ms for N = 192 (960 k rows).  Q3TTS_TC_FUSE=0 disables.
+  static const int on = env_int("Q3TTS_TC_FUSE", 1);
   if (!on || !tc2_supported(p, op_dtype)) return false;
   // one N tile (the 1x1 conv needs every channel of the row), whole 64-channel blocks, operand tile + W1 half + rings in smem
   return p.N == p.Cin && p.N % 64 == 0 && p.N <= 192 && pick_bn2(p.N, true) == p.N && p.bias && p.snake_ea && p.act == ACT_NONE &&
@@ -786,7 +842,7 @@ cudaError_t launch_conv_gemm_tc2(const ConvGemmParams& p, const BatchGeom& g, in
   if (fuse && !pair) return cudaErrorNotSupported;
   q.cs = cs;
   q.nacc = (!fuse && BN <= 128 && nacc_env >= 4) ? 4 : 2;   // the fused unit tracks two conv1 accumulators
-  q.acc_stride = (int)T2_TMEM_COLS / q.nacc;
+  q.acc_stride = fuse ? BN : (int)T2_TMEM_COLS / q.nacc;            // fused unit: 2 x BN + BN/2 columns
   const CUtensorMapDataType dt = op_dtype == DT_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   CUtensorMap map_a, map_w;
   {
@@ -814,7 +870,10 @@ cudaError_t launch_conv_gemm_tc2(const ConvGemmParams& p, const BatchGeom& g, in
   q.w_tap_bytes = (uint32_t)(pair ? BN / 2 : BN) * 128u;     // pair mode: each CTA stages half of the weight tile
   {  // several taps share one W stage when the tiles are small: one barrier wait / commit per wg*nk MMAs
     static const int wg_env = env_int("Q3TTS_TC_WG_KB", 40);
-    const int wg_max = fuse ? 1 : std::max(1, (wg_env * 1024) / (int)q.w_tap_bytes);   // fused unit: small stages, deep ring
+    static const int fuse_ts_env = env_int("Q3TTS_FUSE_TS", 1);
+    // one wait + commit per W stage costs the issuing thread ~the time of two MMAs: 1-tap stages run N = 192 at 1.09 PFLOP/s,
+    // 3-tap stages at 1.36.  The fused unit can afford big stages only when conv1's operand lives in tensor memory.
+    const int wg_max = (fuse && !fuse_ts_env) ? 1 : std::max(1, (wg_env * 1024) / (int)q.w_tap_bytes);
     q.ngroups = (p.taps + wg_max - 1) / wg_max;
     q.wg = (p.taps + q.ngroups - 1) / q.ngroups;
     q.ngroups = (p.taps + q.wg - 1) / q.wg;
@@ -833,15 +892,21 @@ cudaError_t launch_conv_gemm_tc2(const ConvGemmParams& p, const BatchGeom& g, in
   const int yf = y_dtype == DT_F32;
   q.tma_y = !fuse && (epi_block || tma_store_env) && q.out_y && (!yf || plain_a) && p.act != ACT_SWIGLU;
   q.tma_a = !fuse && (epi_block || tma_store_env) && q.out_a && p.act != ACT_SWIGLU;
+  if (fuse) { q.tma_y = 1; q.tma_a = fuse->out_a != nullptr; }   // X (TMA load of the residual + store of X', in place) and the operand
   q.cst_staged = epi_block && (cst_env || fuse) && p.N <= T2_CST_MAX_N;
   CUtensorMap map_w2 = map_w;
   if (fuse) {
-    q.fuse = 1; q.ncb2 = p.N / T2_BK; q.w1_blk_bytes = (uint32_t)(BN / 2) * 128u;
+    static const int after0_env = env_int("Q3TTS_FUSE_AFTER0", 0), after1_env = env_int("Q3TTS_FUSE_AFTER1", 1), dbg_env = env_int("Q3TTS_FUSE_DBG", 0);
+    q.c1_after0 = std::min(after0_env, q.ncb - 1); q.c1_after1 = std::max(q.c1_after0, std::min(after1_env, q.ncb - 1)); q.dbg = dbg_env;
+    static const int ts_env = env_int("Q3TTS_FUSE_TS", 1);
+    q.a_tmem = ts_env != 0;
+    q.fuse = 1; q.ncb2 = p.N / T2_BK; q.w1_blk_bytes = (uint32_t)(BN / 4) * 128u; q.acc2_col = 2 * BN;
+    q.idesc2 = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 4) << 17) | ((uint32_t)((2 * T2_BM) >> 4) << 24);
     q.bias2 = fuse->bias; q.ea2 = fuse->ea; q.ib2 = fuse->ib;
     q.res2 = fuse->res; q.out_y2 = fuse->out_y; q.out_a2 = fuse->out_a; q.o2_bstride = (long long)slot_rows * p.N;
     cuuint64_t dims[2] = {(cuuint64_t)p.N, (cuuint64_t)p.N};
     cuuint64_t strides[1] = {(cuuint64_t)p.N * 2};
-    cuuint32_t box[2] = {T2_BK, (cuuint32_t)(BN / 2)};
+    cuuint32_t box[2] = {T2_BK, (cuuint32_t)(BN / 4)};
     cuuint32_t es[2] = {1, 1};
     if (enc(&map_w2, dt, 2, const_cast<void*>(fuse->W1), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
@@ -858,10 +923,16 @@ cudaError_t launch_conv_gemm_tc2(const ConvGemmParams& p, const BatchGeom& g, in
                epi_block ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
                CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
   };
-  if (q.tma_y && !out_map(&map_y, q.out_y, q.ldy, q.y_bstride)) return cudaErrorInvalidValue;
-  if (q.tma_a && !out_map(&map_o, q.out_a, q.lda_out, q.ao_bstride)) return cudaErrorInvalidValue;
-  q.staging_bytes = !(q.tma_y || q.tma_a) ? 0u : (epi_block ? (uint32_t)T2_EPI_WARPS_BLOCK * ((q.tma_y && q.tma_a) ? 4096u : 2048u) : T2_STAGING_BYTES);
-  const size_t fixed = q.staging_bytes + (fuse ? (size_t)q.ncb2 * (16384 + q.w1_blk_bytes) : 0) + (q.cst_staged ? (size_t)(fuse ? 6 : 3) * p.N * 4 : 0) + 512 + 1024;
+  if (fuse) {
+    if (fuse->out_y && fuse->res != fuse->out_y) return cudaErrorNotSupported;   // the stream is updated in place (or not written)
+    if (!out_map(&map_y, const_cast<void*>(fuse->res), p.N, (long long)slot_rows * p.N)) return cudaErrorInvalidValue;
+    if (q.tma_a && !out_map(&map_o, fuse->out_a, p.N, (long long)slot_rows * p.N)) return cudaErrorInvalidValue;
+  } else {
+    if (q.tma_y && !out_map(&map_y, q.out_y, q.ldy, q.y_bstride)) return cudaErrorInvalidValue;
+    if (q.tma_a && !out_map(&map_o, q.out_a, q.lda_out, q.ao_bstride)) return cudaErrorInvalidValue;
+  }
+  q.staging_bytes = !(q.tma_y || q.tma_a) ? 0u : (epi_block ? (uint32_t)T2_EPI_WARPS_BLOCK * ((q.tma_y && q.tma_a && !fuse) ? 4096u : 2048u) : T2_STAGING_BYTES);
+  const size_t fixed = q.staging_bytes + (fuse ? (size_t)q.ncb2 * ((q.a_tmem ? 0 : 16384) + 2 * q.w1_blk_bytes) : 0) + (q.cst_staged ? (size_t)(fuse ? 6 : 3) * p.N * 4 : 0) + 640 + 1024;
   auto magic = [](uint32_t d, uint32_t* m, uint32_t* sh) {   // x / d == umulhi(x, m) >> sh for 0 <= x < 2^31
     uint32_t lg = 0;
     while ((1u << lg) < d) ++lg;
@@ -890,6 +961,14 @@ cudaError_t launch_conv_gemm_tc2(const ConvGemmParams& p, const BatchGeom& g, in
     na = std::max(2, std::min(T2_MAX_NA, na));
     while (na > 2 && (size_t)na * q.a_stage_bytes + 3 * (size_t)q.w_stage_bytes > budget) --na;
     q.na = na;
+    q.nw = (int)std::min<size_t>(T2_MAX_NW, (budget - (size_t)q.na * q.a_stage_bytes) / q.w_stage_bytes);
+    static const int max_nw_env = env_int("Q3TTS_TC_MAX_NW", T2_MAX_NW);   // experiments: cap the W ring depth
+    q.nw = std::min(q.nw, std::max(2, max_nw_env));
+  }
+  static const int na_env = env_int("Q3TTS_TC_NA", 0);   // experiments
+  if (na_env > 0 && !q.w_resident) {
+    q.na = std::min(T2_MAX_NA, na_env);
+    if ((size_t)q.na * q.a_stage_bytes + 2 * (size_t)q.w_stage_bytes > budget) return cudaErrorInvalidConfiguration;
     q.nw = (int)std::min<size_t>(T2_MAX_NW, (budget - (size_t)q.na * q.a_stage_bytes) / q.w_stage_bytes);
   }
   // Two MMA issuer warps on alternate tiles: a warp then waits on ring slots up to one tile ahead of the other's, and

@@ -179,6 +179,20 @@ __device__ __forceinline__ void tc_mma_f16_2sm(uint32_t tmem_d, uint64_t adesc, 
       "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// A operand from TENSOR MEMORY (lane = row, one 32-bit column = two consecutive K elements), B from smem.
+__device__ __forceinline__ void tc_mma_f16_2sm_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit_2sm(uint64_t* bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(smem_u32(bar)), "h"(mask) : "memory");
@@ -281,6 +295,71 @@ __device__ __forceinline__ void epi_block_chunk(const uint32_t (&r)[32], const f
         *(uint4*)(row_a + at) = make_uint4(Cvt<T16>::pack(v[0], v[1]), Cvt<T16>::pack(v[2], v[3]),
                                            Cvt<T16>::pack(v[4], v[5]), Cvt<T16>::pack(v[6], v[7]));
     }
+  }
+}
+
+// Two-pass form of the residual epilogue for ONE staging buffer per warp (fused residual unit): pass 1 turns the accumulator
+// chunk into v = acc + bias + residual IN PLACE (fp32 bits in r) and writes the packed stream row; pass 2 writes snake(v).
+// `row` is this lane's 64-byte row of the warp's SWIZZLE_64B staging buffer (swz = (lane >> 1) & 3).
+template <typename T16>
+__device__ __forceinline__ void epi_res_pass1(uint32_t (&r)[32], uint32_t s_bias, const uint4 (&rres)[4], uint32_t row, uint32_t swz) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const float4 b0 = lds4f(s_bias + 32u * c), b1 = lds4f(s_bias + 32u * c + 16u);
+    const uint4 u = rres[c];
+    const float2 r0 = Cvt<T16>::unpack(u.x), r1 = Cvt<T16>::unpack(u.y), r2 = Cvt<T16>::unpack(u.z), r3 = Cvt<T16>::unpack(u.w);
+    float v[8];
+    v[0] = __uint_as_float(r[8 * c + 0]) + b0.x + r0.x; v[1] = __uint_as_float(r[8 * c + 1]) + b0.y + r0.y;
+    v[2] = __uint_as_float(r[8 * c + 2]) + b0.z + r1.x; v[3] = __uint_as_float(r[8 * c + 3]) + b0.w + r1.y;
+    v[4] = __uint_as_float(r[8 * c + 4]) + b1.x + r2.x; v[5] = __uint_as_float(r[8 * c + 5]) + b1.y + r2.y;
+    v[6] = __uint_as_float(r[8 * c + 6]) + b1.z + r3.x; v[7] = __uint_as_float(r[8 * c + 7]) + b1.w + r3.y;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) r[8 * c + e] = __float_as_uint(v[e]);
+    sts128(row + ((((uint32_t)c) ^ swz) << 4), make_uint4(Cvt<T16>::pack(v[0], v[1]), Cvt<T16>::pack(v[2], v[3]),
+                                                          Cvt<T16>::pack(v[4], v[5]), Cvt<T16>::pack(v[6], v[7])));
+  }
+}
+// acc + bias -> [snake] -> 16 packed words (the 1x1 conv's operand, kept in tensor memory)
+template <typename T16>
+__device__ __forceinline__ void epi_snake_pack(const uint32_t (&r)[32], uint32_t s_bias, uint32_t s_ea, uint32_t s_ib, bool snake, uint32_t (&out)[16]) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const float4 b0 = lds4f(s_bias + 32u * c), b1 = lds4f(s_bias + 32u * c + 16u);
+    float v[8];
+    v[0] = __uint_as_float(r[8 * c + 0]) + b0.x; v[1] = __uint_as_float(r[8 * c + 1]) + b0.y;
+    v[2] = __uint_as_float(r[8 * c + 2]) + b0.z; v[3] = __uint_as_float(r[8 * c + 3]) + b0.w;
+    v[4] = __uint_as_float(r[8 * c + 4]) + b1.x; v[5] = __uint_as_float(r[8 * c + 5]) + b1.y;
+    v[6] = __uint_as_float(r[8 * c + 6]) + b1.z; v[7] = __uint_as_float(r[8 * c + 7]) + b1.w;
+    if (snake) {
+      const float4 e0 = lds4f(s_ea + 32u * c), e1 = lds4f(s_ea + 32u * c + 16u);
+      const float4 i0 = lds4f(s_ib + 32u * c), i1 = lds4f(s_ib + 32u * c + 16u);
+      const float ee[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w}, ii[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float sn = __sinf(v[e] * ee[e]);
+        v[e] = fmaf(ii[e], sn * sn, v[e]);
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) out[4 * c + e] = Cvt<T16>::pack(v[2 * e], v[2 * e + 1]);
+  }
+}
+template <typename T16>
+__device__ __forceinline__ void epi_res_pass2(uint32_t (&r)[32], uint32_t s_ea, uint32_t s_ib) {   // r <- packed snake(v), 16 words
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const float4 e0 = lds4f(s_ea + 32u * c), e1 = lds4f(s_ea + 32u * c + 16u);
+    const float4 i0 = lds4f(s_ib + 32u * c), i1 = lds4f(s_ib + 32u * c + 16u);
+    const float ee[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w}, ii[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      v[e] = __uint_as_float(r[8 * c + e]);
+      const float sn = __sinf(v[e] * ee[e]);
+      v[e] = fmaf(ii[e], sn * sn, v[e]);
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) r[4 * c + e] = Cvt<T16>::pack(v[2 * e], v[2 * e + 1]);
   }
 }
 
