@@ -46,12 +46,15 @@ constexpr uint32_t R_W7_BYTES = 7 * R_SUB * R_WBLK;  // 64512
 constexpr uint32_t R_W1_BYTES = R_SUB * R_WBLK;      // 9216
 constexpr uint32_t R_CST = 6 * R_C * 4;              // b7, ea2, ib2, b1, ea3, ib3
 constexpr uint32_t R_TMEM_COLS = 512;
+constexpr uint32_t R_STG_WARP = 32 * 48 * 2;         // epilogue 2: one warp's 32 rows x 48 channels (residual in, X' out)
+constexpr uint32_t R_STG_BYTES = R_E2W * R_STG_WARP;
 
 struct Res96Params {
   int B, Tmax, rows_per_frame;
   const int* len_frames;
   int dil, halo, hb;              // halo = 6*dil rows; hb = halo rounded up to 8 rows (TMA box and smem alignment)
   int tiles_per_cta;
+  int nslots;                     // ring depth (3 or 4 tiles)
   uint32_t tsub_bytes;            // one 32-channel block of the ring: 4 slots x (hb + 128) rows x 64 B, rounded to 1024
   void* out;                      // [B, slot_rows, 96] 16-bit
   uint32_t idesc7;                // M = 256, N = 96
@@ -59,6 +62,7 @@ struct Res96Params {
   int out_snake;                  // write snake3(X') instead of X' (last unit of the block)
   const void* x_in; long long x_bstride;   // residual rows (elements)
   long long* dbg;                 // optional [16 events][32 tiles] clock64 stamps of CTA 0 (pipeline debugging)
+  int skip;                       // experiments (wrong results): 1 = no residual loads, 2 = no output stores
 };
 
 // Position of a CTA in its strip of valid tiles (warp-uniform).
@@ -111,16 +115,23 @@ __device__ __forceinline__ void arrive_pair(uint32_t* cnt, uint32_t nwarps, uint
   }
 }
 
+__device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+
 template <typename T16>
 __global__ void __launch_bounds__(R_THREADS, 1)
 resunit96_kernel(const __grid_constant__ CUtensorMap map_main, const __grid_constant__ CUtensorMap map_halo,
-                 const __grid_constant__ CUtensorMap map_w7, const __grid_constant__ CUtensorMap map_w1, Res96Params p) {
+                 const __grid_constant__ CUtensorMap map_w7, const __grid_constant__ CUtensorMap map_w1,
+                 const __grid_constant__ CUtensorMap map_res, const __grid_constant__ CUtensorMap map_out, Res96Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* t_ring = smem;                                    // [3 blocks][4 slots][hb halo rows + 128 rows][64 B]
   uint8_t* w7s = t_ring + (size_t)R_SUB * p.tsub_bytes;      // [7 taps][3 blocks][48 rows][64 B]
   uint8_t* w1s = w7s + R_W7_BYTES;                           // [3 blocks][48 rows][64 B]
-  float* cst = (float*)(w1s + R_W1_BYTES);
+  uint8_t* stg = w1s + R_W1_BYTES;                           // [8 epilogue-2 warps][32 rows][96 B]
+  float* cst = (float*)(stg + R_STG_BYTES);
   uint64_t* bars = (uint64_t*)((uint8_t*)cst + R_CST);
   uint64_t* w_full = bars;              // 1
   uint64_t* t_full = bars + 1;          // [4] local: X tile landed
@@ -131,7 +142,8 @@ resunit96_kernel(const __grid_constant__ CUtensorMap map_main, const __grid_cons
   uint64_t* c_ready = bars + 19;        // [2] leader: epilogue 1 done in both CTAs (conv1 operand written, acc1 drained)
   uint64_t* acc2_full = bars + 21;      // [2] both: conv1 has completed
   uint64_t* acc2_free = bars + 23;      // [2] leader: epilogue 2 has drained acc2 in both CTAs
-  uint32_t* cnt = (uint32_t*)(bars + 25);   // cnt_a[4], cnt_c[2], cnt_f[2]
+  uint64_t* xbar = bars + 25;           // [8] local: an epilogue-2 warp's residual rows have landed
+  uint32_t* cnt = (uint32_t*)(bars + 33);   // cnt_a[4], cnt_c[2], cnt_f[2]
   uint32_t* tmem_ptr = cnt + 8;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -139,18 +151,21 @@ resunit96_kernel(const __grid_constant__ CUtensorMap map_main, const __grid_cons
   const uint16_t mc_mask = 3;
   const int q = p.tiles_per_cta;
   const int hb = p.hb, rs = p.hb + R_BM;          // rows per ring slot: its own halo rows, then the tile
+  const int ns = p.nslots;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_main) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_halo) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w7) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w1) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_res) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_out) : "memory");
   }
   if (warp == 1 && lane == 0) {
     mbar_init(w_full, 1);
     for (int i = 0; i < R_SLOTS; ++i) { mbar_init(&t_full[i], 1); mbar_init(&a_ready[i], 2); mbar_init(&c7_done[i], 1); mbar_init(&slot_free[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc1_full[i], 1); mbar_init(&c_ready[i], 2); mbar_init(&acc2_full[i], 1); mbar_init(&acc2_free[i], 2); }
-    for (int i = 0; i < 8; ++i) cnt[i] = 0;
+    for (int i = 0; i < 8; ++i) { cnt[i] = 0; mbar_init(&xbar[i], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -183,8 +198,8 @@ resunit96_kernel(const __grid_constant__ CUtensorMap map_main, const __grid_cons
     Walker w;
     w.init(p, g0);
     for (int j = 0; j < q; ++j) {
-      const int slot = j % R_SLOTS;
-      if (j >= R_SLOTS) mbar_wait_sleep(&slot_free[slot], (uint32_t)(((j - R_SLOTS) / R_SLOTS) & 1));   // conv7 and conv1 of the slot's previous tile are over
+      const int slot = j % ns;
+      if (j >= ns) mbar_wait_sleep(&c7_done[slot], (uint32_t)(((j - ns) / ns) & 1));   // conv7 of the slot's previous tile is over (conv1 reads tensor memory)
       R_STAMP(0, j);
       if (elect_one()) {
         if (w.live(p)) {
@@ -212,8 +227,8 @@ resunit96_kernel(const __grid_constant__ CUtensorMap map_main, const __grid_cons
       mbar_wait_sleep(w_full, 0);
       for (int i = 0; i <= q; ++i) {
         if (i < q) {
-          const int slot = i % R_SLOTS;
-          mbar_wait_sleep(&a_ready[slot], (uint32_t)((i / R_SLOTS) & 1));
+          const int slot = i % ns;
+          mbar_wait_sleep(&a_ready[slot], (uint32_t)((i / ns) & 1));
           tc_fence_after();
           R_STAMP(4, i);
           if (elect_one()) {
@@ -246,16 +261,19 @@ resunit96_kernel(const __grid_constant__ CUtensorMap map_main, const __grid_cons
           tc_fence_after();
           R_STAMP(6, t);
           if (elect_one()) {
-            const uint32_t d_tmem = tmem_base + 256u + (uint32_t)((t & 1) * 128);
-            const int tslot = t % R_SLOTS;          // epilogue 1 wrote conv1's operand over the tile's own (dead) rows
-            const uint64_t ad = desc_fixed | (uint64_t)((t_u32 + (uint32_t)(tslot * rs + hb) * 64u) >> 4), wd = desc_fixed | (uint64_t)(w1_u32 >> 4);
+            // epilogue 1 packed conv1's operand over the drained conv7 accumulator: channels 0..47 in columns 0..23,
+            // channels 48..95 in columns 48..71 of the slot (each epilogue warp writes inside the columns it has read)
+            const uint32_t d_tmem = tmem_base + 256u + (uint32_t)((t & 1) * 128), a_tmem = tmem_base + (uint32_t)((t & 1) * 128);
+            const uint64_t wd = desc_fixed | (uint64_t)(w1_u32 >> 4);
 #pragma unroll
             for (int c = 0; c < R_SUB; ++c) {
 #pragma unroll
-              for (int k = 0; k < 2; ++k)
-                tc_mma_f16_2sm(d_tmem, ad + (uint64_t)(c * tsub16 + 2 * k), wd + (uint64_t)(c * (R_WBLK >> 4) + 2 * k), idesc, (uint32_t)(c | k));
+              for (int k = 0; k < 2; ++k) {
+                const int j16 = 2 * c + k;                       // 16-channel step
+                const uint32_t a_col = (uint32_t)(j16 < 3 ? 8 * j16 : 48 + 8 * (j16 - 3));
+                tc_mma_f16_2sm_ts(d_tmem, a_tmem + a_col, wd + (uint64_t)(c * (R_WBLK >> 4) + 2 * k), idesc, (uint32_t)(c | k));
+              }
             }
-            tc_commit_2sm(&slot_free[tslot], mc_mask);
             tc_commit_2sm(&acc2_full[t & 1], mc_mask);
           }
           __syncwarp();
@@ -278,19 +296,19 @@ resunit96_kernel(const __grid_constant__ CUtensorMap map_main, const __grid_cons
     Walker w;
     w.init(p, g0);
     for (int j = 0; j < q; ++j) {
-      const int slot = j % R_SLOTS, nslot = (j + 1) % R_SLOTS;
+      const int slot = j % ns, nslot = (j + 1) % ns;
       const bool live = w.live(p), first = w.first;
       w.next(p);                                                  // now describes tile j+1
       const bool copy_tail = live && j + 1 < q && w.live(p) && !w.first;
-      mbar_wait_sleep(&t_full[slot], (uint32_t)((j / R_SLOTS) & 1));
+      mbar_wait_sleep(&t_full[slot], (uint32_t)((j / ns) & 1));
       if (pw == 0) R_STAMP(2, j);
-      bool tail_ok = !(copy_tail && j >= R_SLOTS - 1);          // else: conv7 of the next slot's previous tile may still read its halo rows
+      bool tail_ok = !(copy_tail && j >= ns - 1);          // else: conv7 of the next slot's previous tile may still read its halo rows
       if (live) {
         for (int G = (first ? 0 : hb / 8) + par; G < ngroups; G += 4) {
           const int G2 = G + 2;
           const bool two = G2 < ngroups;
           if (!tail_ok && (two ? G2 : G) * 8 >= R_BM) {            // first iteration that touches the tail (groups ascend)
-            mbar_wait_sleep(&c7_done[nslot], (uint32_t)(((j - (R_SLOTS - 1)) / R_SLOTS) & 1));
+            mbar_wait_sleep(&c7_done[nslot], (uint32_t)(((j - (ns - 1)) / ns) & 1));
             tail_ok = true;
           }
           uint32_t addr[2], naddr[2];
@@ -334,8 +352,6 @@ resunit96_kernel(const __grid_constant__ CUtensorMap map_main, const __grid_cons
     // The operand is written over the tile's own rows in the ring (dead once conv7 has completed).
     const int quarter = warp & 3, col_base = ((warp - R_CTRL - R_PW) >> 2) * 48;
     const uint32_t cst_u32 = smem_u32(cst);
-    const uint32_t sw64 = (uint32_t)((lane >> 1) & 3);
-    const uint32_t ring_row_u32 = smem_u32(t_ring) + (uint32_t)(hb + quarter * 32 + lane) * 64u;
     Walker w;
     w.init(p, g0);
     for (int t = 0; t < q; ++t) {
@@ -344,7 +360,6 @@ resunit96_kernel(const __grid_constant__ CUtensorMap map_main, const __grid_cons
       tc_fence_after();
       if (warp == R_CTRL + R_PW) R_STAMP(8, t);
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((t & 1) * 128 + col_base);
-      const uint32_t slot_u32 = ring_row_u32 + (uint32_t)((t % R_SLOTS) * rs) * 64u;
       uint32_t r[2][16];
       tc_ld16(taddr, r[0]);
 #pragma unroll
@@ -354,8 +369,7 @@ resunit96_kernel(const __grid_constant__ CUtensorMap map_main, const __grid_cons
         if (live) {
           const int col = col_base + 16 * m;
           const uint32_t sb = cst_u32 + 4u * (uint32_t)col, se = sb + 4u * R_C, si = se + 4u * R_C;
-          const uint32_t dst = slot_u32 + (uint32_t)(col >> 5) * p.tsub_bytes;
-          const uint32_t kc = (uint32_t)((col & 31) >> 3);
+          uint32_t pk[8];
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const float4 b0 = lds4f(sb + 32u * h), b1 = lds4f(sb + 32u * h + 16u);
@@ -371,12 +385,13 @@ resunit96_kernel(const __grid_constant__ CUtensorMap map_main, const __grid_cons
               const float sn = __sinf(x * ee[e]);
               v[e] = fmaf(ii[e], sn * sn, x);
             }
-            sts128(dst + (((kc + (uint32_t)h) ^ sw64) << 4),
-                   make_uint4(Cvt<T16>::pack(v[0], v[1]), Cvt<T16>::pack(v[2], v[3]), Cvt<T16>::pack(v[4], v[5]), Cvt<T16>::pack(v[6], v[7])));
+#pragma unroll
+            for (int e = 0; e < 4; ++e) pk[4 * h + e] = Cvt<T16>::pack(v[2 * e], v[2 * e + 1]);
           }
+          tc_st8(taddr + 8u * (uint32_t)m, pk);   // columns of chunks already in registers (chunk m+1 at most in flight, further right)
         }
       }
-      fence_async_smem();
+      tc_wait_st();
       tc_fence_before();
       __syncwarp();
       if (warp == R_CTRL + R_PW) R_STAMP(9, t);
@@ -385,28 +400,38 @@ resunit96_kernel(const __grid_constant__ CUtensorMap map_main, const __grid_cons
     }
   } else if (warp >= R_CTRL + R_PW + R_E1W) {
     // ================= epilogue-2 warps (two per TMEM lane quarter, 48 channels each): acc2 + b1 + X -> X' (or snake3(X')) =================
-    // The residual rows (L2 hits: the tile went through L2 a few microseconds ago) are requested before the accumulator
-    // is waited for.  Stored straight from registers: a lane owns 96 contiguous bytes of its row.
-    const int quarter = warp & 3, col_base = ((warp - R_CTRL - R_PW - R_E1W) >> 2) * 48;
+    // The residual rows (L2 hits: the tile went through L2 a few microseconds ago) come in by TMA into the warp's staging
+    // buffer before the accumulator is waited for; X' is written over them and leaves by TMA.  (Direct 16-byte global
+    // accesses with a 192-byte row pitch cost 32 LSU wavefronts per instruction and slowed every other role by 15-20 %.)
+    const int e2w = warp - R_CTRL - R_PW - R_E1W;
+    const int quarter = warp & 3, col_base = (e2w >> 2) * 48;
     const uint32_t cst_u32 = smem_u32(cst);
-    const int slot_rows = p.Tmax * p.rows_per_frame;
+    uint8_t* my_stg = stg + (size_t)e2w * R_STG_WARP;
+    const uint32_t my_row = smem_u32(my_stg) + (uint32_t)lane * 96u;
+    uint32_t xpar = 0;
     Walker w;
     w.init(p, g0);
     for (int u = 0; u < q; ++u) {
-      const int row = w.t0 + quarter * 32 + lane;
-      const bool row_ok = w.live(p) && row < slot_rows;
-      const long long off = (long long)min(w.b, p.B - 1) * p.x_bstride + (long long)min(row, slot_rows - 1) * R_C + col_base;
-      const uint4* res_row = (const uint4*)((const T16*)p.x_in + off);
-      uint4* out_row = (uint4*)((T16*)p.out + off);
-      uint4 rr[6];
-#pragma unroll
-      for (int c = 0; c < 6; ++c) rr[c] = row_ok ? __ldg(res_row + c) : make_uint4(0, 0, 0, 0);
+      const bool row_ok = w.live(p) && !(p.skip & 4);               // warp-uniform
+      const int row0 = w.t0 + quarter * 32;
+      if (row_ok && lane == 0) {
+        tma_store_wait_read0();                                      // my previous store has drained the buffer
+        mbar_expect_tx(&xbar[e2w], R_STG_WARP);
+        tma_load_3d(my_stg, &map_res, &xbar[e2w], col_base, row0, w.b);
+      }
       mbar_wait_sleep(&acc2_full[u & 1], (uint32_t)((u >> 1) & 1));
       tc_fence_after();
       if (warp == R_CTRL + R_PW + R_E1W) R_STAMP(10, u);
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(256 + (u & 1) * 128 + col_base);
       uint32_t r[2][16];
       tc_ld16(taddr, r[0]);
+      uint4 rr[6];
+      if (row_ok) {
+        mbar_wait_sleep(&xbar[e2w], xpar);
+        xpar ^= 1;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) rr[c] = lds128(my_row + 16u * (uint32_t)c);
+      }
 #pragma unroll
       for (int m = 0; m < 3; ++m) {
         tc_wait_ld();
@@ -454,13 +479,19 @@ resunit96_kernel(const __grid_constant__ CUtensorMap map_main, const __grid_cons
                                                              __uint_as_float(r[m & 1][8 * h + 2 * e + 1]) + bb[2 * e + 1]), rw[e]);
             }
           }
-          out_row[2 * m] = make_uint4(o[0], o[1], o[2], o[3]);
-          out_row[2 * m + 1] = make_uint4(o[4], o[5], o[6], o[7]);
+          sts128(my_row + 32u * (uint32_t)m, make_uint4(o[0], o[1], o[2], o[3]));
+          sts128(my_row + 32u * (uint32_t)m + 16u, make_uint4(o[4], o[5], o[6], o[7]));
         }
+      }
+      if (row_ok) {
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) { tma_store_3d(&map_out, my_stg, col_base, row0, w.b); tma_store_commit(); }
       }
       if (warp == R_CTRL + R_PW + R_E1W) R_STAMP(11, u);
       w.next(p);
     }
+    if (lane == 0) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
@@ -503,7 +534,11 @@ cudaError_t launch_resunit96(const ResUnitParams& p, const BatchGeom& g, int op_
   Res96Params q{};
   q.B = g.B; q.Tmax = g.Tmax; q.rows_per_frame = p.rows_per_frame; q.len_frames = g.len_frames;
   q.dil = p.dil; q.halo = 6 * p.dil; q.hb = (q.halo + 7) & ~7;
-  q.tsub_bytes = ((uint32_t)(R_SLOTS * (q.hb + R_BM)) * 64u + 1023u) & ~1023u;
+  static const int slots_env = []() { const char* e = getenv("Q3TTS_RES_SLOTS"); return e ? atoi(e) : 0; }();
+  const size_t fixed = R_W7_BYTES + R_W1_BYTES + R_STG_BYTES + R_CST + 512 + 1024;
+  auto tsub = [&](int n) { return ((uint32_t)(n * (q.hb + R_BM)) * 64u + 1023u) & ~1023u; };
+  q.nslots = (slots_env == 3 || (size_t)R_SUB * tsub(R_SLOTS) + fixed > 227 * 1024) ? 3 : R_SLOTS;   // dil 9: three slots
+  q.tsub_bytes = tsub(q.nslots);
   q.out = p.out;
   const uint32_t fmt = op_dtype == DT_F16 ? 0u : 1u;
   q.idesc7 = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(R_C >> 3) << 17) | ((uint32_t)((2 * R_BM) >> 4) << 24);
@@ -511,6 +546,7 @@ cudaError_t launch_resunit96(const ResUnitParams& p, const BatchGeom& g, int op_
   q.out_snake = p.ea3 != nullptr;
   q.x_in = p.x_in; q.x_bstride = (long long)slot_rows * R_C;
   q.dbg = (long long*)p.dbg;
+  { const char* e = getenv("Q3TTS_RES_SKIP"); q.skip = e ? atoi(e) : 0; }
   int sms = 0, dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -518,14 +554,14 @@ cudaError_t launch_resunit96(const ResUnitParams& p, const BatchGeom& g, int op_
   int grid = (int)std::min<long long>(sms / 2 * 2, (tiles_bound + 1) / 2 * 2);
   grid = std::max(grid, 2);
   q.tiles_per_cta = (int)((tiles_bound + grid - 1) / grid);
-  CUtensorMap map_main, map_halo, map_w7, map_w1;
+  CUtensorMap map_main, map_halo, map_w7, map_w1, map_res, map_out;
   auto act_map = [&](CUtensorMap* m, const void* base, cuuint32_t cols, cuuint32_t rows) -> bool {
     cuuint64_t dims[3] = {(cuuint64_t)R_C, (cuuint64_t)slot_rows, (cuuint64_t)g.B};
     cuuint64_t strides[2] = {(cuuint64_t)R_C * 2, (cuuint64_t)slot_rows * R_C * 2};
     cuuint32_t box[3] = {cols, rows, 1};
     cuuint32_t es[3] = {1, 1, 1};
     return enc(m, dt, 3, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               cols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
+               cols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE,
                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
   };
   auto w_map = [&](CUtensorMap* m, const void* base, int rows) -> bool {
@@ -537,9 +573,10 @@ cudaError_t launch_resunit96(const ResUnitParams& p, const BatchGeom& g, int op_
                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
   };
   if (!act_map(&map_main, p.x_in, 32, R_BM) || !act_map(&map_halo, p.x_in, 32, (cuuint32_t)q.hb) ||
-      !w_map(&map_w7, p.w7, 7 * R_C) || !w_map(&map_w1, p.w1, R_C))
+      !w_map(&map_w7, p.w7, 7 * R_C) || !w_map(&map_w1, p.w1, R_C) ||
+      !act_map(&map_res, p.x_in, 48, 32) || !act_map(&map_out, p.out, 48, 32))
     return cudaErrorInvalidValue;
-  const size_t smem = (size_t)R_SUB * q.tsub_bytes + R_W7_BYTES + R_W1_BYTES + R_CST + 512 + 1024;
+  const size_t smem = (size_t)R_SUB * q.tsub_bytes + fixed;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(R_THREADS);
@@ -555,8 +592,8 @@ cudaError_t launch_resunit96(const ResUnitParams& p, const BatchGeom& g, int op_
     cudaFuncSetAttribute(resunit96_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaFuncSetAttribute(resunit96_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   });
-  if (op_dtype == DT_F16) return cudaLaunchKernelEx(&cfg, resunit96_kernel<__half>, map_main, map_halo, map_w7, map_w1, q);
-  return cudaLaunchKernelEx(&cfg, resunit96_kernel<__nv_bfloat16>, map_main, map_halo, map_w7, map_w1, q);
+  if (op_dtype == DT_F16) return cudaLaunchKernelEx(&cfg, resunit96_kernel<__half>, map_main, map_halo, map_w7, map_w1, map_res, map_out, q);
+  return cudaLaunchKernelEx(&cfg, resunit96_kernel<__nv_bfloat16>, map_main, map_halo, map_w7, map_w1, map_res, map_out, q);
 }
 
 }  // namespace q3
