@@ -8,20 +8,22 @@
 //
 //   * the two CTAs of a cluster form a cta_group::2 pair (M = 256): each CTA walks its OWN contiguous strip of 128-row
 //     tiles in time order and holds half (48 output channels) of W7 [7,96,96] and W1 [96,96] in smem (72 KB);
-//   * activations live in a 4-slot smem ring per 32-channel block (64-byte rows, SWIZZLE_64B, K-major); a slot is the tile's
-//     causal halo (6*dil rows) followed by its 128 rows.  The halo is a copy of the previous tile's last rows made by pass 1,
-//     so it is neither re-read nor re-activated.  Epilogue 1 writes conv1's operand over the tile's own rows (dead once conv7
-//     has completed): there is no separate operand tile, and a slot is free again when its conv1 has completed.  Only the
-//     first tile of a strip loads its halo from HBM (out-of-range rows of an utterance's first tile are TMA zero fill =
-//     the causal padding, and snake(0) = 0);
+//   * activations live in a 3- or 4-slot smem ring per 32-channel block (64-byte rows, SWIZZLE_64B, K-major); a slot is the
+//     tile's causal halo (6*dil rows) followed by its 128 rows.  The halo is a copy of the previous tile's last rows made by
+//     pass 1, so it is neither re-read nor re-activated.  Only the first tile of a strip loads its halo from HBM (out-of-range
+//     rows of an utterance's first tile are TMA zero fill = the causal padding, and snake(0) = 0).  A slot is free again as
+//     soon as conv7 of its tile has completed;
 //   * pass 1 (6 warps): snake1 in place on the freshly landed tile;  conv7 = 42 tcgen05.mma (7 taps x 3 blocks x 2 k-steps,
-//     tap j = the ring viewed from row j*dil) into TMEM;  epilogue 1: + b7, snake2, 16-bit, written straight into the
-//     swizzled operand tile of conv1 (6 MMAs);  epilogue 2: + b1 + X (residual rows re-read from L2), stored from registers (8 + 8 warps);
+//     tap j = the ring viewed from row j*dil) into TMEM;  epilogue 1 (8 warps): + b7, snake2, packed to 16 bits and written
+//     with tcgen05.st over the accumulator columns it has just read -- conv1 (6 MMAs) takes its A operand from TENSOR MEMORY,
+//     so there is no operand tile in smem at all;  epilogue 2 (8 warps): + b1 + X -> X'.  The residual rows come in by TMA
+//     (L2 hits) into a per-warp staging buffer, X' is written over them and leaves by TMA: direct 16-byte global accesses
+//     with a 192-byte row pitch cost 32 LSU wavefronts per instruction and slowed every role by 10-20 %;
 //   * the roles are decoupled (producer, MMA issuer, pass-1, epilogue-1 and epilogue-2 warps) and meet only at mbarriers, so
 //     pass 1 of tile i+1 and the epilogues of tiles i-1 / i-2 fill the issue slots while conv7(i) runs; MMA order is
 //     c7(0) c7(1) c1(0) c7(2) c1(1) ...
-//   * cross-CTA hand-offs (operand tile ready, accumulator drained) are counted per CTA in smem; the last arriving warp
-//     forwards ONE arrive to the leader's mbarrier (a cluster-scope release per warp would cost a MEMBAR.ALL.GPU each).
+//   * cross-CTA hand-offs (operand tile ready, accumulator drained): every role warp arrives once on the LEADER's mbarrier
+//     with default (CTA-scope) semantics; a cluster-scope release per warp would cost a MEMBAR.ALL.GPU each.
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -98,21 +100,12 @@ struct Walker {
   }
 };
 
-// Called by lane 0 of each warp of a role (after __syncwarp): the last of the role's `nwarps` warps in this CTA forwards one
-// arrive to the LEADER's barrier (count 2: one per CTA of the pair).
-__device__ __forceinline__ void arrive_pair(uint32_t* cnt, uint32_t nwarps, uint64_t* leader_bar, uint32_t rank) {
-  __threadfence_block();
-  const uint32_t old = atomicAdd(cnt, 1u);
-  if (old == nwarps - 1) {
-    atomicExch(cnt, 0u);
-    __threadfence_block();
-    if (rank == 0) {
-      mbar_arrive(leader_bar);
-    } else {
-      mbar_arrive_remote(leader_bar, 0);   // default (.release.cta) semantics, as CUTLASS's ClusterBarrier::arrive(cta_id): the
-                                           // operand tiles were published to the async proxy by their writers (fence.proxy.async)
-    }
-  }
+// Called by lane 0 of each warp of a role (after __syncwarp): one arrive on the LEADER's barrier (count = the role's warps in
+// both CTAs).  Default (.release.cta) semantics, as CUTLASS's ClusterBarrier::arrive(cta_id): the operand tiles were published
+// to the async proxy by their writers (fence.proxy.async).  Counting arrivals in smem first (atomics + fences) cost each warp
+// several hundred cycles per tile.
+__device__ __forceinline__ void arrive_leader(uint64_t* leader_bar, uint32_t rank) {
+  if (rank == 0) mbar_arrive(leader_bar); else mbar_arrive_remote(leader_bar, 0);
 }
 
 __device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t (&r)[8]) {
@@ -136,15 +129,13 @@ resunit96_kernel(const __grid_constant__ CUtensorMap map_main, const __grid_cons
   uint64_t* w_full = bars;              // 1
   uint64_t* t_full = bars + 1;          // [4] local: X tile landed
   uint64_t* a_ready = bars + 5;         // [4] leader: pass 1 done in both CTAs
-  uint64_t* c7_done = bars + 9;         // [4] both: conv7 of the tile in this slot has completed
-  uint64_t* slot_free = bars + 13;      // [4] both: conv1 of the tile in this slot has completed (it read the slot's rows)
+  uint64_t* c7_done = bars + 9;         // [4] both: conv7 of the tile in this slot has completed (the slot may be refilled)
   uint64_t* acc1_full = bars + 17;      // [2] both
   uint64_t* c_ready = bars + 19;        // [2] leader: epilogue 1 done in both CTAs (conv1 operand written, acc1 drained)
   uint64_t* acc2_full = bars + 21;      // [2] both: conv1 has completed
   uint64_t* acc2_free = bars + 23;      // [2] leader: epilogue 2 has drained acc2 in both CTAs
   uint64_t* xbar = bars + 25;           // [8] local: an epilogue-2 warp's residual rows have landed
-  uint32_t* cnt = (uint32_t*)(bars + 33);   // cnt_a[4], cnt_c[2], cnt_f[2]
-  uint32_t* tmem_ptr = cnt + 8;
+  uint32_t* tmem_ptr = (uint32_t*)(bars + 33);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -163,9 +154,9 @@ resunit96_kernel(const __grid_constant__ CUtensorMap map_main, const __grid_cons
   }
   if (warp == 1 && lane == 0) {
     mbar_init(w_full, 1);
-    for (int i = 0; i < R_SLOTS; ++i) { mbar_init(&t_full[i], 1); mbar_init(&a_ready[i], 2); mbar_init(&c7_done[i], 1); mbar_init(&slot_free[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc1_full[i], 1); mbar_init(&c_ready[i], 2); mbar_init(&acc2_full[i], 1); mbar_init(&acc2_free[i], 2); }
-    for (int i = 0; i < 8; ++i) { cnt[i] = 0; mbar_init(&xbar[i], 1); }
+    for (int i = 0; i < R_SLOTS; ++i) { mbar_init(&t_full[i], 1); mbar_init(&a_ready[i], 2 * R_PW); mbar_init(&c7_done[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc1_full[i], 1); mbar_init(&c_ready[i], 2 * R_E1W); mbar_init(&acc2_full[i], 1); mbar_init(&acc2_free[i], 2 * R_E2W); }
+    for (int i = 0; i < R_E2W; ++i) mbar_init(&xbar[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -300,12 +291,14 @@ resunit96_kernel(const __grid_constant__ CUtensorMap map_main, const __grid_cons
       const bool live = w.live(p), first = w.first;
       w.next(p);                                                  // now describes tile j+1
       const bool copy_tail = live && j + 1 < q && w.live(p) && !w.first;
+      if (pw == 0) R_STAMP(1, j);
       mbar_wait_sleep(&t_full[slot], (uint32_t)((j / ns) & 1));
       if (pw == 0) R_STAMP(2, j);
       bool tail_ok = !(copy_tail && j >= ns - 1);          // else: conv7 of the next slot's previous tile may still read its halo rows
       if (live) {
-        for (int G = (first ? 0 : hb / 8) + par; G < ngroups; G += 4) {
-          const int G2 = G + 2;
+        constexpr int NP = R_PW / R_SUB;                            // warps per 32-channel block
+        for (int G = (first ? 0 : hb / 8) + par; G < ngroups; G += 2 * NP) {
+          const int G2 = G + NP;
           const bool two = G2 < ngroups;
           if (!tail_ok && (two ? G2 : G) * 8 >= R_BM) {            // first iteration that touches the tail (groups ascend)
             mbar_wait_sleep(&c7_done[nslot], (uint32_t)(((j - (ns - 1)) / ns) & 1));
@@ -345,7 +338,7 @@ resunit96_kernel(const __grid_constant__ CUtensorMap map_main, const __grid_cons
       fence_async_smem();
       __syncwarp();
       if (pw == 0) R_STAMP(3, j);
-      if (lane == 0) arrive_pair(&cnt[slot], R_PW, &a_ready[slot], rank);
+      if (lane == 0) arrive_leader(&a_ready[slot], rank);
     }
   } else if (warp >= R_CTRL + R_PW && warp < R_CTRL + R_PW + R_E1W) {
     // ================= epilogue-1 warps (two per TMEM lane quarter, 48 channels each): acc1 + b7 -> snake2 -> conv1's operand =================
@@ -395,7 +388,7 @@ resunit96_kernel(const __grid_constant__ CUtensorMap map_main, const __grid_cons
       tc_fence_before();
       __syncwarp();
       if (warp == R_CTRL + R_PW) R_STAMP(9, t);
-      if (lane == 0) arrive_pair(&cnt[R_SLOTS + (t & 1)], R_E1W, &c_ready[t & 1], rank);
+      if (lane == 0) arrive_leader(&c_ready[t & 1], rank);
       w.next(p);
     }
   } else if (warp >= R_CTRL + R_PW + R_E1W) {
@@ -440,7 +433,7 @@ resunit96_kernel(const __grid_constant__ CUtensorMap map_main, const __grid_cons
         } else {   // the accumulator has been read completely
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) arrive_pair(&cnt[R_SLOTS + 2 + (u & 1)], R_E2W, &acc2_free[u & 1], rank);
+          if (lane == 0) arrive_leader(&acc2_free[u & 1], rank);
         }
         if (row_ok) {
           const int col = col_base + 16 * m;
