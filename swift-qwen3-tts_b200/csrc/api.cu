@@ -840,7 +840,8 @@ int q3tts_debug_fused_unit(int32_t B, int32_t rows, int32_t C, int32_t dil, int3
       launch_conv_gemm_simt(p, g, op, op, s); }
     ConvGemmParams pf = base(A, W7, 7, dil, b7);
     pf.snake_ea = ea[0]; pf.snake_ib = ib[0];
-    FusedConv1 f{W1, b1, y[1], y[1], with_operand ? a[1] : nullptr, with_operand ? ea[1] : nullptr, with_operand ? ib[1] : nullptr};
+    // with_operand: 0 = stream only, 1 = stream + next operand, 2 = operand only (a block's last unit: the stream is not written)
+    FusedConv1 f{W1, b1, y[1], with_operand == 2 ? nullptr : y[1], with_operand ? a[1] : nullptr, with_operand ? ea[1] : nullptr, with_operand ? ib[1] : nullptr};
     if (!tc2_fuse_supported(pf, op)) return fail(Q3TTS_EINVAL, "shape not supported by the fused unit");
     CUDA_OK(launch_conv_gemm_tc2(pf, g, op, op, s, &f));
     CUDA_OK(cudaStreamSynchronize(s));
@@ -864,7 +865,7 @@ int q3tts_debug_fused_unit(int32_t B, int32_t rows, int32_t C, int32_t dil, int3
           }
       return worst;
     };
-    if (max_diff_y) *max_diff_y = max_diff(y[0], y[1]);
+    if (max_diff_y) *max_diff_y = max_diff(with_operand == 2 ? X : y[0], y[1]);   // operand only: the stream buffer must be untouched
     if (max_diff_a) *max_diff_a = with_operand ? max_diff(a[0], a[1]) : 0.f;
     if (iters > 0 && ms_out) {
       cudaEvent_t e0, e1;

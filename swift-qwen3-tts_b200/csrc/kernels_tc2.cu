@@ -837,7 +837,7 @@ cudaError_t launch_conv_gemm_tc2(const ConvGemmParams& p, const BatchGeom& g, in
   q.tiles_per_utt = (slot_rows + T2_BM - 1) / T2_BM;
   q.n_tiles = p.N / BN;
   q.m_tiles_total = g.B * q.tiles_per_utt;
-  int cs = (cs_env == 2 && BN % 16 == 0 && q.m_tiles_total >= 2) ? 2 : 1;
+  int cs = (cs_env == 2 && BN % 16 == 0 && (q.m_tiles_total >= 2 || fuse)) ? 2 : 1;   // the fused unit always runs as a pair
   const bool pair = pair_env && cs == 2;
   if (fuse && !pair) return cudaErrorNotSupported;
   q.cs = cs;

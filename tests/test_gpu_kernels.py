@@ -43,3 +43,19 @@ def test_fused_residual_unit_matches_composed_unit(dil, out_snake):
 def test_fused_residual_unit_bf16():
     _, d = q.debug_resunit(2, 5000, 3, 0, q.PREC_BF16, 0)
     assert d <= 0.13          # bf16: 8 mantissa bits, |x| <= 8
+
+
+@pytest.mark.parametrize("C", [192, 128, 64])
+@pytest.mark.parametrize("dil", [1, 9])
+@pytest.mark.parametrize("mode", [0, 1, 2])     # stream only / stream + next operand / operand only (a block's last unit)
+def test_gemm_fused_conv7_conv1_unit_matches_composed_unit(C, dil, mode):
+    # conv7 -> SnakeBeta -> (operand in tensor memory) -> conv1 -> + residual in ONE tcgen05 kernel vs the two CUDA-core GEMMs;
+    # ragged lengths (rows - 211 b), partial last tiles, pair tiles that straddle utterances
+    for B, rows in ((3, 3000), (1, 77), (4, 640)):
+        _, dy, da = q.debug_fused_unit(B, rows, C, dil, mode, q.PREC_FP16, 0)
+        assert dy <= (0 if mode == 2 else 2 * ULP) and da <= 3 * ULP, (C, dil, mode, B, rows, dy, da)
+
+
+def test_gemm_fused_unit_bf16():
+    _, dy, da = q.debug_fused_unit(2, 5000, 192, 3, 1, q.PREC_BF16, 0)
+    assert dy <= 0.07 and da <= 0.13
