@@ -64,7 +64,6 @@ struct Res96Params {
   int out_snake;                  // write snake3(X') instead of X' (last unit of the block)
   const void* x_in; long long x_bstride;   // residual rows (elements)
   long long* dbg;                 // optional [16 events][32 tiles] clock64 stamps of CTA 0 (pipeline debugging)
-  int skip;                       // experiments (wrong results): 1 = no residual loads, 2 = no output stores
 };
 
 // Position of a CTA in its strip of valid tiles (warp-uniform).
@@ -405,7 +404,7 @@ resunit96_kernel(const __grid_constant__ CUtensorMap map_main, const __grid_cons
     Walker w;
     w.init(p, g0);
     for (int u = 0; u < q; ++u) {
-      const bool row_ok = w.live(p) && !(p.skip & 4);               // warp-uniform
+      const bool row_ok = w.live(p);                                // warp-uniform
       const int row0 = w.t0 + quarter * 32;
       if (row_ok && lane == 0) {
         tma_store_wait_read0();                                      // my previous store has drained the buffer
@@ -539,7 +538,6 @@ cudaError_t launch_resunit96(const ResUnitParams& p, const BatchGeom& g, int op_
   q.out_snake = p.ea3 != nullptr;
   q.x_in = p.x_in; q.x_bstride = (long long)slot_rows * R_C;
   q.dbg = (long long*)p.dbg;
-  { const char* e = getenv("Q3TTS_RES_SKIP"); q.skip = e ? atoi(e) : 0; }
   int sms = 0, dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

@@ -69,7 +69,7 @@ struct Tc2Params {
   // The 1x1 conv runs as two N halves through ONE extra accumulator of BN/2 columns (TMEM: 2 x BN + BN/2 <= 512), issued
   // in the middle of the NEXT tile's conv7, so that neither epilogue ever holds up the tensor pipe.
   int a_tmem;                                    // conv1's operand lives in TENSOR MEMORY, packed over the drained conv7 accumulator
-  int fuse, ncb2, acc2_col, c1_after0, c1_after1, dbg;   // c1_after*: 64-channel block of the next conv7 after which half 0 / 1 of conv1 is issued
+  int fuse, ncb2, acc2_col, c1_after1;           // c1_after1: 64-channel block of the next conv7 after which half 1 of conv1 is issued (half 0: after block 0)
   uint32_t idesc2;                               // N = BN/2
   uint32_t w1_blk_bytes;                         // one (N half, 64-channel block) of this CTA's part of W1: (BN/4) rows x 128 B
   const float* bias2; const float* ea2; const float* ib2;
@@ -390,7 +390,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
           }
           if (++sa == T2_NA) { sa = 0; pa ^= 1; }
           if (kBlockEpi && p.fuse && n_done > 0) {
-            if (cb == p.c1_after0) issue_conv1(0);
+            if (cb == 0) issue_conv1(0);
             if (cb == p.c1_after1) issue_conv1(1);
           }
         }
@@ -420,7 +420,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     uint32_t xpar = 0;
     auto epilogue2 = [&](int h) {
       const int n = h * (p.BN / 2) + grp * 32, trow0 = pv_t0 + quarter * 32;
-      const bool ok = pv_mine && grp < hch && !(p.dbg & 2);              // warp-uniform
+      const bool ok = pv_mine && grp < hch;                              // warp-uniform
       if (ok && lane == 0) {
         tma_store_wait_read0();                                          // my previous store has drained the buffer
         mbar_expect_tx(&xbar[ew], 2048u);
@@ -483,7 +483,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
           tc_wait_ld();
           const int n = (2 * grp + c2) * 32;
           const uint32_t sb = cst_u32 + 4u * (uint32_t)n, se = sb + 4u * (uint32_t)p.N, si = se + 4u * (uint32_t)p.N;
-          epi_snake_pack<T16>(r, sb, se, si, !(p.dbg & 1), pk);
+          epi_snake_pack<T16>(r, sb, se, si, true, pk);
           tc_st16(t0a + (uint32_t)(c2 * 16), pk);
         }
         tc_wait_st();
@@ -496,8 +496,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         const uint32_t sb = cst_u32 + 4u * (uint32_t)n, se = sb + 4u * (uint32_t)p.N, si = se + 4u * (uint32_t)p.N;
         const uint4 none[4] = {};
         uint8_t* row_a = c_row + (size_t)(ch >> 1) * 16384;
-        if (p.dbg & 1) epi_block_chunk<T16, false, true, false, true>(r, nullptr, nullptr, nullptr, sb, se, si, none, row_a, nullptr, (uint32_t)((ch & 1) * 4), sw128, true);
-        else epi_block_chunk<T16, false, false, true, true>(r, nullptr, nullptr, nullptr, sb, se, si, none, nullptr, row_a, (uint32_t)((ch & 1) * 4), sw128, true);
+        epi_block_chunk<T16, false, false, true, true>(r, nullptr, nullptr, nullptr, sb, se, si, none, nullptr, row_a, (uint32_t)((ch & 1) * 4), sw128, true);
       }
       fence_async_smem();
       tc_fence_before();
@@ -896,8 +895,7 @@ cudaError_t launch_conv_gemm_tc2(const ConvGemmParams& p, const BatchGeom& g, in
   q.cst_staged = epi_block && (cst_env || fuse) && p.N <= T2_CST_MAX_N;
   CUtensorMap map_w2 = map_w;
   if (fuse) {
-    static const int after0_env = env_int("Q3TTS_FUSE_AFTER0", 0), after1_env = env_int("Q3TTS_FUSE_AFTER1", 1), dbg_env = env_int("Q3TTS_FUSE_DBG", 0);
-    q.c1_after0 = std::min(after0_env, q.ncb - 1); q.c1_after1 = std::max(q.c1_after0, std::min(after1_env, q.ncb - 1)); q.dbg = dbg_env;
+    q.c1_after1 = std::min(1, q.ncb - 1);
     static const int ts_env = env_int("Q3TTS_FUSE_TS", 1);
     q.a_tmem = ts_env != 0;
     q.fuse = 1; q.ncb2 = p.N / T2_BK; q.w1_blk_bytes = (uint32_t)(BN / 4) * 128u; q.acc2_col = 2 * BN;
