@@ -3,7 +3,8 @@ import csv, subprocess, sys
 rep = sys.argv[1]; top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
 raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
-hdr = rows[1]; data = rows[2:]
+hdr = rows[1]; data = [r for r in rows[2:] if len(r) == len(hdr) and r != hdr]
+if len(sys.argv) > 5: data = data[:len(data) // int(sys.argv[5])]   # several launches in one report: keep the first
 isamp = hdr.index("# Samples"); isrc = hdr.index("Source"); iex = hdr.index("Instructions Executed")
 sc = [i for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
 print("total samples", sum(int(d[isamp]) for d in data), "instructions", len(data))
