@@ -119,6 +119,16 @@ int q3tts_decode(q3tts_model* m, const int32_t* codes, int32_t B, int32_t T, int
 int q3tts_decode_varlen(q3tts_model* m, const int32_t* codes_packed, const int64_t* frame_offsets,
                         int32_t n_utterances, float* pcm_out, int32_t* lengths_out);
 
+/* ---- decode straight to 16-bit PCM ------------------------------------------------------------
+ * Same as q3tts_decode / q3tts_decode_varlen, but the last kernel of the chain writes
+ * Int16(clamp(x,-1,1) * 32767) -- the conversion the reference's WAV writer applies to every
+ * sample on the CPU (Sources/Qwen3TTSDemo/main.swift:158-160) -- so the device-to-host copy and the
+ * PCM write traffic halve.  Bit-identical to q3tts_pcm_to_int16 of the float output.            */
+int q3tts_decode_int16(q3tts_model* m, const int32_t* codes, int32_t B, int32_t T, int32_t layout,
+                       int16_t* pcm_out, int32_t* lengths_out);
+int q3tts_decode_varlen_int16(q3tts_model* m, const int32_t* codes_packed, const int64_t* frame_offsets,
+                              int32_t n_utterances, int16_t* pcm_out, int32_t* lengths_out);
+
 /* ---- decode: device buffers (codes and PCM already in HBM), asynchronous on `stream` ---------
  * Same semantics as q3tts_decode; `stream` is a cudaStream_t (NULL = legacy default stream).
  * Returns after enqueueing; errors detected on device (bad code ids) surface at

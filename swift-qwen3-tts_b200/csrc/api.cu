@@ -246,8 +246,15 @@ int64_t q3tts_output_samples(const q3tts_model* h, int64_t frames) {
   return frames * h->m->cfg.total_upsample;
 }
 
+// RAII: the tail of this call writes 16-bit PCM (the model mutex is held for the whole call)
+struct PcmFormat {
+  Model& m;
+  PcmFormat(Model& mm, bool i16) : m(mm) { m.pcm_i16 = i16; }
+  ~PcmFormat() { m.pcm_i16 = false; }
+};
+
 static int decode_common(q3tts_model* h, const int32_t* codes, int32_t B, int32_t T, int32_t layout, float* pcm,
-                         int32_t* lengths, bool device_ptrs, cudaStream_t user_stream) {
+                         int32_t* lengths, bool device_ptrs, cudaStream_t user_stream, bool i16 = false) {
   return guarded([&]() {
     if (!h) return fail(Q3TTS_EINVAL, "model is NULL");
     if (B < 0 || T < 0) return fail(Q3TTS_EINVAL, "negative B or T");
@@ -257,6 +264,7 @@ static int decode_common(q3tts_model* h, const int32_t* codes, int32_t B, int32_
     Model& m = *h->m;
     std::lock_guard<std::mutex> lock(m.mu);
     CUDA_OK(cudaSetDevice(m.device));
+    PcmFormat fmt(m, i16);
     const int Q = m.cfg.num_quantizers;
     const int64_t up = m.cfg.total_upsample;
     const size_t n_codes = (size_t)B * T * Q, n_pcm = (size_t)B * T * up;
@@ -278,7 +286,7 @@ static int decode_common(q3tts_model* h, const int32_t* codes, int32_t B, int32_
     const int64_t sq = layout == Q3TTS_CODES_BQT ? T : 1, st = layout == Q3TTS_CODES_BQT ? 1 : Q;
     decode_core(m, d_codes, utts, sq, st, d_pcm, d_len, s);
     if (!device_ptrs) {
-      CUDA_OK(cudaMemcpyAsync(pcm, m.d_pcm, n_pcm * 4, cudaMemcpyDeviceToHost, s));
+      CUDA_OK(cudaMemcpyAsync(pcm, m.d_pcm, n_pcm * (i16 ? 2 : 4), cudaMemcpyDeviceToHost, s));
       if (lengths) CUDA_OK(cudaMemcpyAsync(lengths, m.d_lengths, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
       check_device_errors(m, s);
     }
@@ -289,6 +297,11 @@ static int decode_common(q3tts_model* h, const int32_t* codes, int32_t B, int32_
 int q3tts_decode(q3tts_model* h, const int32_t* codes, int32_t B, int32_t T, int32_t layout, float* pcm_out,
                  int32_t* lengths_out) {
   return decode_common(h, codes, B, T, layout, pcm_out, lengths_out, false, nullptr);
+}
+
+int q3tts_decode_int16(q3tts_model* h, const int32_t* codes, int32_t B, int32_t T, int32_t layout, int16_t* pcm_out,
+                       int32_t* lengths_out) {
+  return decode_common(h, codes, B, T, layout, (float*)pcm_out, lengths_out, false, nullptr, true);
 }
 
 int q3tts_decode_device(q3tts_model* h, const int32_t* d_codes, int32_t B, int32_t T, int32_t layout, float* d_pcm_out,
@@ -307,8 +320,8 @@ int q3tts_sync(q3tts_model* h, void* stream) {
   });
 }
 
-int q3tts_decode_varlen(q3tts_model* h, const int32_t* codes_packed, const int64_t* frame_offsets, int32_t n,
-                        float* pcm_out, int32_t* lengths_out) {
+static int decode_varlen_common(q3tts_model* h, const int32_t* codes_packed, const int64_t* frame_offsets, int32_t n,
+                                void* pcm_out, int32_t* lengths_out, bool i16) {
   return guarded([&]() {
     if (!h) return fail(Q3TTS_EINVAL, "model is NULL");
     if (n < 0) return fail(Q3TTS_EINVAL, "negative utterance count");
@@ -322,6 +335,7 @@ int q3tts_decode_varlen(q3tts_model* h, const int32_t* codes_packed, const int64
     Model& m = *h->m;
     std::lock_guard<std::mutex> lock(m.mu);
     CUDA_OK(cudaSetDevice(m.device));
+    PcmFormat fmt(m, i16);
     if (total == 0) {
       if (lengths_out) std::memset(lengths_out, 0, (size_t)n * 4);
       return (int)Q3TTS_OK;
@@ -338,11 +352,21 @@ int q3tts_decode_varlen(q3tts_model* h, const int32_t* codes_packed, const int64
     for (int i = 0; i < n; ++i)
       utts[(size_t)i] = Utt{frame_offsets[i] * Q, frame_offsets[i] * up, (int)(frame_offsets[i + 1] - frame_offsets[i]), i};
     decode_core(m, m.d_codes, utts, 1, Q, m.d_pcm, lengths_out ? m.d_lengths : nullptr, s);
-    CUDA_OK(cudaMemcpyAsync(pcm_out, m.d_pcm, (size_t)total * up * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_OK(cudaMemcpyAsync(pcm_out, m.d_pcm, (size_t)total * up * (i16 ? 2 : 4), cudaMemcpyDeviceToHost, s));
     if (lengths_out) CUDA_OK(cudaMemcpyAsync(lengths_out, m.d_lengths, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
     check_device_errors(m, s);
     return (int)Q3TTS_OK;
   });
+}
+
+int q3tts_decode_varlen(q3tts_model* h, const int32_t* codes_packed, const int64_t* frame_offsets, int32_t n,
+                        float* pcm_out, int32_t* lengths_out) {
+  return decode_varlen_common(h, codes_packed, frame_offsets, n, pcm_out, lengths_out, false);
+}
+
+int q3tts_decode_varlen_int16(q3tts_model* h, const int32_t* codes_packed, const int64_t* frame_offsets, int32_t n,
+                              int16_t* pcm_out, int32_t* lengths_out) {
+  return decode_varlen_common(h, codes_packed, frame_offsets, n, pcm_out, lengths_out, true);
 }
 
 // ---- taps -------------------------------------------------------------------------------------------

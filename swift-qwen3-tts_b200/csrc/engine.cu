@@ -620,7 +620,7 @@ void run_microbatch(Model& m, const int32_t* d_codes, const int64_t* d_code_base
     m.arena_cap = need;
   }
   Plan P = make_plan(m, m.arena, B, Tmax);
-  Ctx x{m, BatchGeom{B, Tmax, d_len, (long long)valid_frames}, s, valid_frames};
+  Ctx x{m, BatchGeom{B, Tmax, d_len, (long long)valid_frames, nullptr, m.pcm_i16 ? 1 : 0}, s, valid_frames};
   const int op = m.op_dtype;
   const int64_t R = (int64_t)B * Tmax;
   const int half = c.codebook_dim / 2;

@@ -87,6 +87,7 @@ struct Model {
   uint64_t default_workspace = 24ull << 30;   // activation budget when q3tts_options.workspace_bytes == 0 (set at load)
   int32_t* d_codes = nullptr; size_t d_codes_cap = 0;
   float* d_pcm = nullptr;     size_t d_pcm_cap = 0;
+  bool pcm_i16 = false;       // this call's tail writes int16 PCM into the (float-sized) output buffer
   int32_t* d_lengths = nullptr; size_t d_lengths_cap = 0;
   char* d_meta = nullptr;     size_t d_meta_cap = 0;     // len_frames / code_base / pcm_base per micro-batch
   char* h_meta = nullptr;     size_t h_meta_cap = 0;     // pinned staging

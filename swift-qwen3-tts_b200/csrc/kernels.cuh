@@ -21,7 +21,17 @@ struct BatchGeom {
   long long valid_frames;  // host copy of sum(len_frames) (work-list sizing of the strip-walking kernels)
   const int* row_begin;    // [B] device or null: first valid row of a slot (attention only: streaming keeps its KV history
                            //   right-aligned in front of the new frames, so a young stream's slot starts late)
+  int pcm_i16 = 0;         // the tail writes 16-bit PCM (Int16(clamp(x,-1,1) * 32767), main.swift:158-160) instead of float
 };
+
+#ifdef __CUDACC__
+// Final sample store of the tail kernels: clip (ST.swift:781), then float or the demo's WAV conversion (truncation toward zero).
+__device__ __forceinline__ void store_pcm(float* pcm, long long i, float v, int i16) {
+  v = fminf(fmaxf(v, -1.0f), 1.0f);
+  if (i16) ((short*)pcm)[i] = (short)__float2int_rz(v * 32767.0f);
+  else pcm[i] = v;
+}
+#endif
 
 // Generic "multi-tap GEMM": out[b,t,n] = epi( sum_{j<taps} sum_c A[b, t-(taps-1-j)*dil, c] * W[j,n,c] ).
 //  - plain conv:        W[j,n,c] = w_mlx[n,j,c]

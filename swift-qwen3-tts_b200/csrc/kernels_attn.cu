@@ -230,7 +230,7 @@ tail_mma_kernel(const T16* __restrict__ a, int64_t a_bstride, const float* __res
 #pragma unroll
     for (int j = 0; j < 7; ++j) v += P[tid + j][j];      // input row t-6+j sits at tile row (t - t0) + j
     if (tap) tap[(int64_t)b * tap_bstride + t] = v;
-    pcm[pcm_base[b] + t] = fminf(fmaxf(v, -1.0f), 1.0f);
+    store_pcm(pcm, pcm_base[b] + t, v, g.pcm_i16);
   }
 }
 }  // namespace

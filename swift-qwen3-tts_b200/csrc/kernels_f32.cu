@@ -505,7 +505,7 @@ tail_kernel(const TI* a, int64_t a_bstride, const float* w, float bias, int C, f
   if (lane == 0) {
     const float v = acc + bias;
     if (tap) tap[(int64_t)b * tap_bstride + t] = v;
-    pcm[pcm_base[b] + t] = fminf(fmaxf(v, -1.0f), 1.0f);
+    store_pcm(pcm, pcm_base[b] + t, v, g.pcm_i16);
   }
 }
 
@@ -559,7 +559,7 @@ tail16_kernel(const T16* a, int64_t a_bstride, float bias, float* pcm, const int
   if (t < valid) {
     const float v = acc + bias;
     if (tap) tap[(int64_t)b * tap_bstride + t] = v;
-    pcm[pcm_base[b] + t] = fminf(fmaxf(v, -1.0f), 1.0f);
+    store_pcm(pcm, pcm_base[b] + t, v, g.pcm_i16);
   }
 }
 

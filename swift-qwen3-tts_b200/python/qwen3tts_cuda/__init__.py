@@ -103,6 +103,8 @@ def lib() -> C.CDLL:
         "q3tts_output_samples": (i64, [vp, i64]),
         "q3tts_decode": (C.c_int, [vp, vp, i32, i32, i32, vp, vp]),
         "q3tts_decode_varlen": (C.c_int, [vp, vp, vp, i32, vp, vp]),
+        "q3tts_decode_int16": (C.c_int, [vp, vp, i32, i32, i32, vp, vp]),
+        "q3tts_decode_varlen_int16": (C.c_int, [vp, vp, vp, i32, vp, vp]),
         "q3tts_decode_device": (C.c_int, [vp, vp, i32, i32, i32, vp, vp, vp]),
         "q3tts_sync": (C.c_int, [vp, vp]),
         "q3tts_set_taps": (C.c_int, [vp, i32]),
@@ -298,8 +300,19 @@ class Qwen3TTSSpeechTokenizer:
         _check(lib().q3tts_decode(self._h, ac.ctypes.data, B, T, CODES_BTQ, audio.ctypes.data, lengths.ctypes.data))
         return audio, lengths
 
-    def decode_varlen(self, utterances: Sequence[np.ndarray]):
-        """List of [T_i,16] code arrays -> (list of [T_i*1920] PCM arrays, lengths [N])."""
+    def decode_int16(self, audio_codes: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+        """audio_codes [B,T,16] -> (audio [B, T*1920] int16 = Int16(clamp(x) * 32767), audio_lengths [B]); main.swift:158-160."""
+        ac = np.ascontiguousarray(audio_codes, dtype=np.int32)
+        if ac.ndim != 3 or ac.shape[2] != self.config.num_quantizers:
+            raise AudioDecodingFailed(1, f"audio_codes must be [B,T,{self.config.num_quantizers}], got {ac.shape}")
+        B, T, _ = ac.shape
+        audio = np.empty((B, T * self.config.total_upsample), dtype=np.int16)
+        lengths = np.zeros(B, dtype=np.int32)
+        _check(lib().q3tts_decode_int16(self._h, ac.ctypes.data, B, T, CODES_BTQ, audio.ctypes.data, lengths.ctypes.data))
+        return audio, lengths
+
+    def decode_varlen(self, utterances: Sequence[np.ndarray], int16: bool = False):
+        """List of [T_i,16] code arrays -> (list of [T_i*1920] PCM arrays (float32, or int16 when `int16`), lengths [N])."""
         n = len(utterances)
         offs = np.zeros(n + 1, dtype=np.int64)
         for i, u in enumerate(utterances):
@@ -312,10 +325,10 @@ class Qwen3TTSSpeechTokenizer:
                   if total else np.zeros((0, self.config.num_quantizers), np.int32))
         packed = np.ascontiguousarray(packed, dtype=np.int32)
         up = self.config.total_upsample
-        pcm = np.empty(total * up, dtype=np.float32)
+        pcm = np.empty(total * up, dtype=np.int16 if int16 else np.float32)
         lengths = np.zeros(n, dtype=np.int32)
-        _check(lib().q3tts_decode_varlen(self._h, packed.ctypes.data, offs.ctypes.data, n, pcm.ctypes.data,
-                                         lengths.ctypes.data))
+        fn = lib().q3tts_decode_varlen_int16 if int16 else lib().q3tts_decode_varlen
+        _check(fn(self._h, packed.ctypes.data, offs.ctypes.data, n, pcm.ctypes.data, lengths.ctypes.data))
         return [pcm[offs[i] * up: offs[i + 1] * up] for i in range(n)], lengths
 
     # ---- chunked streaming (Q3TTS_ATTN_CAUSAL_SW; the reference only streams token ids, Qwen3+Streaming.swift) ----

@@ -130,6 +130,24 @@ public final class Qwen3TTSSpeechTokenizer {
         return (FloatTensor(shape: [b, t * decoder.totalUpsample], data: pcm), lengths)
     }
 
+    /// Decode straight to the 16-bit samples the demo's WAV writer produces (`Int16(clamped * 32767.0)`,
+    /// Sources/Qwen3TTSDemo/main.swift:158-160): the conversion runs in the last CUDA kernel.
+    public func decodeInt16(_ audioCodes: Int32Tensor) throws -> (audio: [Int16], audioLengths: [Int32]) {
+        precondition(audioCodes.shape.count == 3 && audioCodes.shape[2] == decoder.numQuantizers)
+        let (b, t) = (audioCodes.shape[0], audioCodes.shape[1])
+        var pcm = [Int16](repeating: 0, count: b * t * decoder.totalUpsample)
+        var lengths = [Int32](repeating: 0, count: b)
+        try audioCodes.data.withUnsafeBufferPointer { c in
+            try pcm.withUnsafeMutableBufferPointer { p in
+                try lengths.withUnsafeMutableBufferPointer { l in
+                    try check(q3tts_decode_int16(handle, c.baseAddress, Int32(b), Int32(t), Int32(Q3TTS_CODES_BTQ.rawValue),
+                                                 p.baseAddress, l.baseAddress))
+                }
+            }
+        }
+        return (pcm, lengths)
+    }
+
     /// Batch of utterances of different lengths, each [T_i, 16]; every result equals its own B=1 decode.
     public func decodeBatch(_ utterances: [Int32Tensor]) throws -> (audio: [[Float]], audioLengths: [Int32]) {
         var offsets = [Int64](repeating: 0, count: utterances.count + 1)

@@ -130,6 +130,36 @@ def test_varlen_equals_per_utterance_decode(tiny_tok, tiny_oracle):
         assert np.abs(pcms[i] - single[0]).max() <= 1e-6      # padding never leaks into valid frames (H5)
 
 
+def test_int16_decode_equals_host_conversion_of_float_decode(tiny_tok, tiny_oracle):
+    # row N1 of SURVEY 8(f): Int16(clamp(x,-1,1) * 32767) (main.swift:158-160) written by the tail kernel itself;
+    # bit-exact against the C ABI's host conversion and against numpy's truncation of the oracle-checked float PCM
+    cfg, _, _ = tiny_oracle
+    codes = np.ascontiguousarray(np.transpose(_nct_codes(cfg, 3, 9, 77), (0, 2, 1)))        # [B,T,16]
+    audio, lengths = tiny_tok.decode(codes)
+    audio16, lengths16 = tiny_tok.decode_int16(codes)
+    assert audio16.dtype == np.int16 and audio16.shape == audio.shape
+    assert np.array_equal(lengths, lengths16)
+    assert np.array_equal(audio16.ravel(), q.pcm_to_int16(audio.ravel()))
+    assert np.array_equal(audio16, np.trunc(np.clip(audio, -1.0, 1.0) * np.float32(32767.0)).astype(np.int16))
+    utts = [codes[0, :4], codes[1, :0], codes[2]]
+    pcms, _ = tiny_tok.decode_varlen(utts)
+    pcms16, _ = tiny_tok.decode_varlen(utts, int16=True)
+    for f, i in zip(pcms, pcms16):
+        assert np.array_equal(i, q.pcm_to_int16(f))
+    again, _ = tiny_tok.decode(codes)                       # the float path is untouched by the int16 call before it
+    assert np.array_equal(again, audio)
+
+
+def test_int16_decode_16bit_engine(full_dir, full_oracle):
+    cfg, _, _ = full_oracle
+    tok = q.Qwen3TTSSpeechTokenizer(full_dir, precision=q.PREC_FP16)
+    codes = np.ascontiguousarray(np.transpose(_nct_codes(cfg, 2, 11, 5), (0, 2, 1)))
+    audio, _ = tok.decode(codes)
+    audio16, _ = tok.decode_int16(codes)
+    assert np.array_equal(audio16.ravel(), q.pcm_to_int16(audio.ravel()))
+    tok.close()
+
+
 def test_microbatching_is_invisible(tiny_dir, tiny_oracle):
     cfg, _, _ = tiny_oracle
     codes = _nct_codes(cfg, 5, 12, 31)
