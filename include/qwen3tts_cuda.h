@@ -129,6 +129,26 @@ int q3tts_decode_int16(q3tts_model* m, const int32_t* codes, int32_t B, int32_t 
 int q3tts_decode_varlen_int16(q3tts_model* m, const int32_t* codes_packed, const int64_t* frame_offsets,
                               int32_t n_utterances, int16_t* pcm_out, int32_t* lengths_out);
 
+/* ---- codec-embedding sum for the Talker's next-step input -----------------
+ * Replaces  codecEmbed = talker.getInputEmbeddings()(code0); for i in 1..<G { codecEmbed = codecEmbed +
+ * codePredictor.codecEmbedding[i-1](code_i) }  (Qwen3.swift:720-728, 927-935, 1157-1162 per generated frame;
+ * 485-491 for the whole reference-audio prefix of voice cloning), batched over frames.
+ * q3tts_codec_embedder_load reads talker.model.codec_embedding.weight [3072,H] (Talker.swift:495, 510) and
+ * talker.code_predictor.model.codec_embedding.{i}.weight [2048,H] (CodePredictor.swift:206, 217-219) from
+ * the .safetensors files of <model_dir> and keeps them in their on-disk dtype.  codes: int32 [n_frames, G] frame-major
+ * (the rows `generate` stacks, Q3.swift:736-741).  out: [n_frames, H] in the tables' dtype; every add is rounded
+ * to that dtype, left to right, exactly as the reference's sequence of MLX adds.
+ * A code id outside its table is Q3TTS_EINVAL (host variant; the reference leaves it unchecked).  */
+typedef struct q3tts_codec_embedder q3tts_codec_embedder;
+int q3tts_codec_embedder_load(const char* model_dir, int32_t device, q3tts_codec_embedder** out);
+void q3tts_codec_embedder_free(q3tts_codec_embedder* e);
+/* precision: Q3TTS_PREC_* of the tables; vocab (may be NULL): int32 [groups] table sizes */
+int q3tts_codec_embedder_info(const q3tts_codec_embedder* e, int32_t* hidden, int32_t* groups, int32_t* precision,
+                              int32_t* vocab);
+int q3tts_codec_embed_sum(q3tts_codec_embedder* e, const int32_t* codes, int64_t n_frames, void* out);
+int q3tts_codec_embed_sum_device(q3tts_codec_embedder* e, const int32_t* d_codes, int64_t n_frames, void* d_out,
+                                 void* stream);
+
 /* ---- decode: device buffers (codes and PCM already in HBM), asynchronous on `stream` ---------
  * Same semantics as q3tts_decode; `stream` is a cudaStream_t (NULL = legacy default stream).
  * Returns after enqueueing; errors detected on device (bad code ids) surface at

@@ -912,6 +912,124 @@ int q3tts_debug_fused_unit(int32_t B, int32_t rows, int32_t C, int32_t dil, int3
   });
 }
 
+// ---- codec-embedding sum --------------------------------------------------------------------------
+struct q3tts_codec_embedder {
+  int device = 0, dtype = DT_BF16, groups = 0;
+  int64_t hidden = 0;
+  std::vector<int> vocab;
+  std::vector<void*> d_tables;
+  int* d_err = nullptr;
+  int32_t* d_codes = nullptr; size_t d_codes_cap = 0;
+  void* d_out = nullptr;      size_t d_out_cap = 0;
+  cudaStream_t stream = nullptr;
+  std::mutex mu;
+  ~q3tts_codec_embedder() {
+    cudaSetDevice(device);
+    for (void* t : d_tables) cudaFree(t);
+    if (d_err) cudaFree(d_err);
+    if (d_codes) cudaFree(d_codes);
+    if (d_out) cudaFree(d_out);
+    if (stream) cudaStreamDestroy(stream);
+  }
+};
+
+int q3tts_codec_embedder_load(const char* model_dir, int32_t device, q3tts_codec_embedder** out) {
+  return guarded([&]() {
+    if (!model_dir || !out) return fail(Q3TTS_EINVAL, "NULL argument");
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(Q3TTS_ECUDA, "no CUDA device (this library has no CPU path)");
+    CodecEmbeddingTables host;
+    load_codec_embeddings(model_dir, &host);
+    if ((int)host.tables.size() > kMaxCodeGroups) return fail(Q3TTS_EFORMAT, "too many code groups");
+    if (host.hidden % 8) return fail(Q3TTS_EFORMAT, "hidden size must be a multiple of 8");
+    std::unique_ptr<q3tts_codec_embedder> e(new q3tts_codec_embedder());
+    e->device = device < 0 ? 0 : device;
+    if (e->device >= ndev) return fail(Q3TTS_EINVAL, "device index out of range");
+    CUDA_OK(cudaSetDevice(e->device));
+    e->dtype = host.dtype == "F32" ? DT_F32 : (host.dtype == "F16" ? DT_F16 : DT_BF16);
+    e->hidden = host.hidden;
+    e->groups = (int)host.tables.size();
+    CUDA_OK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    CUDA_OK(cudaMalloc(&e->d_err, 4));
+    CUDA_OK(cudaMemsetAsync(e->d_err, 0, 4, e->stream));
+    for (auto& t : host.tables) {
+      const int64_t n = t.numel();
+      float* d32 = nullptr;
+      CUDA_OK(cudaMalloc(&d32, (size_t)n * 4));
+      CUDA_OK(cudaMemcpyAsync(d32, t.data.data(), (size_t)n * 4, cudaMemcpyHostToDevice, e->stream));
+      void* d = d32;
+      if (e->dtype != DT_F32) {   // the fp32 copies are exact images of the 16-bit values on disk: converting back is lossless
+        CUDA_OK(cudaMalloc(&d, (size_t)n * 2));
+        launch_convert(d32, d, e->dtype, n, e->stream);
+        CUDA_OK(cudaStreamSynchronize(e->stream));
+        cudaFree(d32);
+      }
+      e->d_tables.push_back(d);
+      e->vocab.push_back((int)t.shape[0]);
+    }
+    CUDA_OK(cudaStreamSynchronize(e->stream));
+    *out = e.release();
+    return (int)Q3TTS_OK;
+  });
+}
+
+void q3tts_codec_embedder_free(q3tts_codec_embedder* e) { delete e; }
+
+int q3tts_codec_embedder_info(const q3tts_codec_embedder* e, int32_t* hidden, int32_t* groups, int32_t* precision, int32_t* vocab) {
+  if (!e) return fail(Q3TTS_EINVAL, "embedder is NULL");
+  if (hidden) *hidden = (int32_t)e->hidden;
+  if (groups) *groups = e->groups;
+  if (precision) *precision = e->dtype == DT_F32 ? Q3TTS_PREC_FP32 : (e->dtype == DT_F16 ? Q3TTS_PREC_FP16 : Q3TTS_PREC_BF16);
+  if (vocab) for (int i = 0; i < e->groups; ++i) vocab[i] = e->vocab[(size_t)i];
+  return Q3TTS_OK;
+}
+
+static int codec_embed_common(q3tts_codec_embedder* e, const int32_t* codes, int64_t n, void* out, bool device_ptrs, cudaStream_t user) {
+  return guarded([&]() {
+    if (!e) return fail(Q3TTS_EINVAL, "embedder is NULL");
+    if (n < 0) return fail(Q3TTS_EINVAL, "negative frame count");
+    if (n == 0) return (int)Q3TTS_OK;
+    if (!codes || !out) return fail(Q3TTS_EINVAL, "NULL buffer");
+    std::lock_guard<std::mutex> lock(e->mu);
+    CUDA_OK(cudaSetDevice(e->device));
+    cudaStream_t s = device_ptrs ? user : e->stream;
+    const size_t es = e->dtype == DT_F32 ? 4 : 2, out_bytes = (size_t)n * e->hidden * es, code_bytes = (size_t)n * e->groups * 4;
+    CodecEmbedParams p{};
+    for (int g = 0; g < e->groups; ++g) { p.tables[g] = e->d_tables[(size_t)g]; p.vocab[g] = e->vocab[(size_t)g]; }
+    p.groups = e->groups; p.H = (int)e->hidden; p.dtype = e->dtype; p.n = n; p.err_flag = e->d_err;
+    if (device_ptrs) {
+      p.codes = codes; p.out = out;
+    } else {
+      if (code_bytes > e->d_codes_cap) { if (e->d_codes) cudaFree(e->d_codes); e->d_codes = nullptr; CUDA_OK(cudaMalloc(&e->d_codes, code_bytes)); e->d_codes_cap = code_bytes; }
+      if (out_bytes > e->d_out_cap) { if (e->d_out) cudaFree(e->d_out); e->d_out = nullptr; CUDA_OK(cudaMalloc(&e->d_out, out_bytes)); e->d_out_cap = out_bytes; }
+      CUDA_OK(cudaMemcpyAsync(e->d_codes, codes, code_bytes, cudaMemcpyHostToDevice, s));
+      p.codes = e->d_codes; p.out = e->d_out;
+    }
+    launch_codec_embed_sum(p, s);
+    CUDA_OK(cudaGetLastError());
+    if (!device_ptrs) {
+      int flag = 0;
+      CUDA_OK(cudaMemcpyAsync(out, e->d_out, out_bytes, cudaMemcpyDeviceToHost, s));
+      CUDA_OK(cudaMemcpyAsync(&flag, e->d_err, 4, cudaMemcpyDeviceToHost, s));
+      CUDA_OK(cudaStreamSynchronize(s));
+      if (flag) {
+        CUDA_OK(cudaMemsetAsync(e->d_err, 0, 4, s));
+        return fail(Q3TTS_EINVAL, "a code id is outside its embedding table");
+      }
+    }
+    return (int)Q3TTS_OK;
+  });
+}
+
+int q3tts_codec_embed_sum(q3tts_codec_embedder* e, const int32_t* codes, int64_t n_frames, void* out) {
+  return codec_embed_common(e, codes, n_frames, out, false, nullptr);
+}
+
+int q3tts_codec_embed_sum_device(q3tts_codec_embedder* e, const int32_t* d_codes, int64_t n_frames, void* d_out, void* stream) {
+  return codec_embed_common(e, d_codes, n_frames, d_out, true, (cudaStream_t)stream);
+}
+
 // ---- measurement --------------------------------------------------------------------------------------------
 int q3tts_profile_enable(q3tts_model* h, int32_t enable) {
   if (!h) return fail(Q3TTS_EINVAL, "model is NULL");

@@ -272,7 +272,9 @@ void replace_all(std::string& s, const std::string& from, const std::string& to)
   }
 }
 
-void read_safetensors(const std::string& path, TensorMap* raw) {
+// `needle`: keep keys that START with it (contains == false) or CONTAIN it; `dtypes` (optional) receives the on-disk dtype names.
+void read_safetensors(const std::string& path, TensorMap* raw, const char* needle = "decoder.", bool contains = false,
+                      std::map<std::string, std::string>* dtypes = nullptr) {
   Mapped m;
   m.fd = open(path.c_str(), O_RDONLY);
   if (m.fd < 0) throw Error(Q3TTS_EIO, "cannot open " + path);
@@ -297,7 +299,7 @@ void read_safetensors(const std::string& path, TensorMap* raw) {
   for (auto& kv : hdr.obj) {
     const std::string& key = kv.first;
     if (key == "__metadata__") continue;
-    if (!starts(key, "decoder.")) continue;  // encoder.* is out of scope (and absent from the lite variant)
+    if (contains ? !has(key, needle) : !starts(key, needle)) continue;  // decoder load: encoder.* is out of scope (and absent from the lite variant)
     const Json& e = kv.second;
     const Json *jd = e.find("dtype"), *js = e.find("shape"), *jo = e.find("data_offsets");
     if (!jd || !js || !jo || jd->kind != Json::Str || js->kind != Json::Arr || jo->kind != Json::Arr || jo->arr.size() != 2)
@@ -310,11 +312,50 @@ void read_safetensors(const std::string& path, TensorMap* raw) {
     if (en < b || en > payload || (en - b) != (size_t)n * es)
       throw Error(Q3TTS_EFORMAT, path + ": data_offsets out of range for " + key);
     to_float(base + b, jd->str, n, &t.data);
+    if (dtypes) (*dtypes)[key] = jd->str;
     (*raw)[key] = std::move(t);
   }
 }
 
 }  // namespace
+
+static std::vector<std::string> list_safetensors(const std::string& dir) {
+  std::vector<std::string> files;
+  DIR* d = opendir(dir.c_str());
+  if (!d) throw Error(Q3TTS_EIO, "cannot list " + dir);
+  while (dirent* e = readdir(d)) {
+    std::string n = e->d_name;
+    if (n.size() > 12 && n.substr(n.size() - 12) == ".safetensors") files.push_back(dir + "/" + n);
+  }
+  closedir(d);
+  std::sort(files.begin(), files.end());
+  if (files.empty()) throw Error(Q3TTS_EIO, "no *.safetensors in " + dir);
+  return files;
+}
+
+void load_codec_embeddings(const std::string& model_dir, CodecEmbeddingTables* out) {
+  TensorMap raw;
+  std::map<std::string, std::string> dtypes;
+  for (auto& f : list_safetensors(model_dir)) read_safetensors(f, &raw, "codec_embedding", true, &dtypes);
+  const std::string k0 = "talker.model.codec_embedding.weight";
+  auto it = raw.find(k0);
+  if (it == raw.end()) throw Error(Q3TTS_EFORMAT, model_dir + ": no " + k0);
+  if (it->second.shape.size() != 2) throw Error(Q3TTS_EFORMAT, k0 + " must be 2-D");
+  out->hidden = it->second.shape[1];
+  out->dtype = dtypes[k0];
+  out->tables.clear();
+  out->tables.push_back(std::move(it->second));
+  for (int i = 0;; ++i) {
+    const std::string k = "talker.code_predictor.model.codec_embedding." + std::to_string(i) + ".weight";
+    auto jt = raw.find(k);
+    if (jt == raw.end()) break;
+    if (jt->second.shape.size() != 2 || jt->second.shape[1] != out->hidden)
+      throw Error(Q3TTS_EFORMAT, k + ": expected [vocab, " + std::to_string(out->hidden) + "]");
+    if (dtypes[k] != out->dtype) throw Error(Q3TTS_EFORMAT, k + ": dtype differs from " + k0);
+    out->tables.push_back(std::move(jt->second));
+  }
+  if (out->tables.size() < 2) throw Error(Q3TTS_EFORMAT, model_dir + ": no talker.code_predictor.model.codec_embedding.N.weight");
+}
 
 void load_checkpoint(const std::string& dir, Checkpoint* out) {
   parse_tokenizer_config(dir, &out->cfg);

@@ -44,6 +44,16 @@ void parse_tokenizer_config(const std::string& dir, q3tts_config* cfg);
 // Load + sanitize + validate.  Throws q3::Error(Q3TTS_EIO / Q3TTS_EFORMAT).
 void load_checkpoint(const std::string& dir, Checkpoint* out);
 
+// Row N2 of SURVEY 8(f): the 1 + (num_code_groups - 1) codec-embedding tables of the MAIN checkpoint
+// (<model_dir>/*.safetensors): talker.model.codec_embedding.weight [3072, H] (Talker.swift:495, 510) and
+// talker.code_predictor.model.codec_embedding.{i}.weight [2048, H] (CodePredictor.swift:206, 217-219).
+struct CodecEmbeddingTables {
+  int64_t hidden = 0;
+  std::string dtype;                 // on-disk dtype name ("BF16", "F16", "F32"): the sums are rounded to it after every add
+  std::vector<HostTensor> tables;    // [0] = talker table, [1..] = code-predictor tables, values exact in float
+};
+void load_codec_embeddings(const std::string& model_dir, CodecEmbeddingTables* out);
+
 // The decoder's expected tensor inventory after sanitize: key -> MLX-layout shape.
 std::map<std::string, std::vector<int64_t>> expected_decoder_tensors(const q3tts_config& cfg);
 

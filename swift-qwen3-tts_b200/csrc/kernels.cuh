@@ -91,6 +91,21 @@ void launch_attention_mma(const void* qkv, int dtype, void* out, const BatchGeom
 
 // Tail: causal conv C->1, k=7 on the (already outSnake-activated) operand, + bias, clip to [-1,1].
 // pcm address = pcm + pcm_base[b] + t.  Optional unclipped fp32 copy for the "out_conv" tap.
+// Codec-embedding sum for the Talker's next-step input (Q3.swift:485-491, 720-728, 927-935, 1157-1162):
+//   out[t,:] = (((E0[c[t,0]] + E1[c[t,1]]) + E2[c[t,2]]) + ...), every add rounded to the tables' dtype (MLX adds 16-bit arrays in
+//   fp32 and rounds the result: the sequential order and the intermediate roundings are part of the reference's result).
+constexpr int kMaxCodeGroups = 32;
+struct CodecEmbedParams {
+  const void* tables[kMaxCodeGroups];   // [vocab[g], H] each, dtype `dtype`
+  int vocab[kMaxCodeGroups];
+  int groups, H, dtype;                 // DT_F32 / DT_F16 / DT_BF16
+  const int32_t* codes;                 // [n, groups] frame-major
+  void* out;                            // [n, H], dtype `dtype`
+  long long n;
+  int* err_flag;                        // set when a code is outside its table (the reference leaves it unchecked)
+};
+void launch_codec_embed_sum(const CodecEmbedParams& p, cudaStream_t s);
+
 void launch_tail(const void* a, int a_dtype, int64_t a_bstride, const float* w /*[7][C]*/, float bias, int C,
                  float* pcm, const int64_t* pcm_base, float* tap, int64_t tap_bstride, const BatchGeom& g,
                  int rows_per_frame, cudaStream_t s);

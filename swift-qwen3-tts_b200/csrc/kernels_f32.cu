@@ -4,6 +4,9 @@
 // each kernel cites the lines it implements.
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
 
 #include "kernels.cuh"
 
@@ -584,6 +587,80 @@ void launch_tail(const void* a, int a_dtype, int64_t a_bstride, const float* w, 
   const int64_t warps = (int64_t)g.B * g.Tmax * rows_per_frame;
   const unsigned blocks = (unsigned)((warps * 32 + 255) / 256);
   Q3_DISPATCH_DT(a_dtype, T, (tail_kernel<T><<<blocks, 256, 0, s>>>((const T*)a, a_bstride, w, bias, C, pcm, pcm_base, tap, tap_bstride, g, rows_per_frame)));
+}
+
+// ================================================================================================
+// Codec-embedding sum: one CTA per frame, a thread owns 8 consecutive channels (16-byte row reads for the
+// 16-bit tables); 1 + 15 table rows are read once each, the running sum stays in registers in the tables' dtype.
+// ================================================================================================
+template <typename T> struct Emb8;
+template <> struct Emb8<float> {
+  float v[8];
+  __device__ void load(const float* p) { const float4 a = __ldg((const float4*)p), b = __ldg((const float4*)p + 1); v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w; }
+  __device__ void add(const Emb8& o) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __fadd_rn(v[i], o.v[i]);
+  }
+  __device__ void store(float* p) const { *(float4*)p = make_float4(v[0], v[1], v[2], v[3]); *((float4*)p + 1) = make_float4(v[4], v[5], v[6], v[7]); }
+};
+template <> struct Emb8<__half> {
+  __half2 v[4];
+  __device__ void load(const __half* p) { const uint4 u = __ldg((const uint4*)p); memcpy(v, &u, 16); }
+  __device__ void add(const Emb8& o) {      // fp32 add, one rounding to half per add (= MLX's 16-bit add)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 a = __half22float2(v[i]), b = __half22float2(o.v[i]);
+      v[i] = __floats2half2_rn(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y));
+    }
+  }
+  __device__ void store(__half* p) const { uint4 u; memcpy(&u, v, 16); *(uint4*)p = u; }
+};
+template <> struct Emb8<__nv_bfloat16> {
+  __nv_bfloat162 v[4];
+  __device__ void load(const __nv_bfloat16* p) { const uint4 u = __ldg((const uint4*)p); memcpy(v, &u, 16); }
+  __device__ void add(const Emb8& o) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 a = __bfloat1622float2(v[i]), b = __bfloat1622float2(o.v[i]);
+      v[i] = __floats2bfloat162_rn(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y));
+    }
+  }
+  __device__ void store(__nv_bfloat16* p) const { uint4 u; memcpy(&u, v, 16); *(uint4*)p = u; }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) codec_embed_sum_kernel(CodecEmbedParams p) {
+  __shared__ int s_code[kMaxCodeGroups];
+  for (long long t = blockIdx.x; t < p.n; t += gridDim.x) {
+    if (threadIdx.x < p.groups) {
+      int c = p.codes[t * p.groups + threadIdx.x];
+      if (c < 0 || c >= p.vocab[threadIdx.x]) { atomicOr(p.err_flag, 1); c = 0; }
+      s_code[threadIdx.x] = c;
+    }
+    __syncthreads();
+    for (int d0 = threadIdx.x * 8; d0 < p.H; d0 += blockDim.x * 8) {
+      Emb8<T> row[4], acc;
+      acc.load((const T*)p.tables[0] + (long long)s_code[0] * p.H + d0);
+      for (int g0 = 1; g0 < p.groups; g0 += 4) {       // four independent row reads in flight, adds in order
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (g0 + j < p.groups) row[j].load((const T*)p.tables[g0 + j] + (long long)s_code[g0 + j] * p.H + d0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (g0 + j < p.groups) acc.add(row[j]);
+      }
+      acc.store((T*)p.out + t * p.H + d0);
+    }
+    __syncthreads();
+  }
+}
+
+void launch_codec_embed_sum(const CodecEmbedParams& p, cudaStream_t s) {
+  if (p.n <= 0) return;
+  const unsigned blocks = (unsigned)std::min<long long>(p.n, 148LL * 8 * 16);
+  if (p.dtype == DT_F32) codec_embed_sum_kernel<float><<<blocks, 256, 0, s>>>(p);
+  else if (p.dtype == DT_F16) codec_embed_sum_kernel<__half><<<blocks, 256, 0, s>>>(p);
+  else codec_embed_sum_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>(p);
 }
 
 // ================================================================================================

@@ -24,7 +24,7 @@ import numpy as np
 
 __all__ = ["Qwen3TTSSpeechTokenizer", "DecodeStream", "Qwen3TTSSpeechTokenizerDecoder", "AudioDecodingFailed", "lib",
            "partition_lpt", "PREC_FP32", "PREC_FP16", "PREC_BF16", "ATTN_REFERENCE", "ATTN_CAUSAL_SW",
-           "library_path", "checkpoint_inspect", "pcm_to_int16", "write_wav", "trim_length",
+           "library_path", "checkpoint_inspect", "CodecEmbedder", "pcm_to_int16", "write_wav", "trim_length",
            "voice_clone_cut", "device_count"]
 
 PREC_FP32, PREC_FP16, PREC_BF16 = 0, 1, 2
@@ -106,6 +106,11 @@ def lib() -> C.CDLL:
         "q3tts_decode_int16": (C.c_int, [vp, vp, i32, i32, i32, vp, vp]),
         "q3tts_decode_varlen_int16": (C.c_int, [vp, vp, vp, i32, vp, vp]),
         "q3tts_decode_device": (C.c_int, [vp, vp, i32, i32, i32, vp, vp, vp]),
+        "q3tts_codec_embedder_load": (C.c_int, [cp, i32, C.POINTER(vp)]),
+        "q3tts_codec_embedder_free": (None, [vp]),
+        "q3tts_codec_embedder_info": (C.c_int, [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), vp]),
+        "q3tts_codec_embed_sum": (C.c_int, [vp, vp, i64, vp]),
+        "q3tts_codec_embed_sum_device": (C.c_int, [vp, vp, i64, vp, vp]),
         "q3tts_sync": (C.c_int, [vp, vp]),
         "q3tts_set_taps": (C.c_int, [vp, i32]),
         "q3tts_stage_tap_shape": (C.c_int, [vp, cp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i64)]),
@@ -189,6 +194,42 @@ def debug_resunit(B: int, rows: int, dil: int, out_snake: int = 0, precision: in
     ms, d = C.c_float(0), C.c_float(0)
     _check(lib().q3tts_debug_resunit(B, rows, dil, out_snake, precision, iters, C.byref(ms), C.byref(d)))
     return float(ms.value), float(d.value)
+
+
+class CodecEmbedder:
+    """Codec-embedding sum for the Talker's next-step input (Qwen3.swift:720-728, 485-491): 16 table rows per frame,
+    added left to right in the tables' dtype.  `model_dir` holds the main checkpoint's *.safetensors."""
+
+    def __init__(self, model_dir: str, device: int = 0):
+        h = C.c_void_p()
+        _check(lib().q3tts_codec_embedder_load(model_dir.encode(), device, C.byref(h)))
+        self._h = h
+        hid, grp, prec = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        vocab = (C.c_int32 * 32)()
+        _check(lib().q3tts_codec_embedder_info(self._h, C.byref(hid), C.byref(grp), C.byref(prec), vocab))
+        self.hidden, self.groups, self.precision = int(hid.value), int(grp.value), int(prec.value)
+        self.vocab = [int(vocab[i]) for i in range(self.groups)]
+
+    def __call__(self, codes: np.ndarray) -> np.ndarray:
+        """codes [n, groups] int32 -> [n, hidden]: float32, float16, or the raw bf16 bit patterns as uint16."""
+        ac = np.ascontiguousarray(codes, dtype=np.int32)
+        if ac.ndim != 2 or ac.shape[1] != self.groups:
+            raise AudioDecodingFailed(1, f"codes must be [n,{self.groups}], got {ac.shape}")
+        dt = {PREC_FP32: np.float32, PREC_FP16: np.float16, PREC_BF16: np.uint16}[self.precision]
+        out = np.empty((ac.shape[0], self.hidden), dtype=dt)
+        _check(lib().q3tts_codec_embed_sum(self._h, ac.ctypes.data, ac.shape[0], out.ctypes.data))
+        return out
+
+    def close(self) -> None:
+        if self._h:
+            lib().q3tts_codec_embedder_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def device_count() -> int:

@@ -175,6 +175,41 @@ public final class Qwen3TTSSpeechTokenizer {
     }
 }
 
+/// Codec-embedding sum for the Talker's next-step input (Qwen3.swift:720-728; 485-491 for the voice-cloning prefix):
+/// `talker.getInputEmbeddings()(code0) + codePredictor.codecEmbedding[0](code1) + ...`, left to right in the checkpoint's
+/// dtype, for `n` frames in one launch.  `modelDir` holds the main checkpoint's safetensors.
+public final class Qwen3TTSCodecEmbedder {
+    private let handle: OpaquePointer
+    public let hiddenSize: Int
+    public let numCodeGroups: Int
+
+    public init(modelDir: URL, device: Int32 = 0) throws {
+        var e: OpaquePointer?
+        try check(q3tts_codec_embedder_load(modelDir.path, device, &e))
+        guard let opened = e else { throw Qwen3TTSCUDAError.audioDecodingFailed("q3tts_codec_embedder_load returned NULL") }
+        handle = opened
+        var h: Int32 = 0, g: Int32 = 0, p: Int32 = 0
+        try check(q3tts_codec_embedder_info(opened, &h, &g, &p, nil))
+        hiddenSize = Int(h)
+        numCodeGroups = Int(g)
+    }
+
+    deinit { q3tts_codec_embedder_free(handle) }
+
+    /// - Parameter codes: [n, numCodeGroups]
+    /// - Returns: n * hiddenSize 16-bit patterns (bf16 / fp16, the checkpoint's dtype), row-major
+    public func callAsFunction(_ codes: Int32Tensor) throws -> [UInt16] {
+        precondition(codes.shape.count == 2 && codes.shape[1] == numCodeGroups)
+        var out = [UInt16](repeating: 0, count: codes.shape[0] * hiddenSize)
+        try codes.data.withUnsafeBufferPointer { c in
+            try out.withUnsafeMutableBufferPointer { o in
+                try check(q3tts_codec_embed_sum(handle, c.baseAddress, Int64(codes.shape[0]), o.baseAddress))
+            }
+        }
+        return out
+    }
+}
+
 /// Chunked streaming decode: feed codec frames as the Talker emits them (Qwen3.swift:640-729 produces one
 /// 16-code vector per step), get the matching 1920·n samples back.  The model must have been loaded with the
 /// causal sliding-window attention mode (`q3tts_options.attn_mode = Q3TTS_ATTN_CAUSAL_SW`); per-stream state is the

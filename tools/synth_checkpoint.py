@@ -184,3 +184,22 @@ def synth_codes(cfg: DecoderConfig, B: int, T: int, seed: int, zero_frac: float 
         mask = rng.random((B, T)) < zero_frac
         codes[:, 0, :][mask] = 0
     return codes.astype(np.int32)
+
+
+def write_codec_embeddings(model_dir: str, hidden: int = 2048, talker_vocab: int = 3072, vocab: int = 2048, groups: int = 16,
+                           dtype: str = "bfloat16", seed: int = DEFAULT_SEED) -> str:
+    """Write ``<model_dir>/model.safetensors`` holding the codec-embedding tables of the MAIN checkpoint under the
+    reference's key names (Talker.swift:495, CodePredictor.swift:206) plus two unrelated tensors a loader must skip.
+    Values ~ N(0, 0.5): wide enough that the intermediate roundings of the 16-bit sequential sum matter."""
+    from safetensors.torch import save_file
+    os.makedirs(model_dir, exist_ok=True)
+    g = torch.Generator().manual_seed(seed)
+    tdtype = {"float32": torch.float32, "float16": torch.float16, "bfloat16": torch.bfloat16}[dtype]
+    out = {"talker.model.codec_embedding.weight": (torch.randn(talker_vocab, hidden, generator=g) * 0.5).to(tdtype)}
+    for i in range(groups - 1):
+        out[f"talker.code_predictor.model.codec_embedding.{i}.weight"] = (torch.randn(vocab, hidden, generator=g) * 0.5).to(tdtype)
+    out["talker.model.text_embedding.weight"] = torch.zeros(4, 8, dtype=tdtype)
+    out["talker.model.norm.weight"] = torch.ones(hidden, dtype=tdtype)
+    save_file(out, os.path.join(model_dir, "model.safetensors"))
+    return model_dir
+
