@@ -2,6 +2,7 @@
 #include "engine.hpp"
 
 #include <algorithm>
+#include <functional>
 #include <cmath>
 #include <cstring>
 #include <memory>
@@ -24,6 +25,8 @@ Model::~Model() {
   if (arena) cudaFree(arena);
   if (d_codes) cudaFree(d_codes);
   if (d_pcm) cudaFree(d_pcm);
+  if (stream_hook_h) cudaFreeHost(stream_hook_h);
+  if (stream_hook_d) cudaFree(stream_hook_d);
   if (d_lengths) cudaFree(d_lengths);
   if (d_meta) cudaFree(d_meta);
   if (h_meta) cudaFreeHost(h_meta);
@@ -356,7 +359,14 @@ struct Ctx {
   cudaStream_t s;
   int64_t valid_frames;   // sum of len_frames over the micro-batch (host copy, for the work model)
   int cur_stage = -1;
+  // streaming: called right before every consumer that reads rows in front of its tile (buf = its input, rows_per_frame, C, bytes
+  // per element): the chunked decode restores the context rows of `buf` from the stream states and saves the new tail
+  std::function<void(void*, int, int, int)>* halo_hook = nullptr;
 };
+
+inline void halo_in(Ctx& x, const void* buf, int rows_per_frame, int C, int es) {
+  if (x.halo_hook) (*x.halo_hook)(const_cast<void*>(buf), rows_per_frame, C, es);
+}
 
 void account(Ctx& x, double flops, double bytes) {
   if (x.m.profile_enabled && x.cur_stage >= 0) {
@@ -494,6 +504,7 @@ static void run_back(Ctx& x, Plan& P, const void* to, const int64_t* d_pcm_base,
     UpsampleW& U = m.ups[i];
     { Epi e; e.out_y = P.up[i].X; e.y_dtype = DT_F32; gemm(x, U.tconv, cur, rate, e, "convT"); }   // [T*rate, r*L] == [T*rate*r, L]
     rate *= U.ratio;
+    halo_in(x, P.up[i].X, rate, c.latent_dim, 4);
     launch_begin(x, "dwconv_ln", 2.0 * 7 * c.latent_dim * (double)valid_frames * rate, (double)valid_frames * rate * c.latent_dim * (4.0 + dt_size(op)));
     launch_dwconv_ln(P.up[i].X, U.dw_w, U.dw_b, U.ln_w, U.ln_b, 1e-6f, P.up[i].N, op, x.g, rate, c.latent_dim, s);
     launch_end(x);
@@ -510,6 +521,7 @@ static void run_back(Ctx& x, Plan& P, const void* to, const int64_t* d_pcm_base,
   {
     Epi e; e.out_a = P.A0; e.snake = &m.block_in_snake[0];
     if (taps) e.out_tap = tap_buffer(m, "init_conv_cl", B, c.decoder_dim, (int64_t)Tmax * rate);
+    halo_in(x, cur, rate, c.latent_dim, (int)dt_size(op));
     gemm(x, m.init_conv, cur, rate, e, "conv7");
     if (taps) tap(x, "init_conv", m.taps["init_conv_cl"].d, DT_F32, rate, c.decoder_dim, c.decoder_dim);
   }
@@ -526,6 +538,7 @@ static void run_back(Ctx& x, Plan& P, const void* to, const int64_t* d_pcm_base,
     {
       Epi e; e.out_y = P.blk[i].X; e.y_dtype = m.st_dtype;
       if (!fused) { e.out_a = P.blk[i].A; e.snake = &Bk.act_in_next[0]; }   // the fused units activate their own input
+      halo_in(x, a_in, rate, Bk.tconv.Cin, (int)dt_size(op));
       gemm(x, Bk.tconv, a_in, rate, e, "convT");
     }
     rate *= Bk.rate;
@@ -540,6 +553,7 @@ static void run_back(Ctx& x, Plan& P, const void* to, const int64_t* d_pcm_base,
         rp.ea1 = Bk.act_in_next[j].ea; rp.ib1 = Bk.act_in_next[j].ib; rp.ea2 = Bk.act2[j].ea; rp.ib2 = Bk.act2[j].ib;
         rp.ea3 = j == 2 ? block_out->ea : nullptr; rp.ib3 = j == 2 ? block_out->ib : nullptr;
         rp.dil = Bk.conv7[j].dil;
+        halo_in(x, bufs[j], rate, Bk.cout, (int)dt_size(op));
         const double rows = (double)valid_frames * rate, C = (double)Bk.cout;
         const double fl = 2.0 * rows * 8.0 * C * C, by = rows * C * 2.0 * 2.0 + 8.0 * C * C * 2.0;   // X in, X' out (the halo stays on chip), weights once
         launch_begin(x, "resunit", fl, by);
@@ -563,6 +577,7 @@ static void run_back(Ctx& x, Plan& P, const void* to, const int64_t* d_pcm_base,
         const SnakeW* next = (j < 2) ? &Bk.act_in_next[j + 1] : block_out;
         // the block's last unit feeds only the next consumer's operand: its stream output is never read again
         void* x_out = (j == 2 && !taps && op != DT_F32) ? nullptr : P.blk[i].X;
+        halo_in(x, fuse1 ? abuf[j & 1] : P.blk[i].A, rate, Bk.cout, (int)dt_size(op));
         if (fuse1) {
           const GemmW& w7 = Bk.conv7[j];
           const GemmW& w1 = Bk.conv1[j];
@@ -597,6 +612,7 @@ static void run_back(Ctx& x, Plan& P, const void* to, const int64_t* d_pcm_base,
   {
     const int C = m.blocks[3].cout;
     float* tp = taps ? tap_buffer(m, "out_conv", B, 1, (int64_t)Tmax * rate) : nullptr;
+    halo_in(x, a_in, rate, C, (int)dt_size(op));
     launch_begin(x, "conv7_clip", 2.0 * 7 * C * (double)valid_frames * rate, (double)valid_frames * rate * (C * (double)dt_size(op) + 4.0));
     launch_tail(a_in, op, (int64_t)Tmax * rate * C, m.tail_w, m.tail_bias, C, d_pcm, d_pcm_base, tp, (int64_t)Tmax * rate, x.g, rate, s);
     launch_end(x);
@@ -696,38 +712,56 @@ void run_microbatch(Model& m, const int32_t* d_codes, const int64_t* d_code_base
 
 
 // ---- chunked streaming ------------------------------------------------------------------------------------------------
-int stream_context_frames(const q3tts_config& c) {
-  // causal receptive field of stages 4-6, walked from the PCM sample back to the pre-transformer output (rows at each rate)
-  int64_t rows = 6;                                              // outConv k = 7
-  for (int i = 3; i >= 0; --i) {
-    rows += 6 * (1 + 3 + 9);                                     // three residual units, conv7 with dilation 1, 3, 9
-    const int r = c.upsample_rates[i];
-    rows = (rows + r - 1) / r + 1;                               // transposed conv k = 2r, s = r: y[t*r+p] needs x[t], x[t-1]
+std::vector<HaloStage> conv_state_layout(const Model& m) {
+  // mirrors the halo_in() calls of run_back, in order (the streaming hook checks every call against this list)
+  const q3tts_config& c = m.cfg;
+  const int ops = (int)dt_size(m.op_dtype);
+  std::vector<HaloStage> v;
+  size_t off = 0;
+  auto push = [&](int halo_rows, int rate, int C, int es) {
+    HaloStage h{(halo_rows + rate - 1) / rate, rate, C, es, off, 0};
+    h.bytes = (size_t)h.frames * rate * C * es;
+    off += (h.bytes + 255) & ~(size_t)255;
+    v.push_back(h);
+  };
+  int rate = 1;
+  for (size_t i = 0; i < m.ups.size(); ++i) {
+    rate *= m.ups[i].ratio;
+    push(6, rate, c.latent_dim, 4);                                          // ConvNeXt depthwise k = 7 on the fp32 stream
   }
-  rows += 6;                                                     // initConv k = 7
-  for (int i = c.num_upsampling_ratios - 1; i >= 0; --i) {
-    rows += 6;                                                   // ConvNeXt depthwise k = 7
-    const int r = c.upsampling_ratios[i];
-    rows = (rows + r - 1) / r;                                   // transposed conv k = s = r: y[t*r+p] needs x[t] only
+  push((m.init_conv.taps - 1) * m.init_conv.dil, rate, c.latent_dim, ops);   // initConv
+  for (int i = 0; i < 4; ++i) {
+    const BlockW& Bk = m.blocks[(size_t)i];
+    push(1, rate, Bk.tconv.Cin, ops);                                        // transposed conv k = 2r, s = r: x[t], x[t-1]
+    rate *= Bk.rate;
+    for (int j = 0; j < 3; ++j) push((Bk.conv7[j].taps - 1) * Bk.conv7[j].dil, rate, Bk.cout, ops);
   }
-  return (int)rows;
+  push(6, rate, m.blocks[3].cout, ops);                                      // outConv k = 7
+  return v;
+}
+
+int stream_context_frames(const Model& m) {
+  int h = 1;
+  for (const HaloStage& st : conv_state_layout(m)) h = std::max(h, st.frames);
+  return h;
 }
 
 void stream_state_alloc(Model& m, StreamState& st) {
   const q3tts_config& c = m.cfg;
   const size_t op = dt_size(m.op_dtype);
   const size_t ld = (size_t)(c.num_attention_heads + 2 * c.num_key_value_heads) * c.head_dim;
-  const int Hc = stream_context_frames(c), W1 = std::max(c.sliding_window - 1, 0);
+  const int W1 = std::max(c.sliding_window - 1, 0);
+  const std::vector<HaloStage> lay = conv_state_layout(m);
   CUDA_OK(cudaMalloc(&st.q_hist, 2 * (size_t)c.codebook_dim * op));
   CUDA_OK(cudaMalloc(&st.kv, std::max<size_t>((size_t)c.num_hidden_layers * W1 * ld * op, 16)));
-  CUDA_OK(cudaMalloc(&st.to_hist, (size_t)Hc * c.latent_dim * op));
+  CUDA_OK(cudaMalloc(&st.conv, lay.back().off + ((lay.back().bytes + 255) & ~(size_t)255)));
   st.frames_done = 0;
 }
 void stream_state_free(Model& m, StreamState& st) {
   cudaSetDevice(m.device);
   if (st.q_hist) cudaFree(st.q_hist);
   if (st.kv) cudaFree(st.kv);
-  if (st.to_hist) cudaFree(st.to_hist);
+  if (st.conv) cudaFree(st.conv);
   st = StreamState{};
 }
 
@@ -736,7 +770,8 @@ void run_stream_batch(Model& m, StreamState* const* streams, int S, const int32_
   const q3tts_config& c = m.cfg;
   const int op = m.op_dtype;
   const size_t ops = dt_size(op);
-  const int Hc = stream_context_frames(c), W1 = c.sliding_window - 1, Q = c.num_quantizers;
+  const int Hc = stream_context_frames(m), W1 = c.sliding_window - 1, Q = c.num_quantizers;
+  const std::vector<HaloStage> lay = conv_state_layout(m);
   const int cb = c.codebook_dim, lat = c.latent_dim, hid = c.hidden_size, inter = c.intermediate_size;
   const int A = c.num_attention_heads * c.head_dim, ld = (c.num_attention_heads + 2 * c.num_key_value_heads) * c.head_dim;
   const int64_t up = c.total_upsample;
@@ -828,20 +863,10 @@ void run_stream_batch(Model& m, StreamState* const* streams, int S, const int32_
       if (W1 > 0) kv_out[(size_t)l].push_back({slot + (size_t)n * ld * ops, cache, (long long)((size_t)W1 * ld * ops)});   // rows n .. n+W1-1
     }
     char* cin = (char*)w.Cin + (size_t)i * Tc * lat * ops;
-    if (cc > 0) mid.push_back({(char*)st.to_hist + (size_t)(Hc - cc) * lat * ops, cin, (long long)((size_t)cc * lat * ops)});
+    if (cc > 0) mid.push_back({nullptr, cin, (long long)((size_t)cc * lat * ops)});   // context frames: placeholders (their outputs are never read)
     mid.push_back({(char*)w.TO + (size_t)i * nmax * lat * ops, cin + (size_t)cc * lat * ops, (long long)((size_t)n * lat * ops)});
     post.push_back({(char*)w.pcm + ((size_t)i * Tc + cc) * up * 4, (char*)d_pcm_out + (size_t)frame_off * up * 4, (long long)((size_t)n * up * 4)});
     frame_off += n;
-  }
-  // the to_hist update reads Cin after it is complete: a second list run after `mid`
-  std::vector<CopyItem> mid2;
-  for (int i = 0; i < S; ++i) {
-    const int n = n_frames[i];
-    if (n == 0) continue;
-    StreamState& st = *streams[i];
-    const int cc = ctxc[(size_t)i], keep = std::min(Hc, cc + n);
-    char* cin = (char*)w.Cin + (size_t)i * Tc * lat * ops;
-    mid2.push_back({cin + (size_t)(cc + n - keep) * lat * ops, (char*)st.to_hist + (size_t)(Hc - keep) * lat * ops, (long long)((size_t)keep * lat * ops)});
   }
   size_t cursor = 0;
   auto place = [&](const std::vector<CopyItem>& v) {
@@ -850,7 +875,7 @@ void run_stream_batch(Model& m, StreamState* const* streams, int S, const int32_
     for (const CopyItem& it : v) h_items[cursor++] = it;
     return at;
   };
-  const size_t at_pre = place(pre), at_mid = place(mid), at_mid2 = place(mid2), at_post = place(post);
+  const size_t at_pre = place(pre), at_mid = place(mid), at_post = place(post);
   std::vector<size_t> at_in((size_t)c.num_hidden_layers), at_out((size_t)c.num_hidden_layers);
   for (int l = 0; l < c.num_hidden_layers; ++l) { at_in[(size_t)l] = place(kv_in[(size_t)l]); at_out[(size_t)l] = place(kv_out[(size_t)l]); }
   CUDA_OK(cudaMemcpyAsync(w.len_new, hm, meta_bytes, cudaMemcpyHostToDevice, s));
@@ -893,13 +918,56 @@ void run_stream_batch(Model& m, StreamState* const* streams, int S, const int32_
   launch_rmsnorm(w.H, m.final_norm, c.rms_norm_eps, w.NB, op, Rn, hid, s); m.launches += 1;
   { Epi e; e.out_a = w.TO; gemm(xn, m.out_proj, w.NB, 1, e, "out_proj"); }
   run_copies(at_mid, mid.size());
-  run_copies(at_mid2, mid2.size());
 
   // ---- back: the conv stack over [context | new] frames; only the new frames' PCM is kept ----
   int64_t valid_c = 0;
   for (int i = 0; i < S; ++i) valid_c += n_frames[i] > 0 ? ctxc[(size_t)i] + n_frames[i] : 0;
   Ctx xc{m, BatchGeom{S, Tc, w.len_c, (long long)valid_c, nullptr}, s, valid_c};
+  // Per-consumer state carry: [restore the context rows the consumer reads] then [save the new tail], two copy lists per
+  // haloed consumer, built here and uploaded through a pinned block that is only appended to during the push.
+  const size_t hook_items = lay.size() * 2 * (size_t)S;
+  if (hook_items * sizeof(CopyItem) > m.stream_hook_cap) {
+    CUDA_OK(cudaStreamSynchronize(s));
+    if (m.stream_hook_h) cudaFreeHost(m.stream_hook_h);
+    if (m.stream_hook_d) cudaFree(m.stream_hook_d);
+    m.stream_hook_h = nullptr; m.stream_hook_d = nullptr; m.stream_hook_cap = 0;
+    CUDA_OK(cudaMallocHost(&m.stream_hook_h, hook_items * sizeof(CopyItem)));
+    CUDA_OK(cudaMalloc(&m.stream_hook_d, hook_items * sizeof(CopyItem)));
+    m.stream_hook_cap = hook_items * sizeof(CopyItem);
+  }
+  size_t hook_k = 0, hook_cursor = 0;
+  std::function<void(void*, int, int, int)> hook = [&](void* buf, int rate, int C, int es) {
+    if (hook_k >= lay.size()) throw Error(Q3TTS_EINVAL, "internal: more haloed consumers than conv_state_layout lists");
+    const HaloStage& h = lay[hook_k++];
+    if (h.rate != rate || h.C != C || h.es != es) throw Error(Q3TTS_EINVAL, "internal: conv_state_layout is out of step with run_back");
+    const size_t frame_bytes = (size_t)rate * C * es, slot_bytes = (size_t)Tc * frame_bytes;
+    CopyItem* items = (CopyItem*)m.stream_hook_h + hook_cursor;
+    size_t n_restore = 0, n_save = 0;
+    for (int i = 0; i < S; ++i) {       // restore: the last r context frames <- the newest r frames of the state (right-aligned)
+      const int n = n_frames[i], cc = ctxc[(size_t)i], r = std::min(h.frames, cc);
+      if (n == 0 || r == 0) continue;
+      char* slot = (char*)buf + (size_t)i * slot_bytes;
+      items[n_restore++] = {(char*)streams[i]->conv + h.off + (size_t)(h.frames - r) * frame_bytes, slot + (size_t)(cc - r) * frame_bytes,
+                            (long long)((size_t)r * frame_bytes)};
+    }
+    for (int i = 0; i < S; ++i) {       // save: the last `keep` frames of [context | new] (all restored or freshly computed)
+      const int n = n_frames[i], cc = ctxc[(size_t)i], keep = std::min(h.frames, cc + n);
+      if (n == 0) continue;
+      char* slot = (char*)buf + (size_t)i * slot_bytes;
+      items[n_restore + n_save++] = {slot + (size_t)(cc + n - keep) * frame_bytes, (char*)streams[i]->conv + h.off + (size_t)(h.frames - keep) * frame_bytes,
+                                     (long long)((size_t)keep * frame_bytes)};
+    }
+    const size_t cnt = n_restore + n_save;
+    if (cnt == 0) return;
+    CopyItem* d_items = (CopyItem*)m.stream_hook_d + hook_cursor;
+    CUDA_OK(cudaMemcpyAsync(d_items, items, cnt * sizeof(CopyItem), cudaMemcpyHostToDevice, s));
+    if (n_restore) { launch_block_copy(d_items, (int)n_restore, s); m.launches += 1; }
+    if (n_save) { launch_block_copy(d_items + n_restore, (int)n_save, s); m.launches += 1; }   // a separate launch: its sources include restored rows
+    hook_cursor += cnt;
+  };
+  xc.halo_hook = &hook;
   run_back(xc, P, w.Cin, w.pcm_base, w.pcm);
+  if (hook_k != lay.size()) throw Error(Q3TTS_EINVAL, "internal: fewer haloed consumers than conv_state_layout lists");
   run_copies(at_post, post.size());
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) throw Error(Q3TTS_ECUDA, std::string("kernel launch: ") + cudaGetErrorString(err));

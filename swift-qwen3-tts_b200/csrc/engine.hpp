@@ -86,6 +86,7 @@ struct Model {
   size_t arena_cap = 0;
   uint64_t default_workspace = 24ull << 30;   // activation budget when q3tts_options.workspace_bytes == 0 (set at load)
   int32_t* d_codes = nullptr; size_t d_codes_cap = 0;
+  char* stream_hook_h = nullptr; char* stream_hook_d = nullptr; size_t stream_hook_cap = 0;   // streaming: per-consumer copy lists
   float* d_pcm = nullptr;     size_t d_pcm_cap = 0;
   bool pcm_i16 = false;       // this call's tail writes int16 PCM into the (float-sized) output buffer
   int32_t* d_lengths = nullptr; size_t d_lengths_cap = 0;
@@ -115,16 +116,22 @@ struct Model {
 // Chunked streaming (Q3TTS_ATTN_CAUSAL_SW only).  Per stream, on the device, right-aligned histories:
 //   q_hist  [2][codebook_dim]            last inputs of pre_conv (k = 3)
 //   kv      [layers][W-1][qkv width]     K and V of the last W-1 frames of every transformer layer (W = sliding_window)
-//   to_hist [Hc][latent_dim]             last pre-transformer outputs: the conv stack (stages 4-6) is re-run over Hc context
-//                                        frames per chunk (overlap-save; Hc = its causal receptive field, 10 frames for
-//                                        the 12 Hz decoder) -- exact, at (Hc + n) / n times the conv work of a chunk of n.
+//   conv   per haloed consumer of the conv stack (ConvNeXt depthwise convs, initConv, the blocks' transposed convs,
+//          every residual unit's dilated conv7, outConv): the last ceil(halo / rate) frames of ITS INPUT.  A push lays
+//          the slots out as [Hs context frames | new frames] (Hs = the largest of those frame counts, 3 for the 12 Hz
+//          decoder), computes every stage over the whole slot and, right before each haloed consumer, overwrites the
+//          context rows it reads with the saved state (and saves the new tail).  Outputs computed for context frames
+//          are garbage by construction and are never read: exact, at (Hs + n) / n times the conv work of a chunk of n
+//          frames (the receptive-field overlap-save this replaces cost (10 + n) / n).
 struct StreamState {
   int64_t frames_done = 0;
   void* q_hist = nullptr;
   void* kv = nullptr;
-  void* to_hist = nullptr;
+  void* conv = nullptr;          // one block, stages at the offsets of conv_state_layout()
 };
-int stream_context_frames(const q3tts_config& c);      // Hc
+struct HaloStage { int frames, rate, C, es; size_t off, bytes; };   // state of one haloed consumer: frames x rate rows x C x es bytes
+std::vector<HaloStage> conv_state_layout(const Model& m);           // in the order run_back reaches the consumers
+int stream_context_frames(const Model& m);             // Hs
 void stream_state_alloc(Model& m, StreamState& st);
 void stream_state_free(Model& m, StreamState& st);
 // One chunk for each of S streams in one launch chain.  d_codes: packed [sum n, Q] frame-major; n_frames: host [S];

@@ -38,7 +38,7 @@ def main():
     line = {"workload": f"{S} streams/GPU x {n_chunks} chunks of 0.5 s (6,6,6,7 frames), causal-SW state carry", "n_gpus": world, "rank": rank,
             "chunk_latency_ms": {"p50": float(np.percentile(steady, 50)), "p99": float(np.percentile(steady, 99)), "max": float(steady.max())},
             "audio_s_per_s_per_gpu": audio_s / (steady.sum() / 1e3), "realtime_streams_per_gpu": audio_s / (steady.sum() / 1e3),
-            "context_frames_recomputed": 10, "launches": tok.launch_count()}
+            "context_frames_per_push": 3, "launches": tok.launch_count()}
     print(json.dumps(line), flush=True)
     for s in streams:
         s.close()
