@@ -816,8 +816,16 @@ bool tc2_fuse_supported(const ConvGemmParams& p, int op_dtype) {
          !p.res && !p.out_y && !p.out_tap && !p.scale;
 }
 
+static cudaError_t launch_tc2_impl(const ConvGemmParams& p, const BatchGeom& g, int op_dtype, int y_dtype, cudaStream_t s,
+                                   const FusedConv1* fuse, bool allow_pair);
+
 cudaError_t launch_conv_gemm_tc2(const ConvGemmParams& p, const BatchGeom& g, int op_dtype, int y_dtype, cudaStream_t s,
                                  const FusedConv1* fuse) {
+  return launch_tc2_impl(p, g, op_dtype, y_dtype, s, fuse, true);
+}
+
+static cudaError_t launch_tc2_impl(const ConvGemmParams& p, const BatchGeom& g, int op_dtype, int y_dtype, cudaStream_t s,
+                                   const FusedConv1* fuse, bool allow_pair) {
   EncodeTiledFn enc = encode_fn2();
   if (!enc) return cudaErrorNotSupported;
   static const int cs_env = env_int("Q3TTS_TC_CLUSTER", 2);
@@ -837,7 +845,7 @@ cudaError_t launch_conv_gemm_tc2(const ConvGemmParams& p, const BatchGeom& g, in
   q.n_tiles = p.N / BN;
   q.m_tiles_total = g.B * q.tiles_per_utt;
   int cs = (cs_env == 2 && BN % 16 == 0 && (q.m_tiles_total >= 2 || fuse)) ? 2 : 1;   // the fused unit always runs as a pair
-  const bool pair = pair_env && cs == 2;
+  const bool pair = pair_env && cs == 2 && allow_pair;
   if (fuse && !pair) return cudaErrorNotSupported;
   q.cs = cs;
   q.nacc = (!fuse && BN <= 128 && nacc_env >= 4) ? 4 : 2;   // the fused unit tracks two conv1 accumulators
@@ -963,6 +971,10 @@ cudaError_t launch_conv_gemm_tc2(const ConvGemmParams& p, const BatchGeom& g, in
     static const int max_nw_env = env_int("Q3TTS_TC_MAX_NW", T2_MAX_NW);   // experiments: cap the W ring depth
     q.nw = std::min(q.nw, std::max(2, max_nw_env));
   }
+  // Small-K, HBM-bound GEMMs whose weights do not fit in smem even halved (block 1's 1x1 conv: K = 384, two N tiles) run
+  // 10 % faster as independent 128-row CTAs (no cross-CTA commits / arrives per item) than as CTA pairs; measured, gemm_bench.
+  if (pair && !fuse && !q.w_resident && p.taps * p.Cin <= 384 && q.n_tiles >= 2)
+    return launch_tc2_impl(p, g, op_dtype, y_dtype, s, fuse, false);
   static const int na_env = env_int("Q3TTS_TC_NA", 0);   // experiments
   if (na_env > 0 && !q.w_resident) {
     q.na = std::min(T2_MAX_NA, na_env);
