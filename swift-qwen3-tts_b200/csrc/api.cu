@@ -126,7 +126,7 @@ void decode_core(Model& m, const int32_t* d_codes, std::vector<Utt> utts, int64_
   for (auto& mb : mbs) {
     int64_t valid = 0;
     for (int i = 0; i < mb.B; ++i) valid += utts[(size_t)(mb.first + i)].frames;
-    run_microbatch(m, d_codes, d_cb + mb.first, sq, st, d_len + mb.first, d_pb + mb.first, d_pcm, mb.B, mb.Tmax, valid, s);
+    run_microbatch_graphed(m, d_codes, d_cb + mb.first, sq, st, d_len + mb.first, d_pb + mb.first, d_pcm, mb.B, mb.Tmax, valid, s);
     if (m.profile_enabled) {
       CUDA_OK(cudaStreamSynchronize(s));
       for (auto& sp : m.prof)
@@ -374,6 +374,14 @@ int q3tts_set_taps(q3tts_model* h, int32_t enable) {
   if (!h) return fail(Q3TTS_EINVAL, "model is NULL");
   std::lock_guard<std::mutex> lock(h->m->mu);
   h->m->taps_enabled = enable != 0;
+  return Q3TTS_OK;
+}
+
+int q3tts_set_graphs(q3tts_model* h, int32_t mode) {
+  if (!h) return fail(Q3TTS_EINVAL, "model is NULL");
+  if (mode < -1 || mode > 1) return fail(Q3TTS_EINVAL, "mode must be -1 (automatic), 0 (off) or 1 (always)");
+  std::lock_guard<std::mutex> lock(h->m->mu);
+  h->m->graph_mode = mode;
   return Q3TTS_OK;
 }
 

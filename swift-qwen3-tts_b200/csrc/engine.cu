@@ -25,6 +25,7 @@ Model::~Model() {
   if (arena) cudaFree(arena);
   if (d_codes) cudaFree(d_codes);
   if (d_pcm) cudaFree(d_pcm);
+  for (auto& g : graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
   if (stream_hook_h) cudaFreeHost(stream_hook_h);
   if (stream_hook_d) cudaFree(stream_hook_d);
   if (d_lengths) cudaFree(d_lengths);
@@ -738,6 +739,78 @@ std::vector<HaloStage> conv_state_layout(const Model& m) {
   }
   push(6, rate, m.blocks[3].cout, ops);                                      // outConv k = 7
   return v;
+}
+
+void run_microbatch_graphed(Model& m, const int32_t* d_codes, const int64_t* d_code_base, int64_t sq, int64_t st,
+                            const int* d_len, const int64_t* d_pcm_base, float* d_pcm, int B, int Tmax, int64_t valid_frames,
+                            cudaStream_t s) {
+  static const int env_mode = []() { const char* e = getenv("Q3TTS_GRAPHS"); return e ? atoi(e) : -2; }();
+  const int mode = env_mode != -2 ? env_mode : m.graph_mode;
+  // the legacy default stream cannot be captured
+  const bool capturable = s != nullptr && s != cudaStreamLegacy && s != cudaStreamPerThread;
+  const bool want = capturable && !m.profile_enabled && !m.taps_enabled && m.op_dtype != DT_F32 &&
+                    (mode == 1 || (mode < 0 && (long long)B * Tmax <= m.graph_max_frames));
+  if (!want) {
+    run_microbatch(m, d_codes, d_code_base, sq, st, d_len, d_pcm_base, d_pcm, B, Tmax, valid_frames, s);
+    return;
+  }
+  // the arena must not move during (or after) capture: grow it first
+  const size_t need = plan_bytes(m, B, Tmax);
+  if (need > m.arena_cap) {
+    CUDA_OK(cudaStreamSynchronize(s));
+    if (m.arena) cudaFree(m.arena);
+    m.arena = nullptr; m.arena_cap = 0;
+    CUDA_OK(cudaMalloc(&m.arena, need));
+    m.arena_cap = need;
+  }
+  const std::vector<long long> key = {(long long)(uintptr_t)d_codes, (long long)(uintptr_t)d_code_base, (long long)sq, (long long)st,
+                                      (long long)(uintptr_t)d_len, (long long)(uintptr_t)d_pcm_base, (long long)(uintptr_t)d_pcm,
+                                      B, Tmax, (long long)valid_frames, (long long)(uintptr_t)m.arena, m.pcm_i16 ? 1 : 0};
+  Model::GraphEntry* e = nullptr;
+  for (auto& g : m.graphs) if (g.key == key) { e = &g; break; }
+  if (e && e->exec) {
+    CUDA_OK(cudaGraphLaunch(e->exec, s));
+    m.launches += e->launches;
+    return;
+  }
+  if (e && e->seen < 0) {   // this key could not be captured: stay eager
+    run_microbatch(m, d_codes, d_code_base, sq, st, d_len, d_pcm_base, d_pcm, B, Tmax, valid_frames, s);
+    return;
+  }
+  if (!e) {   // first sighting: run eagerly (one-off shapes never pay for a capture; lazy one-time setup happens outside capture)
+    if (m.graphs.size() >= 16) {
+      for (auto& g : m.graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+      m.graphs.clear();
+    }
+    Model::GraphEntry ne; ne.key = key; ne.seen = 1;
+    m.graphs.push_back(ne);
+    run_microbatch(m, d_codes, d_code_base, sq, st, d_len, d_pcm_base, d_pcm, B, Tmax, valid_frames, s);
+    return;
+  }
+  // second sighting: capture, instantiate, launch
+  const long long before = m.launches;
+  cudaGraph_t graph = nullptr;
+  if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    (void)cudaGetLastError();
+    e->seen = -1;
+    run_microbatch(m, d_codes, d_code_base, sq, st, d_len, d_pcm_base, d_pcm, B, Tmax, valid_frames, s);
+    return;
+  }
+  try {
+    run_microbatch(m, d_codes, d_code_base, sq, st, d_len, d_pcm_base, d_pcm, B, Tmax, valid_frames, s);
+  } catch (...) {
+    cudaStreamEndCapture(s, &graph);
+    if (graph) cudaGraphDestroy(graph);
+    throw;
+  }
+  CUDA_OK(cudaStreamEndCapture(s, &graph));
+  cudaGraphExec_t exec = nullptr;
+  cudaError_t err = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (err != cudaSuccess) throw Error(Q3TTS_ECUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(err));
+  e->exec = exec;
+  e->launches = m.launches - before;
+  CUDA_OK(cudaGraphLaunch(exec, s));
 }
 
 int stream_context_frames(const Model& m) {

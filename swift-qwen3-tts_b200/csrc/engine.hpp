@@ -86,6 +86,12 @@ struct Model {
   size_t arena_cap = 0;
   uint64_t default_workspace = 24ull << 30;   // activation budget when q3tts_options.workspace_bytes == 0 (set at load)
   int32_t* d_codes = nullptr; size_t d_codes_cap = 0;
+  // CUDA graphs for launch-bound chains (small micro-batches: ~95 launches of a few microseconds each): a micro-batch whose
+  // key (shape, every pointer the launches bake in, output format) has been seen before is captured once and replayed.
+  struct GraphEntry { std::vector<long long> key; cudaGraphExec_t exec = nullptr; long long launches = 0; int seen = 0; };
+  std::vector<GraphEntry> graphs;
+  int graph_mode = 0;            // 0: off (default: measured SLOWER than eager launches), 1: always, -1: chains of <= graph_max_frames frames
+  long long graph_max_frames = 2048;
   char* stream_hook_h = nullptr; char* stream_hook_d = nullptr; size_t stream_hook_cap = 0;   // streaming: per-consumer copy lists
   float* d_pcm = nullptr;     size_t d_pcm_cap = 0;
   bool pcm_i16 = false;       // this call's tail writes int16 PCM into the (float-sized) output buffer
@@ -136,6 +142,10 @@ void stream_state_alloc(Model& m, StreamState& st);
 void stream_state_free(Model& m, StreamState& st);
 // One chunk for each of S streams in one launch chain.  d_codes: packed [sum n, Q] frame-major; n_frames: host [S];
 // d_pcm_out: packed [sum n * total_upsample].  Advances frames_done.
+// run_microbatch, or the replay of its captured graph (see Model::graphs).
+void run_microbatch_graphed(Model& m, const int32_t* d_codes, const int64_t* d_code_base, int64_t sq, int64_t st,
+                            const int* d_len, const int64_t* d_pcm_base, float* d_pcm, int B, int Tmax, int64_t valid_frames,
+                            cudaStream_t s);
 void run_stream_batch(Model& m, StreamState* const* streams, int S, const int32_t* d_codes, const int* n_frames,
                       float* d_pcm_out, cudaStream_t s);
 

@@ -113,6 +113,7 @@ def lib() -> C.CDLL:
         "q3tts_codec_embed_sum_device": (C.c_int, [vp, vp, i64, vp, vp]),
         "q3tts_sync": (C.c_int, [vp, vp]),
         "q3tts_set_taps": (C.c_int, [vp, i32]),
+        "q3tts_set_graphs": (C.c_int, [vp, i32]),
         "q3tts_stage_tap_shape": (C.c_int, [vp, cp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i64)]),
         "q3tts_stage_tap": (C.c_int, [vp, cp, vp, i64]),
         "q3tts_weight_shape": (C.c_int, [vp, cp, C.POINTER(i32), C.POINTER(i64 * 4)]),
@@ -340,6 +341,10 @@ class Qwen3TTSSpeechTokenizer:
         lengths = np.zeros(B, dtype=np.int32)
         _check(lib().q3tts_decode(self._h, ac.ctypes.data, B, T, CODES_BTQ, audio.ctypes.data, lengths.ctypes.data))
         return audio, lengths
+
+    def set_graphs(self, mode: int) -> None:
+        """1: replay a CUDA graph for launch chains seen before; -1: only for chains of <= 2048 frames; 0: never (default)."""
+        _check(lib().q3tts_set_graphs(self._h, mode))
 
     def decode_int16(self, audio_codes: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
         """audio_codes [B,T,16] -> (audio [B, T*1920] int16 = Int16(clamp(x) * 32767), audio_lengths [B]); main.swift:158-160."""

@@ -160,6 +160,34 @@ def test_int16_decode_16bit_engine(full_dir, full_oracle):
     tok.close()
 
 
+def test_cuda_graph_replay_is_bit_identical(full_dir, full_oracle):
+    # small decodes are launch-bound: the launch chain is captured on its second sighting and replayed afterwards.
+    # Same kernels in the same order => bit-identical PCM, also when the codes (and so the lengths) change under the same shape.
+    cfg, _, _ = full_oracle
+    tok = q.Qwen3TTSSpeechTokenizer(full_dir, precision=q.PREC_FP16)
+    c1 = np.ascontiguousarray(np.transpose(_nct_codes(cfg, 2, 13, 71), (0, 2, 1)))
+    c2 = np.ascontiguousarray(np.transpose(_nct_codes(cfg, 2, 13, 72, zero_frac=0.3), (0, 2, 1)))
+    tok.set_graphs(0)
+    ref1, len1 = tok.decode(c1)
+    ref2, len2 = tok.decode(c2)
+    n0 = tok.launch_count()
+    tok.decode(c1)
+    per_call = tok.launch_count() - n0
+    tok.set_graphs(1)
+    for i, (c, ref, ln) in enumerate([(c1, ref1, len1), (c1, ref1, len1), (c2, ref2, len2), (c1, ref1, len1), (c2, ref2, len2)]):
+        n0 = tok.launch_count()
+        out, lengths = tok.decode(c)          # eager, capture + launch, replay, replay, replay
+        assert np.array_equal(out, ref) and np.array_equal(lengths, ln), i
+        assert tok.launch_count() - n0 == per_call, i
+    i16, _ = tok.decode_int16(c1)             # another output format = another graph key
+    i16b, _ = tok.decode_int16(c1)
+    assert np.array_equal(i16, i16b) and np.array_equal(i16.ravel(), q.pcm_to_int16(ref1.ravel()))
+    tok.set_graphs(-1)
+    out, _ = tok.decode(c2)                   # automatic mode: 26 frames <= 2048
+    assert np.array_equal(out, ref2)
+    tok.close()
+
+
 def test_microbatching_is_invisible(tiny_dir, tiny_oracle):
     cfg, _, _ = tiny_oracle
     codes = _nct_codes(cfg, 5, 12, 31)
