@@ -249,6 +249,13 @@ int q3tts_debug_resunit(int32_t B, int32_t rows, int32_t dil, int32_t out_snake,
 int q3tts_debug_fused_unit(int32_t B, int32_t rows, int32_t C, int32_t dil, int32_t with_operand, int32_t precision,
                            int32_t iters, float* ms_out, float* max_diff_y, float* max_diff_a);
 
+/* The attention op on its own (ST.swift:519-525: MLXFast.scaledDotProductAttention(q, k, v, scale: head_dim^-0.5, mask)) through the
+ * production dispatch, on caller-provided rows.  qkv: host float [B, T, (nh + 2 nkv) * hd] (q | k | v per row, rounded to the
+ * precision's operand type on the device); out: host float [B, T, nh * hd].  len / row_begin (may be NULL): int32 [B], valid rows
+ * [row_begin[b], len[b]) of each slot; window 0 = full (reference) attention, > 0 = causal sliding window.                     */
+int q3tts_debug_attention(const float* qkv, int32_t B, int32_t T, int32_t nh, int32_t nkv, int32_t hd, const int32_t* len,
+                          const int32_t* row_begin, int32_t window, int32_t precision, float* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -163,17 +163,24 @@ class OracleDecoder:
             v = v.repeat_interleave(nh // nkv, 1)
         if self.attn_mode == "causal_sw" and self.use_rope:
             q, k = self._rope(q, k)
-        scale = float(hd) ** -0.5                           # ST.swift:502
+        o = self.sdpa(q, k, v)
+        o = o.permute(0, 2, 1, 3).reshape(B, L, nh * hd)
+        return self.linear(o, self.w[p + ".o_proj.weight"])
+
+    def sdpa(self, q, k, v):
+        """MLXFast.scaledDotProductAttention(queries:keys:values:scale:mask:) as called at ST.swift:519-525:
+        softmax(scale * Q K^T [+ mask]) V, q/k/v [B, heads, L, head_dim], scale = head_dim^-0.5 (ST.swift:502),
+        mask nil in the reference (ST.swift:629, 763); 'causal_sw' adds the causal sliding-window mask."""
+        L, hd = q.shape[2], q.shape[3]
+        scale = float(hd) ** -0.5
         s = (self._q(q) @ self._q(k).transpose(-1, -2)) * scale
         if self.attn_mode == "causal_sw":
             i = torch.arange(L)[:, None]
             j = torch.arange(L)[None, :]
-            allowed = (j <= i) & ((i - j) < cfg.sliding_window)
+            allowed = (j <= i) & ((i - j) < self.cfg.sliding_window)
             s = s.masked_fill(~allowed, float("-inf"))
         pr = torch.softmax(s, dim=-1)
-        o = self._q(pr) @ self._q(v)
-        o = o.permute(0, 2, 1, 3).reshape(B, L, nh * hd)
-        return self.linear(o, self.w[p + ".o_proj.weight"])
+        return self._q(pr) @ self._q(v)
 
     def transformer(self, x_ntc):
         """DecoderTransformer, ST.swift:629-643; layer = ST.swift:587-601; MLP = 560-562."""

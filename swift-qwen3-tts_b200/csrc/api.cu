@@ -920,6 +920,67 @@ int q3tts_debug_fused_unit(int32_t B, int32_t rows, int32_t C, int32_t dil, int3
   });
 }
 
+// The attention kernel on its own (ST.swift:519-525: softmax(scale * Q K^T [+ mask]) V per utterance and head) on caller-provided
+// q | k | v rows: the production dispatch (launch_attention: the mma.sync kernel for 16-bit head_dim 64, the fp32 kernel otherwise).
+// qkv: host float [B, T, (nh + 2 nkv) * hd], rounded to the precision's operand type on the device; out: host float [B, T, nh * hd].
+// len / row_begin (may be NULL): valid rows [row_begin[b], len[b]) of each slot; window 0 = full attention.
+int q3tts_debug_attention(const float* qkv, int32_t B, int32_t T, int32_t nh, int32_t nkv, int32_t hd, const int32_t* len,
+                          const int32_t* row_begin, int32_t window, int32_t precision, float* out) {
+  return guarded([&]() {
+    if (!qkv || !out || B < 1 || T < 1 || nh < 1 || nkv < 1 || nh % nkv || (hd != 32 && hd != 64 && hd != 128) || window < 0)
+      return fail(Q3TTS_EINVAL, "bad attention shape");
+    if (precision < Q3TTS_PREC_FP32 || precision > Q3TTS_PREC_BF16) return fail(Q3TTS_EINVAL, "bad precision");
+    const int op = precision == Q3TTS_PREC_FP32 ? DT_F32 : (precision == Q3TTS_PREC_FP16 ? DT_F16 : DT_BF16);
+    const size_t es = op == DT_F32 ? 4 : 2;
+    const size_t ld = (size_t)(nh + 2 * nkv) * hd, n_in = (size_t)B * T * ld, n_out = (size_t)B * T * nh * hd;
+    cudaStream_t s = nullptr;
+    CUDA_OK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    std::vector<void*> allocs;
+    auto dmalloc = [&](size_t bytes) { void* d = nullptr; CUDA_OK(cudaMalloc(&d, bytes)); allocs.push_back(d); return d; };
+    float* d32 = (float*)dmalloc(n_in * 4);
+    CUDA_OK(cudaMemcpyAsync(d32, qkv, n_in * 4, cudaMemcpyHostToDevice, s));
+    CUDA_OK(cudaStreamSynchronize(s));
+    void* d_in = d32;
+    if (op != DT_F32) { d_in = dmalloc(n_in * 2); launch_convert(d32, d_in, op, (int64_t)n_in, s); }
+    void* d_out = dmalloc(n_out * es);
+    CUDA_OK(cudaMemsetAsync(d_out, 0, n_out * es, s));
+    std::vector<int> hl((size_t)B, T);
+    long long valid = 0;
+    for (int b = 0; b < B; ++b) {
+      if (len) hl[(size_t)b] = len[b];
+      if (hl[(size_t)b] < 0 || hl[(size_t)b] > T) return fail(Q3TTS_EINVAL, "len out of range");
+      valid += hl[(size_t)b];
+    }
+    int* d_len = (int*)dmalloc((size_t)B * 4);
+    CUDA_OK(cudaMemcpyAsync(d_len, hl.data(), (size_t)B * 4, cudaMemcpyHostToDevice, s));
+    int* d_beg = nullptr;
+    if (row_begin) {
+      d_beg = (int*)dmalloc((size_t)B * 4);
+      CUDA_OK(cudaMemcpyAsync(d_beg, row_begin, (size_t)B * 4, cudaMemcpyHostToDevice, s));
+    }
+    BatchGeom g{B, T, d_len, valid, d_beg};
+    launch_attention(d_in, op, d_out, op, g, nh, nkv, hd, 1.0f / sqrtf((float)hd), window, s);
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaStreamSynchronize(s));
+    if (op == DT_F32) {
+      CUDA_OK(cudaMemcpy(out, d_out, n_out * 4, cudaMemcpyDeviceToHost));
+    } else {
+      std::vector<uint16_t> h(n_out);
+      CUDA_OK(cudaMemcpy(h.data(), d_out, n_out * 2, cudaMemcpyDeviceToHost));
+      for (size_t i = 0; i < n_out; ++i) {
+        const uint16_t u = h[i];
+        if (op == DT_BF16) { const uint32_t v = (uint32_t)u << 16; std::memcpy(&out[i], &v, 4); continue; }
+        const uint32_t sgn = (u >> 15) & 1, e = (u >> 10) & 31, mant = u & 1023;
+        const float f = e == 0 ? ldexpf((float)mant, -24) : (e == 31 ? (mant ? NAN : INFINITY) : ldexpf((float)(mant | 1024), (int)e - 25));
+        out[i] = sgn ? -f : f;
+      }
+    }
+    for (void* d : allocs) cudaFree(d);
+    cudaStreamDestroy(s);
+    return (int)Q3TTS_OK;
+  });
+}
+
 // ---- codec-embedding sum --------------------------------------------------------------------------
 struct q3tts_codec_embedder {
   int device = 0, dtype = DT_BF16, groups = 0;

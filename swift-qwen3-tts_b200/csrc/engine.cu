@@ -535,7 +535,7 @@ static void run_back(Ctx& x, Plan& P, const void* to, const int64_t* d_pcm_base,
     const SnakeW* block_out = i < 3 ? &m.block_in_snake[i + 1] : &m.out_snake;
     ResUnitParams rp{};
     rp.C = Bk.cout; rp.rows_per_frame = rate * Bk.rate; rp.dil = 1;
-    const bool fused = !taps && op != DT_F32 && m.st_dtype == op && Bk.conv7[0].taps == 7 && resunit96_supported(rp, op);
+    const bool fused = op != DT_F32 && m.st_dtype == op && Bk.conv7[0].taps == 7 && resunit96_supported(rp, op);
     {
       Epi e; e.out_y = P.blk[i].X; e.y_dtype = m.st_dtype;
       if (!fused) { e.out_a = P.blk[i].A; e.snake = &Bk.act_in_next[0]; }   // the fused units activate their own input
@@ -565,6 +565,14 @@ static void run_back(Ctx& x, Plan& P, const void* to, const int64_t* d_pcm_base,
         account(x, fl, by);
       }
       a_in = P.blk[i].C;
+      if (taps) {
+        // Stage tap with the fused kernels ON: the block's last unit only writes snake_next(X'), so the tap re-runs that unit
+        // without the consumer's activation into the (now free) A buffer.  One extra launch, in tap mode only.
+        rp.x_in = bufs[2]; rp.out = P.blk[i].A; rp.ea3 = nullptr; rp.ib3 = nullptr;
+        cudaError_t err = launch_resunit96(rp, x.g, op, s);
+        if (err != cudaSuccess) throw Error(Q3TTS_ECUDA, std::string("fused residual unit launch (tap): ") + cudaGetErrorString(err));
+        count_launch(x);
+      }
     } else {
       // conv7 + conv1 of a unit as ONE tcgen05 kernel when the 1x1 conv's operand tile and weights fit in smem (C <= 192):
       // the conv7 output never goes to HBM.  The operand ping-pongs between the A and C buffers (a unit's output operand
@@ -572,7 +580,7 @@ static void run_back(Ctx& x, Plan& P, const void* to, const int64_t* d_pcm_base,
       ConvGemmParams probe{};
       probe.N = Bk.conv7[0].N; probe.Cin = Bk.conv7[0].Cin; probe.lda = probe.Cin; probe.taps = Bk.conv7[0].taps; probe.dil = 9;
       probe.bias = Bk.conv7[0].bias; probe.snake_ea = Bk.act2[0].ea; probe.act = ACT_NONE;
-      const bool fuse1 = !taps && op != DT_F32 && m.st_dtype == op && Bk.conv1[0].taps == 1 && tc2_fuse_supported(probe, op);
+      const bool fuse1 = op != DT_F32 && m.st_dtype == op && Bk.conv1[0].taps == 1 && tc2_fuse_supported(probe, op);
       void* abuf[2] = {P.blk[i].A, P.blk[i].C};
       for (int j = 0; j < 3; ++j) {
         const SnakeW* next = (j < 2) ? &Bk.act_in_next[j + 1] : block_out;
@@ -604,7 +612,7 @@ static void run_back(Ctx& x, Plan& P, const void* to, const int64_t* d_pcm_base,
       a_in = fuse1 ? abuf[1] : P.blk[i].A;        // three units: A -> C -> A -> C
     }
     static const char* kNames[4] = {"block0", "block1", "block2", "block3"};
-    tap(x, kNames[i], P.blk[i].X, m.st_dtype, rate, Bk.cout, Bk.cout);
+    tap(x, kNames[i], (fused && taps) ? P.blk[i].A : P.blk[i].X, m.st_dtype, rate, Bk.cout, Bk.cout);
     stage_end(x);
   }
 

@@ -136,6 +136,7 @@ def lib() -> C.CDLL:
         "q3tts_debug_resunit": (C.c_int, [i32, i32, i32, i32, i32, i32, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
         "q3tts_debug_conv_gemm": (C.c_int, [i32, i32, i32, i32, i32, i32, i32, i32, i32, C.POINTER(C.c_float),
                                             C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+        "q3tts_debug_attention": (C.c_int, [vp, i32, i32, i32, i32, i32, vp, vp, i32, i32, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(L, name)
@@ -195,6 +196,20 @@ def debug_resunit(B: int, rows: int, dil: int, out_snake: int = 0, precision: in
     ms, d = C.c_float(0), C.c_float(0)
     _check(lib().q3tts_debug_resunit(B, rows, dil, out_snake, precision, iters, C.byref(ms), C.byref(d)))
     return float(ms.value), float(d.value)
+
+
+def debug_attention(qkv: np.ndarray, nh: int, nkv: int, hd: int, lens=None, row_begin=None, window: int = 0,
+                    precision: int = PREC_FP16) -> np.ndarray:
+    """The attention kernel alone (production dispatch): qkv [B,T,(nh+2nkv)*hd] float32 -> [B,T,nh*hd] float32."""
+    a = np.ascontiguousarray(qkv, dtype=np.float32)
+    B, T, ld = a.shape
+    assert ld == (nh + 2 * nkv) * hd
+    out = np.zeros((B, T, nh * hd), dtype=np.float32)
+    ln = None if lens is None else np.ascontiguousarray(lens, dtype=np.int32)
+    rb = None if row_begin is None else np.ascontiguousarray(row_begin, dtype=np.int32)
+    _check(lib().q3tts_debug_attention(a.ctypes.data, B, T, nh, nkv, hd, ln.ctypes.data if ln is not None else None,
+                                       rb.ctypes.data if rb is not None else None, window, precision, out.ctypes.data))
+    return out
 
 
 class CodecEmbedder:

@@ -103,7 +103,7 @@ def decoder_tensor_specs(cfg: DecoderConfig):
     return specs
 
 
-def make_decoder_state(cfg: DecoderConfig, seed: int = DEFAULT_SEED) -> Dict[str, torch.Tensor]:
+def make_decoder_state(cfg: DecoderConfig, seed: int = DEFAULT_SEED, out_gain: float = 1.0) -> Dict[str, torch.Tensor]:
     g = torch.Generator(device="cpu")
     g.manual_seed(seed)
     state: Dict[str, torch.Tensor] = {}
@@ -121,7 +121,7 @@ def make_decoder_state(cfg: DecoderConfig, seed: int = DEFAULT_SEED) -> Dict[str
         elif kind == "wres":   # residual-branch convs: MLXNN's own U(-1/sqrt(fan_in), ..) family
             t = _uniform(g, shape, (1.0 / fan_in) ** 0.5)
         elif kind == "wout":
-            t = _uniform(g, shape, (3.0 / fan_in) ** 0.5) * OUT_CONV_GAIN
+            t = _uniform(g, shape, (3.0 / fan_in) ** 0.5) * (OUT_CONV_GAIN * out_gain)
         elif kind == "b":
             t = _normal(g, shape, 0.02)
         elif kind == "b0":
@@ -140,19 +140,20 @@ def make_decoder_state(cfg: DecoderConfig, seed: int = DEFAULT_SEED) -> Dict[str
 
 def write_checkpoint(model_dir: str, cfg: Optional[DecoderConfig] = None, seed: int = DEFAULT_SEED,
                      dtype: str = "float32", with_encoder_stub: bool = False,
-                     mlx_layout: bool = False) -> str:
+                     mlx_layout: bool = False, out_gain: float = 1.0) -> str:
     """Write ``<model_dir>/speech_tokenizer/`` and return that path.
 
     dtype 'float16' + no encoder == the 'lite' variant's on-disk form.
     ``with_encoder_stub`` adds a couple of ``encoder.*`` tensors + ``encoder_config`` that a
     decoder-only loader must ignore.  ``mlx_layout`` stores conv / transposed-conv weights
-    pre-transposed to exercise the layout heuristic's "already MLX" branch.
+    pre-transposed to exercise the layout heuristic's "already MLX" branch.  ``out_gain`` scales outConv
+    (x8 drives a good part of the PCM past [-1, 1] so that the final clip, ST.swift:781, is exercised).
     """
     from safetensors.torch import save_file
     cfg = cfg or DecoderConfig()
     st_dir = os.path.join(model_dir, "speech_tokenizer")
     os.makedirs(st_dir, exist_ok=True)
-    state = make_decoder_state(cfg, seed)
+    state = make_decoder_state(cfg, seed, out_gain)
     if mlx_layout:
         for k in list(state.keys()):
             v = state[k]
