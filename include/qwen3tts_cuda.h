@@ -24,27 +24,27 @@ extern "C" {
 
 #define Q3TTS_ABI_VERSION 1
 
-/* ---- status codes (returned by every function that returns int) ------------------------ */
-enum {
-  Q3TTS_OK = 0,
-  Q3TTS_EINVAL = 1,   /* bad argument / shape / code id >= codebook size (checked on device)  */
-  Q3TTS_EIO = 2,      /* file missing / unreadable                                            */
-  Q3TTS_EFORMAT = 3,  /* malformed config.json / safetensors, missing tensor, wrong shape     */
-  Q3TTS_ECUDA = 4,    /* CUDA error, or no sm_100 device                                      */
-  Q3TTS_ENOMEM = 5,   /* host or device allocation failed                                     */
-  Q3TTS_ESTATE = 6    /* call not valid in this state (e.g. push on a closed stream)          */
-};
+/* ---- status codes (returned by every function that returns int) ------------------------
+ * Plain integer macros, not enums: Swift imports `#define NAME <int literal>` as an Int32 constant that compares directly
+ * with the `int` these functions return (an anonymous C enum would import as `Int`, a named one as a struct with rawValue). */
+#define Q3TTS_OK 0
+#define Q3TTS_EINVAL 1   /* bad argument / shape / code id >= codebook size (checked on device)  */
+#define Q3TTS_EIO 2      /* file missing / unreadable                                            */
+#define Q3TTS_EFORMAT 3  /* malformed config.json / safetensors, missing tensor, wrong shape     */
+#define Q3TTS_ECUDA 4    /* CUDA error, or no sm_100 device                                      */
+#define Q3TTS_ENOMEM 5   /* host or device allocation failed                                     */
+#define Q3TTS_ESTATE 6   /* call not valid in this state (e.g. push on a closed stream)          */
 
 /* ---- options ----------------------------------------------------------------------------- */
-enum { Q3TTS_PREC_FP32 = 0,   /* CUDA-core fp32 everywhere: the parity anchor (PCM max-abs <= 1e-4) */
-       Q3TTS_PREC_FP16 = 1,   /* tcgen05 fp16 operands, fp32 accumulate (SNR >= 40 dB)               */
-       Q3TTS_PREC_BF16 = 2 }; /* tcgen05 bf16 operands, fp32 accumulate                              */
+#define Q3TTS_PREC_FP32 0   /* CUDA-core fp32 everywhere: the parity anchor (PCM max-abs <= 1e-4) */
+#define Q3TTS_PREC_FP16 1   /* tcgen05 fp16 operands, fp32 accumulate (SNR >= 40 dB)               */
+#define Q3TTS_PREC_BF16 2   /* tcgen05 bf16 operands, fp32 accumulate                              */
 
-enum { Q3TTS_ATTN_REFERENCE = 0, /* full, unmasked, no RoPE: what ST.swift:512-528,763 does        */
-       Q3TTS_ATTN_CAUSAL_SW = 1 }; /* causal, window = sliding_window (Cfg.swift:401): streaming    */
+#define Q3TTS_ATTN_REFERENCE 0 /* full, unmasked, no RoPE: what ST.swift:512-528,763 does          */
+#define Q3TTS_ATTN_CAUSAL_SW 1 /* causal, window = sliding_window (Cfg.swift:401): streaming       */
 
-enum { Q3TTS_CODES_BQT = 0,   /* [B,16,T]  -- Qwen3TTSSpeechTokenizerDecoder.callAsFunction, ST.swift:754 */
-       Q3TTS_CODES_BTQ = 1 }; /* [B,T,16]  -- Qwen3TTSSpeechTokenizer.decode, ST.swift:823               */
+#define Q3TTS_CODES_BQT 0   /* [B,16,T]  -- Qwen3TTSSpeechTokenizerDecoder.callAsFunction, ST.swift:754 */
+#define Q3TTS_CODES_BTQ 1   /* [B,T,16]  -- Qwen3TTSSpeechTokenizer.decode, ST.swift:823               */
 
 typedef struct q3tts_options {
   uint32_t struct_size;       /* = sizeof(q3tts_options)                                       */
@@ -182,8 +182,12 @@ int q3tts_weight_shape(const q3tts_model* m, const char* swift_key, int32_t* ndi
  * The reference has no chunked PCM streaming (Qwen3+Streaming.swift:19-120 emits one final
  * .audio); correctness here is chunk-invariance: concatenated chunk PCM == one-shot decode in
  * the same mode.  A stream is pinned to the model's GPU for life.  State per stream (device): the last 2
- * pre_conv inputs, K/V of the last sliding_window-1 frames per transformer layer, and the last 10
- * pre-transformer outputs (the conv stack is re-run over its 10-frame receptive field per chunk).   */
+ * pre_conv inputs, K/V of the last sliding_window-1 frames per transformer layer, and, for each of the 20 consumers
+ * of the conv stack that read rows in front of their tile (ConvNeXt depthwise convs, initConv, the transposed convs, every
+ * dilated conv7, outConv), the last 1-3 frames of ITS input (about 4 MB per stream in fp16).  A push computes the conv stack
+ * over [3 context frames | new frames] and restores each consumer's context rows from that state.
+ * Code ids are validated on the host before anything is enqueued: a rejected push (Q3TTS_EINVAL) advances no stream.
+ * q3tts_model_free on a model with open streams only marks it; the last q3tts_stream_close deletes it.              */
 int q3tts_stream_open(q3tts_model* m, q3tts_stream** out);
 /* codes: int32 [n_frames,16]; pcm_out: float [n_frames*total_upsample].                        */
 int q3tts_stream_push(q3tts_stream* s, const int32_t* codes, int32_t n_frames, float* pcm_out);
@@ -198,6 +202,29 @@ void q3tts_stream_close(q3tts_stream* s);
  * Longest-processing-time-first partition of utterances over `n_parts` GPUs by frame count;
  * part_out[i] in [0,n_parts).  Deterministic (ties by index) so every rank computes the same map. */
 int q3tts_partition_lpt(const int64_t* frames, int32_t n_utterances, int32_t n_parts, int32_t* part_out);
+
+/* ---- multi-GPU pool: one worker thread + CUDA context + model replica per GPU of ONE box (north_star (d)) --------
+ * The reference decodes one utterance at a time on one device (Q3.swift:744, 951, 1186); a batch of independent utterances
+ * shards by utterance with no collective.  q3tts_pool_open loads the checkpoint once per device
+ * (`devices` = NULL: every sm_100 device, else n_devices ordinals; opts->device is ignored).  A decode call partitions the
+ * utterances with q3tts_partition_lpt, hands each worker its share, and returns when every worker has written its PCM into
+ * the caller's buffers (pageable or pinned; each worker pipelines its own copies).  Results are bit-identical to
+ * q3tts_decode_varlen on one GPU: an utterance's PCM does not depend on which utterances share its launch chain.
+ * Calls on one pool are serialised.  Errors: the first failing worker's status and message.                       */
+typedef struct q3tts_pool q3tts_pool;
+int q3tts_pool_open(const char* speech_tokenizer_dir, const q3tts_options* opts, const int32_t* devices,
+                    int32_t n_devices, q3tts_pool** out);
+void q3tts_pool_close(q3tts_pool* p);
+int32_t q3tts_pool_size(const q3tts_pool* p);
+int q3tts_pool_decode_varlen(q3tts_pool* p, const int32_t* codes_packed, const int64_t* frame_offsets,
+                             int32_t n_utterances, float* pcm_out, int32_t* lengths_out);
+int q3tts_pool_decode_varlen_int16(q3tts_pool* p, const int32_t* codes_packed, const int64_t* frame_offsets,
+                                   int32_t n_utterances, int16_t* pcm_out, int32_t* lengths_out);
+/* Uniform batch [B,T,16] / [B,16,T] split by utterance over the pool (q3tts_decode semantics). */
+int q3tts_pool_decode(q3tts_pool* p, const int32_t* codes, int32_t B, int32_t T, int32_t layout, float* pcm_out,
+                      int32_t* lengths_out);
+/* Per worker, for the most recent pool call: wall milliseconds spent in its decode and frames it was given. */
+int q3tts_pool_last_stats(const q3tts_pool* p, float* ms_out, int64_t* frames_out, int32_t cap);
 
 /* ---- PCM post-processing (caller-side semantics of the reference) ------------------------------
  * q3tts_trim_length: Q3.swift:746-752 (valid_len in (0,n) trims, else keeps n).

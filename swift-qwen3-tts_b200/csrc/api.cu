@@ -4,35 +4,25 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <memory>
 #include <numeric>
 
-#include "../../include/qwen3tts_cuda.h"
-#include "engine.hpp"
+#include "api_internal.hpp"
 
 using namespace q3;
 
-namespace {
+namespace q3api {
 thread_local std::string g_last_error;
 
 int fail(int code, const std::string& msg) {
   g_last_error = msg;
   return code;
 }
+}  // namespace q3api
+using namespace q3api;
 
-template <typename F>
-int guarded(F&& f) {
-  try {
-    return f();
-  } catch (const Error& e) {
-    return fail(e.code, e.what());
-  } catch (const std::bad_alloc&) {
-    return fail(Q3TTS_ENOMEM, "host allocation failed");
-  } catch (const std::exception& e) {
-    return fail(Q3TTS_EINVAL, e.what());
-  }
-}
-
+namespace {
 #define CUDA_OK(expr)                                                                                   \
   do {                                                                                                  \
     cudaError_t _e = (expr);                                                                            \
@@ -63,8 +53,10 @@ int64_t frames_cap(const Model& m) {
 
 // Enqueue the decode of `utts` (any order).  d_codes / d_pcm / d_lengths are device pointers.
 // Metadata goes through a pinned staging buffer and is re-uploaded only when it changes.
+// after_mb(first, count): called after the chain of each micro-batch has been enqueued; [first, first+count) index the utterances in
+// decreasing-length order (stable), i.e. `utts` itself when the caller passes it sorted that way.
 void decode_core(Model& m, const int32_t* d_codes, std::vector<Utt> utts, int64_t sq, int64_t st, float* d_pcm,
-                 int32_t* d_lengths, cudaStream_t s) {
+                 int32_t* d_lengths, cudaStream_t s, const std::function<void(int, int)>& after_mb = nullptr) {
   const int n = (int)utts.size();
   if (n == 0) return;
   // lengths first, in the caller's order (ST.swift:831-833)
@@ -145,6 +137,7 @@ void decode_core(Model& m, const int32_t* d_codes, std::vector<Utt> utts, int64_
       }
       m.launch_prof.clear();
     }
+    if (after_mb) after_mb(mb.first, mb.B);
   }
   if (d_lengths) {
     launch_lengths(d_codes, (const int64_t*)(m.d_meta + o_cbo), st, (const int*)(m.d_meta + o_lo), n,
@@ -165,8 +158,125 @@ void check_device_errors(Model& m, cudaStream_t s) {
 
 }  // namespace
 
-struct q3tts_model { Model* m; };
+namespace q3api {
+// Pinned staging of the host-buffer paths (grow-only, owned by the model).
+static void ensure_pinned(char** p, size_t* cap, size_t bytes) {
+  if (bytes <= *cap && *p) return;
+  if (*p) cudaFreeHost(*p);
+  *p = nullptr; *cap = 0;
+  CUDA_OK(cudaMallocHost(p, std::max<size_t>(bytes, 4096)));
+  *cap = bytes;
+}
+static bool is_pinned(const void* p) {
+  cudaPointerAttributes a{};
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+
+void decode_host_list(Model& m, const int32_t* codes, int32_t layout, int32_t T_uniform, std::vector<HostUtt> utts, void* pcm_out,
+                      bool i16, int32_t* lengths_out) {
+  const int n = (int)utts.size();
+  if (n == 0) return;
+  std::lock_guard<std::mutex> lock(m.mu);
+  CUDA_OK(cudaSetDevice(m.device));
+  struct Fmt { Model& m; Fmt(Model& mm, bool v) : m(mm) { m.pcm_i16 = v; } ~Fmt() { m.pcm_i16 = false; } } fmt(m, i16);
+  const int Q = m.cfg.num_quantizers;
+  const int64_t up = m.cfg.total_upsample;
+  const size_t ss = i16 ? 2 : 4;                       // bytes per PCM sample on the way out
+  // decreasing length (stable): decode_core's own order, so device PCM of a micro-batch is one contiguous range
+  std::stable_sort(utts.begin(), utts.end(), [](const HostUtt& a, const HostUtt& b) { return a.frames > b.frames; });
+  int64_t total = 0;
+  for (const HostUtt& u : utts) total += u.frames;
+  if (total == 0) {
+    if (lengths_out) for (const HostUtt& u : utts) lengths_out[u.orig] = 0;
+    return;
+  }
+  cudaStream_t s = m.stream;
+  chain_begin(m, s);
+  ensure_dev(&m.d_codes, &m.d_codes_cap, (size_t)total * Q * 4);
+  ensure_dev(&m.d_pcm, &m.d_pcm_cap, (size_t)total * up * 4);
+  ensure_dev(&m.d_lengths, &m.d_lengths_cap, (size_t)n * 4);
+  if (!m.copy_stream) {
+    CUDA_OK(cudaStreamCreateWithFlags(&m.copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) { CUDA_OK(cudaEventCreateWithFlags(&m.mb_done[i], cudaEventDisableTiming)); CUDA_OK(cudaEventCreateWithFlags(&m.d2h_done[i], cudaEventDisableTiming)); }
+  }
+  // codes: packed in sorted order through pinned staging (a few MB), one H2D
+  ensure_pinned(&m.h_codes, &m.h_codes_cap, (size_t)total * Q * 4);
+  std::vector<Utt> dev((size_t)n);
+  {
+    int64_t f = 0;
+    for (int i = 0; i < n; ++i) {
+      const HostUtt& u = utts[(size_t)i];
+      if (u.frames > 0) std::memcpy(m.h_codes + (size_t)f * Q * 4, codes + u.code_off, (size_t)u.frames * Q * 4);
+      dev[(size_t)i] = Utt{f * Q, f * up, u.frames, i};
+      f += u.frames;
+    }
+  }
+  CUDA_OK(cudaMemcpyAsync(m.d_codes, m.h_codes, (size_t)total * Q * 4, cudaMemcpyHostToDevice, s));
+  const int64_t sq = layout == Q3TTS_CODES_BQT ? T_uniform : 1, st = layout == Q3TTS_CODES_BQT ? 1 : Q;
+  const bool direct = is_pinned(pcm_out);              // pinned / registered destination: DMA straight into it
+  struct Pending { int first = 0, count = 0, buf = 0; bool live = false; } pend;
+  auto scatter = [&](const Pending& pd) {               // pageable destination: pinned staging -> the caller's buffer
+    CUDA_OK(cudaEventSynchronize(m.d2h_done[pd.buf]));
+    if (direct) return;
+    const char* src = m.h_pcm[pd.buf];
+    for (int i = pd.first; i < pd.first + pd.count; ++i) {
+      const HostUtt& u = utts[(size_t)i];
+      const size_t bytes = (size_t)u.frames * up * ss;
+      std::memcpy((char*)pcm_out + (size_t)u.pcm_off * ss, src, bytes);
+      src += bytes;
+    }
+  };
+  int k = 0;
+  auto after_mb = [&](int first, int count) {
+    const int buf = k & 1;
+    CUDA_OK(cudaEventRecord(m.mb_done[buf], s));
+    CUDA_OK(cudaStreamWaitEvent(m.copy_stream, m.mb_done[buf], 0));
+    int64_t f0 = dev[(size_t)first].pcm_base, fr = 0;
+    for (int i = first; i < first + count; ++i) fr += utts[(size_t)i].frames;
+    const char* d_src = (const char*)m.d_pcm + (size_t)f0 * ss;   // the tail wrote `ss`-byte samples at sample offset pcm_base
+    if (direct) {
+      // coalesce neighbours whose destinations are contiguous too (a uniform batch is ONE copy)
+      int i = first;
+      while (i < first + count) {
+        int j = i;
+        size_t bytes = (size_t)utts[(size_t)i].frames * up * ss;
+        while (j + 1 < first + count && utts[(size_t)j + 1].pcm_off == utts[(size_t)j].pcm_off + (int64_t)utts[(size_t)j].frames * up) {
+          ++j;
+          bytes += (size_t)utts[(size_t)j].frames * up * ss;
+        }
+        CUDA_OK(cudaMemcpyAsync((char*)pcm_out + (size_t)utts[(size_t)i].pcm_off * ss, d_src, bytes, cudaMemcpyDeviceToHost, m.copy_stream));
+        d_src += bytes;
+        i = j + 1;
+      }
+    } else {
+      ensure_pinned(&m.h_pcm[buf], &m.h_pcm_cap[buf], (size_t)fr * up * ss);
+      CUDA_OK(cudaMemcpyAsync(m.h_pcm[buf], d_src, (size_t)fr * up * ss, cudaMemcpyDeviceToHost, m.copy_stream));
+    }
+    CUDA_OK(cudaEventRecord(m.d2h_done[buf], m.copy_stream));
+    // the previous micro-batch's copy has had a whole chain's worth of enqueueing to finish: drain it now, while this chain runs
+    if (pend.live) scatter(pend);
+    pend = Pending{first, count, buf, true};
+    ++k;
+  };
+  // NOTE on d_pcm addressing: the tail kernels address samples by INDEX (pcm_base + t) in the output's own sample size, so a
+  // micro-batch occupies bytes [pcm_base * ss, ...) of d_pcm in either format.
+  decode_core(m, m.d_codes, dev, sq, st, m.d_pcm, lengths_out ? m.d_lengths : nullptr, s, after_mb);
+  if (lengths_out) {
+    ensure_pinned(&m.h_len, &m.h_len_cap, (size_t)n * 4);
+    CUDA_OK(cudaMemcpyAsync(m.h_len, m.d_lengths, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+  }
+  // the next chain (any stream) must not overwrite d_pcm before the last copy-out has read it
+  CUDA_OK(cudaStreamWaitEvent(s, m.d2h_done[(k - 1) & 1], 0));
+  chain_end(m, s);
+  if (pend.live) scatter(pend);
+  check_device_errors(m, s);                            // synchronises s (and, through the wait above, the copy stream)
+  if (lengths_out) for (int i = 0; i < n; ++i) lengths_out[utts[(size_t)i].orig] = ((const int32_t*)m.h_len)[i];
+}
+}  // namespace q3api
+
 struct q3tts_stream { q3tts_model* owner; StreamState state; };
+namespace { std::mutex g_lifetime_mu; }
 
 extern "C" {
 
@@ -222,7 +332,8 @@ int q3tts_model_load(const char* dir, const q3tts_options* opts, q3tts_model** o
       cudaGetLastError();
       return fail(Q3TTS_ECUDA, "no CUDA device: libqwen3tts_cuda has no CPU fallback");
     }
-    std::unique_ptr<q3tts_model> h(new q3tts_model{nullptr});
+    std::unique_ptr<q3tts_model> h(new q3tts_model());
+    h->m = nullptr;
     h->m = model_create(ck, o);
     *out = h.release();
     return (int)Q3TTS_OK;
@@ -231,6 +342,10 @@ int q3tts_model_load(const char* dir, const q3tts_options* opts, q3tts_model** o
 
 void q3tts_model_free(q3tts_model* h) {
   if (!h) return;
+  {
+    std::lock_guard<std::mutex> life(g_lifetime_mu);
+    if (h->open_streams > 0) { h->zombie = true; return; }   // deleted by the last q3tts_stream_close
+  }
   delete h->m;
   delete h;
 }
@@ -262,34 +377,24 @@ static int decode_common(q3tts_model* h, const int32_t* codes, int32_t B, int32_
     if (B == 0 || T == 0) return (int)Q3TTS_OK;   // empty input: nothing to decode
     if (!codes || !pcm) return fail(Q3TTS_EINVAL, "NULL buffer");
     Model& m = *h->m;
+    const int Q = m.cfg.num_quantizers;
+    const int64_t up = m.cfg.total_upsample;
+    if (!device_ptrs) {
+      std::vector<HostUtt> utts((size_t)B);
+      for (int b = 0; b < B; ++b) utts[(size_t)b] = HostUtt{(int64_t)b * T * Q, (int64_t)b * T * up, T, b};
+      decode_host_list(m, codes, layout, T, std::move(utts), pcm, i16, lengths);
+      return (int)Q3TTS_OK;
+    }
     std::lock_guard<std::mutex> lock(m.mu);
     CUDA_OK(cudaSetDevice(m.device));
     PcmFormat fmt(m, i16);
-    const int Q = m.cfg.num_quantizers;
-    const int64_t up = m.cfg.total_upsample;
-    const size_t n_codes = (size_t)B * T * Q, n_pcm = (size_t)B * T * up;
-    cudaStream_t s = device_ptrs ? user_stream : m.stream;
-    const int32_t* d_codes = codes;
-    float* d_pcm = pcm;
-    int32_t* d_len = lengths;
-    if (!device_ptrs) {
-      ensure_dev(&m.d_codes, &m.d_codes_cap, n_codes * 4);
-      ensure_dev(&m.d_pcm, &m.d_pcm_cap, n_pcm * 4);
-      ensure_dev(&m.d_lengths, &m.d_lengths_cap, (size_t)B * 4);
-      CUDA_OK(cudaMemcpyAsync(m.d_codes, codes, n_codes * 4, cudaMemcpyHostToDevice, s));
-      d_codes = m.d_codes;
-      d_pcm = m.d_pcm;
-      d_len = lengths ? m.d_lengths : nullptr;
-    }
+    cudaStream_t s = user_stream;
+    chain_begin(m, s);   // the workspace, d_meta and d_err are shared with the previous chain, which may have run on another stream
     std::vector<Utt> utts((size_t)B);
     for (int b = 0; b < B; ++b) utts[(size_t)b] = Utt{(int64_t)b * T * Q, (int64_t)b * T * up, T, b};
     const int64_t sq = layout == Q3TTS_CODES_BQT ? T : 1, st = layout == Q3TTS_CODES_BQT ? 1 : Q;
-    decode_core(m, d_codes, utts, sq, st, d_pcm, d_len, s);
-    if (!device_ptrs) {
-      CUDA_OK(cudaMemcpyAsync(pcm, m.d_pcm, n_pcm * (i16 ? 2 : 4), cudaMemcpyDeviceToHost, s));
-      if (lengths) CUDA_OK(cudaMemcpyAsync(lengths, m.d_lengths, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
-      check_device_errors(m, s);
-    }
+    decode_core(m, codes, utts, sq, st, pcm, lengths, s);
+    chain_end(m, s);
     return (int)Q3TTS_OK;
   });
 }
@@ -315,7 +420,9 @@ int q3tts_sync(q3tts_model* h, void* stream) {
     Model& m = *h->m;
     std::lock_guard<std::mutex> lock(m.mu);
     CUDA_OK(cudaSetDevice(m.device));
+    chain_begin(m, (cudaStream_t)stream);
     check_device_errors(m, (cudaStream_t)stream);
+    chain_end(m, (cudaStream_t)stream);
     return (int)Q3TTS_OK;
   });
 }
@@ -333,9 +440,6 @@ static int decode_varlen_common(q3tts_model* h, const int32_t* codes_packed, con
     if (frame_offsets[0] != 0) return fail(Q3TTS_EINVAL, "frame_offsets[0] must be 0");
     const int64_t total = frame_offsets[n];
     Model& m = *h->m;
-    std::lock_guard<std::mutex> lock(m.mu);
-    CUDA_OK(cudaSetDevice(m.device));
-    PcmFormat fmt(m, i16);
     if (total == 0) {
       if (lengths_out) std::memset(lengths_out, 0, (size_t)n * 4);
       return (int)Q3TTS_OK;
@@ -343,18 +447,10 @@ static int decode_varlen_common(q3tts_model* h, const int32_t* codes_packed, con
     if (!codes_packed || !pcm_out) return fail(Q3TTS_EINVAL, "NULL buffer");
     const int Q = m.cfg.num_quantizers;
     const int64_t up = m.cfg.total_upsample;
-    cudaStream_t s = m.stream;
-    ensure_dev(&m.d_codes, &m.d_codes_cap, (size_t)total * Q * 4);
-    ensure_dev(&m.d_pcm, &m.d_pcm_cap, (size_t)total * up * 4);
-    ensure_dev(&m.d_lengths, &m.d_lengths_cap, (size_t)n * 4);
-    CUDA_OK(cudaMemcpyAsync(m.d_codes, codes_packed, (size_t)total * Q * 4, cudaMemcpyHostToDevice, s));
-    std::vector<Utt> utts((size_t)n);
+    std::vector<HostUtt> utts((size_t)n);
     for (int i = 0; i < n; ++i)
-      utts[(size_t)i] = Utt{frame_offsets[i] * Q, frame_offsets[i] * up, (int)(frame_offsets[i + 1] - frame_offsets[i]), i};
-    decode_core(m, m.d_codes, utts, 1, Q, m.d_pcm, lengths_out ? m.d_lengths : nullptr, s);
-    CUDA_OK(cudaMemcpyAsync(pcm_out, m.d_pcm, (size_t)total * up * (i16 ? 2 : 4), cudaMemcpyDeviceToHost, s));
-    if (lengths_out) CUDA_OK(cudaMemcpyAsync(lengths_out, m.d_lengths, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
-    check_device_errors(m, s);
+      utts[(size_t)i] = HostUtt{frame_offsets[i] * Q, frame_offsets[i] * up, (int)(frame_offsets[i + 1] - frame_offsets[i]), i};
+    decode_host_list(m, codes_packed, Q3TTS_CODES_BTQ, 0, std::move(utts), pcm_out, i16, lengths_out);
     return (int)Q3TTS_OK;
   });
 }
@@ -446,7 +542,19 @@ static int stream_push_common(q3tts_stream* const* streams, int32_t n_streams, c
     CUDA_OK(cudaSetDevice(m.device));
     const int Q = m.cfg.num_quantizers;
     const int64_t up = m.cfg.total_upsample;
+    // Code ids are checked HERE, before anything is enqueued: a push commits KV / conv state for every stream of the batch, so a bad
+    // id found on the device afterwards would leave all of them advanced past frames whose PCM the caller never got.
+    for (int i = 0; i < n_streams; ++i)
+      for (int64_t t = 0; t < n_frames[i]; ++t)
+        for (int qi = 0; qi < Q; ++qi) {
+          const int32_t c = codes[i][t * Q + qi];
+          const int32_t lim = qi < m.cfg.num_semantic_quantizers ? m.cfg.semantic_codebook_size : m.cfg.codebook_size;
+          if (c < 0 || c >= lim)
+            return fail(Q3TTS_EINVAL, "a code id is outside its codebook (stream " + std::to_string(i) + ", frame " + std::to_string(t) +
+                                          ", codebook " + std::to_string(qi) + "); no stream of this push has been advanced");
+        }
     cudaStream_t s = m.stream;
+    chain_begin(m, s);
     ensure_dev(&m.d_codes, &m.d_codes_cap, (size_t)total * Q * 4);
     ensure_dev(&m.d_pcm, &m.d_pcm_cap, (size_t)total * up * 4);
     std::vector<StreamState*> st((size_t)n_streams);
@@ -464,6 +572,7 @@ static int stream_push_common(q3tts_stream* const* streams, int32_t n_streams, c
         CUDA_OK(cudaMemcpyAsync(pcm_out[i], m.d_pcm + off * up, (size_t)n_frames[i] * up * 4, cudaMemcpyDeviceToHost, s));
       off += n_frames[i];
     }
+    chain_end(m, s);
     check_device_errors(m, s);
     return (int)Q3TTS_OK;
   });
@@ -481,6 +590,11 @@ int q3tts_stream_open(q3tts_model* h, q3tts_stream** out) {
     CUDA_OK(cudaSetDevice(m.device));
     std::unique_ptr<q3tts_stream> st(new q3tts_stream{h, StreamState{}});
     stream_state_alloc(m, st->state);
+    {
+      std::lock_guard<std::mutex> life(g_lifetime_mu);
+      if (h->zombie) { stream_state_free(m, st->state); return fail(Q3TTS_ESTATE, "the model has been freed"); }
+      ++h->open_streams;
+    }
     *out = st.release();
     return (int)Q3TTS_OK;
   });
@@ -502,12 +616,20 @@ int64_t q3tts_stream_frames(const q3tts_stream* s) { return s && s->owner ? s->s
 
 void q3tts_stream_close(q3tts_stream* s) {
   if (!s) return;
-  if (s->owner) {
-    std::lock_guard<std::mutex> lock(s->owner->m->mu);
-    cudaStreamSynchronize(s->owner->m->stream);
-    stream_state_free(*s->owner->m, s->state);
+  q3tts_model* owner = s->owner;
+  bool last_of_zombie = false;
+  if (owner) {
+    {
+      std::lock_guard<std::mutex> lock(owner->m->mu);
+      cudaSetDevice(owner->m->device);
+      cudaStreamSynchronize(owner->m->stream);
+      stream_state_free(*owner->m, s->state);
+    }
+    std::lock_guard<std::mutex> life(g_lifetime_mu);
+    last_of_zombie = --owner->open_streams == 0 && owner->zombie;
   }
   delete s;
+  if (last_of_zombie) { delete owner->m; delete owner; }
 }
 
 // ---- scheduler ------------------------------------------------------------------------------------------

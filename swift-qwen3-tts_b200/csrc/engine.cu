@@ -39,7 +39,25 @@ Model::~Model() {
   for (auto& p : prof) { if (p.ev0) cudaEventDestroy(p.ev0); if (p.ev1) cudaEventDestroy(p.ev1); }
   for (auto& lp : launch_prof) { if (lp.ev0) cudaEventDestroy(lp.ev0); if (lp.ev1) cudaEventDestroy(lp.ev1); }
   for (cudaEvent_t e : event_pool) cudaEventDestroy(e);
+  if (chain_done) cudaEventDestroy(chain_done);
+  if (copy_stream) cudaStreamDestroy(copy_stream);
+  for (int i = 0; i < 2; ++i) {
+    if (mb_done[i]) cudaEventDestroy(mb_done[i]);
+    if (d2h_done[i]) cudaEventDestroy(d2h_done[i]);
+    if (h_pcm[i]) cudaFreeHost(h_pcm[i]);
+  }
+  if (h_codes) cudaFreeHost(h_codes);
+  if (h_len) cudaFreeHost(h_len);
   if (stream) cudaStreamDestroy(stream);
+}
+
+void chain_begin(Model& m, cudaStream_t s) {
+  if (m.has_chain && m.last_stream != s) CUDA_OK(cudaStreamWaitEvent(s, m.chain_done, 0));
+}
+void chain_end(Model& m, cudaStream_t s) {
+  CUDA_OK(cudaEventRecord(m.chain_done, s));
+  m.last_stream = s;
+  m.has_chain = true;
 }
 
 // ---- upload helpers -----------------------------------------------------------------------------
@@ -161,6 +179,7 @@ Model* model_create(const Checkpoint& ck, const q3tts_options& opts) {
   m.st_dtype = m.op_dtype;
   if (const char* e = getenv("Q3TTS_STREAM_F32")) { if (e[0] == '1') m.st_dtype = DT_F32; }   // keep the blocks' residual stream in fp32
   CUDA_OK(cudaStreamCreateWithFlags(&m.stream, cudaStreamNonBlocking));
+  CUDA_OK(cudaEventCreateWithFlags(&m.chain_done, cudaEventDisableTiming));
   const q3tts_config& c = m.cfg;
   if (c.latent_dim > 2048) throw Error(Q3TTS_EFORMAT, "latent_dim > 2048 is not supported");
   if (c.head_dim != 32 && c.head_dim != 64 && c.head_dim != 128) throw Error(Q3TTS_EFORMAT, "head_dim must be 32, 64 or 128");

@@ -64,6 +64,12 @@ struct Model {
   int st_dtype = DT_F32;      // stream dtype inside the decoder blocks
   cudaStream_t stream = nullptr;
   std::mutex mu;
+  // Every launch chain shares the workspace arena, d_meta and d_err.  The mutex serialises host-side enqueueing only, so chains on
+  // DIFFERENT streams (q3tts_decode_device takes the caller's) are ordered on the device through this event: recorded at the end of
+  // every chain, waited for by the next chain when its stream differs.
+  cudaEvent_t chain_done = nullptr;
+  cudaStream_t last_stream = nullptr;
+  bool has_chain = false;
 
   // weights
   std::vector<void*> allocs;              // every device allocation made for weights
@@ -94,6 +100,12 @@ struct Model {
   long long graph_max_frames = 2048;
   char* stream_hook_h = nullptr; char* stream_hook_d = nullptr; size_t stream_hook_cap = 0;   // streaming: per-consumer copy lists
   float* d_pcm = nullptr;     size_t d_pcm_cap = 0;
+  // host-buffer decodes: copy-out stream + pinned staging (codes in; PCM out, double-buffered per micro-batch; lengths)
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t mb_done[2] = {nullptr, nullptr}, d2h_done[2] = {nullptr, nullptr};
+  char* h_codes = nullptr;    size_t h_codes_cap = 0;
+  char* h_pcm[2] = {nullptr, nullptr}; size_t h_pcm_cap[2] = {0, 0};
+  char* h_len = nullptr;      size_t h_len_cap = 0;
   bool pcm_i16 = false;       // this call's tail writes int16 PCM into the (float-sized) output buffer
   int32_t* d_lengths = nullptr; size_t d_lengths_cap = 0;
   char* d_meta = nullptr;     size_t d_meta_cap = 0;     // len_frames / code_base / pcm_base per micro-batch
@@ -150,6 +162,10 @@ void run_stream_batch(Model& m, StreamState* const* streams, int S, const int32_
                       float* d_pcm_out, cudaStream_t s);
 
 struct MicroBatch { int first = 0, B = 0, Tmax = 0; };   // utterances [first, first+B) of the sorted order
+
+// Order a new launch chain on `s` behind the previous chain of this model (no-op when it ran on the same stream), and mark its end.
+void chain_begin(Model& m, cudaStream_t s);
+void chain_end(Model& m, cudaStream_t s);
 
 // Build a model from a parsed checkpoint (uploads weights).  Throws q3::Error.
 Model* model_create(const Checkpoint& ck, const q3tts_options& opts);

@@ -513,9 +513,8 @@ tail_kernel(const TI* a, int64_t a_bstride, const float* w, float bias, int C, f
 }
 
 // 16-bit operand, C in {72, 96}: one thread per output sample, the 7-row x C window staged once per CTA in shared
-// memory with 128-bit loads (row stride C+8 halves = conflict-free LDS.128), weights as FFMA constant operands.
+// memory with 128-bit loads (row stride C+8 halves = conflict-free LDS.128), weights in shared memory (broadcast reads).
 constexpr int TAIL_TILE = 192;
-__constant__ float c_tail_w[7 * 128];
 
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8], __half) {
   const float2 a = __half22float2(*(const __half2*)&u.x), b = __half22float2(*(const __half2*)&u.y),
@@ -530,15 +529,17 @@ __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8], __nv_bflo
 
 template <typename T16, int C>
 __global__ void __launch_bounds__(TAIL_TILE)
-tail16_kernel(const T16* a, int64_t a_bstride, float bias, float* pcm, const int64_t* pcm_base, float* tap,
-              int64_t tap_bstride, BatchGeom g, int rows_per_frame, int tiles_per_utt) {
+tail16_kernel(const T16* a, int64_t a_bstride, const float* __restrict__ w /*[7][C], the model's own buffer*/, float bias, float* pcm,
+              const int64_t* pcm_base, float* tap, int64_t tap_bstride, BatchGeom g, int rows_per_frame, int tiles_per_utt) {
   constexpr int STRIDE = C + 8, ROWS = TAIL_TILE + 6, V = C / 8;
   __shared__ __align__(16) T16 tile[ROWS * STRIDE];
+  __shared__ float ws[7 * C];   // per-CTA copy of this model's weights (a process-wide __constant__ would be shared by all models)
   const int b = blockIdx.x / tiles_per_utt;
   const int64_t t0 = (int64_t)(blockIdx.x % tiles_per_utt) * TAIL_TILE;
   const int64_t slot_rows = (int64_t)g.Tmax * rows_per_frame, valid = (int64_t)g.len_frames[b] * rows_per_frame;
   if (t0 >= valid) return;
   const T16* ab = a + (int64_t)b * a_bstride;
+  for (int i = threadIdx.x; i < 7 * C; i += TAIL_TILE) ws[i] = __ldg(w + i);
   for (int idx = threadIdx.x; idx < ROWS * V; idx += TAIL_TILE) {
     const int row = idx / V, c8 = idx % V;
     const int64_t tin = t0 - 6 + row;
@@ -556,7 +557,7 @@ tail16_kernel(const T16* a, int64_t a_bstride, float bias, float* pcm, const int
       float f[8];
       unpack8(*(const uint4*)&tile[(threadIdx.x + j) * STRIDE + c8 * 8], f, T16());
 #pragma unroll
-      for (int e = 0; e < 8; ++e) acc = fmaf(c_tail_w[j * C + c8 * 8 + e], f[e], acc);
+      for (int e = 0; e < 8; ++e) acc = fmaf(ws[j * C + c8 * 8 + e], f[e], acc);
     }
   }
   if (t < valid) {
@@ -575,10 +576,9 @@ void launch_tail(const void* a, int a_dtype, int64_t a_bstride, const float* w, 
     return;
   }
   if (a_dtype != DT_F32 && (C == 96 || C == 72)) {
-    cudaMemcpyToSymbolAsync(c_tail_w, w, (size_t)7 * C * sizeof(float), 0, cudaMemcpyDeviceToDevice, s);
     const int tiles = (int)(((int64_t)g.Tmax * rows_per_frame + TAIL_TILE - 1) / TAIL_TILE);
     const unsigned blocks = (unsigned)(g.B * tiles);
-#define Q3_TAIL(T, CC) tail16_kernel<T, CC><<<blocks, TAIL_TILE, 0, s>>>((const T*)a, a_bstride, bias, pcm, pcm_base, tap, tap_bstride, g, rows_per_frame, tiles)
+#define Q3_TAIL(T, CC) tail16_kernel<T, CC><<<blocks, TAIL_TILE, 0, s>>>((const T*)a, a_bstride, w, bias, pcm, pcm_base, tap, tap_bstride, g, rows_per_frame, tiles)
     if (a_dtype == DT_F16) { if (C == 96) Q3_TAIL(__half, 96); else Q3_TAIL(__half, 72); }
     else { if (C == 96) Q3_TAIL(__nv_bfloat16, 96); else Q3_TAIL(__nv_bfloat16, 72); }
 #undef Q3_TAIL

@@ -578,11 +578,13 @@ cudaError_t launch_resunit96(const ResUnitParams& p, const BatchGeom& g, int op_
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  static std::once_flag once;
-  std::call_once(once, []() {
-    cudaFuncSetAttribute(resunit96_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(resunit96_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  static tc::PerDeviceOnce optin;
+  const cudaError_t oe = optin.ensure([]() {
+    cudaError_t e = cudaFuncSetAttribute(resunit96_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(resunit96_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    return e;
   });
+  if (oe != cudaSuccess) return oe;
   if (op_dtype == DT_F16) return cudaLaunchKernelEx(&cfg, resunit96_kernel<__half>, map_main, map_halo, map_w7, map_w1, map_res, map_out, q);
   return cudaLaunchKernelEx(&cfg, resunit96_kernel<__nv_bfloat16>, map_main, map_halo, map_w7, map_w1, map_res, map_out, q);
 }

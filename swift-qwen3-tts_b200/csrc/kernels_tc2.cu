@@ -775,13 +775,15 @@ int env_int(const char* name, int dflt) {
 template <typename T16>
 cudaError_t launch_variant(const cudaLaunchConfig_t& cfg, bool pair, bool block, const CUtensorMap& ma, const CUtensorMap& mw,
                            const CUtensorMap& my, const CUtensorMap& mo, const CUtensorMap& mw2, const Tc2Params& q, int yf) {
-  static std::once_flag once;
-  std::call_once(once, []() {
-    cudaFuncSetAttribute(conv_gemm_tc2_kernel<T16, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(conv_gemm_tc2_kernel<T16, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(conv_gemm_tc2_kernel<T16, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(conv_gemm_tc2_kernel<T16, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  static tc::PerDeviceOnce optin;   // one per T16 instantiation
+  const cudaError_t oe = optin.ensure([]() {
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc2_kernel<T16, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_gemm_tc2_kernel<T16, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_gemm_tc2_kernel<T16, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_gemm_tc2_kernel<T16, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    return e;
   });
+  if (oe != cudaSuccess) return oe;
   if (pair) {
     if (block) return cudaLaunchKernelEx(&cfg, conv_gemm_tc2_kernel<T16, true, true>, ma, mw, my, mo, mw2, q, yf);
     return cudaLaunchKernelEx(&cfg, conv_gemm_tc2_kernel<T16, true, false>, ma, mw, my, mo, mw2, q, yf);

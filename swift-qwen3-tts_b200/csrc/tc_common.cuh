@@ -7,8 +7,32 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
+
 namespace q3 {
 namespace tc {
+
+// Host: the dynamic-shared-memory opt-in (cudaFuncAttributeMaxDynamicSharedMemorySize) is a property of a kernel ON ONE DEVICE.
+// One handle per GPU in one process launches the same kernels on every device, so the opt-in is made once per
+// (kernel set, device) -- a process-wide once would leave devices 1..N-1 at the 48 KB default and their launches would fail.
+// `set` applies the attributes on the CURRENT device and returns the first error.
+struct PerDeviceOnce {
+  std::mutex mu;
+  unsigned long long done[4] = {0, 0, 0, 0};   // 256 device ordinals
+  template <typename F>
+  cudaError_t ensure(F&& set) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lock(mu);
+    unsigned long long& word = done[(dev >> 6) & 3];
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (word & bit) return cudaSuccess;
+    e = set();
+    if (e == cudaSuccess) word |= bit;
+    return e;
+  }
+};
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

@@ -22,7 +22,7 @@ from typing import Optional, Sequence, Tuple
 
 import numpy as np
 
-__all__ = ["Qwen3TTSSpeechTokenizer", "DecodeStream", "Qwen3TTSSpeechTokenizerDecoder", "AudioDecodingFailed", "lib",
+__all__ = ["Qwen3TTSSpeechTokenizer", "Qwen3TTSDecoderPool", "DecodeStream", "Qwen3TTSSpeechTokenizerDecoder", "AudioDecodingFailed", "lib",
            "partition_lpt", "PREC_FP32", "PREC_FP16", "PREC_BF16", "ATTN_REFERENCE", "ATTN_CAUSAL_SW",
            "library_path", "checkpoint_inspect", "CodecEmbedder", "pcm_to_int16", "write_wav", "trim_length",
            "voice_clone_cut", "device_count"]
@@ -137,6 +137,13 @@ def lib() -> C.CDLL:
         "q3tts_debug_conv_gemm": (C.c_int, [i32, i32, i32, i32, i32, i32, i32, i32, i32, C.POINTER(C.c_float),
                                             C.POINTER(C.c_float), C.POINTER(C.c_float)]),
         "q3tts_debug_attention": (C.c_int, [vp, i32, i32, i32, i32, i32, vp, vp, i32, i32, vp]),
+        "q3tts_pool_open": (C.c_int, [cp, C.POINTER(Options), vp, i32, C.POINTER(vp)]),
+        "q3tts_pool_close": (None, [vp]),
+        "q3tts_pool_size": (i32, [vp]),
+        "q3tts_pool_decode_varlen": (C.c_int, [vp, vp, vp, i32, vp, vp]),
+        "q3tts_pool_decode_varlen_int16": (C.c_int, [vp, vp, vp, i32, vp, vp]),
+        "q3tts_pool_decode": (C.c_int, [vp, vp, i32, i32, i32, vp, vp]),
+        "q3tts_pool_last_stats": (C.c_int, [vp, vp, vp, i32]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(L, name)
@@ -458,3 +465,81 @@ class Qwen3TTSSpeechTokenizer:
 
     def launch_count(self) -> int:
         return int(lib().q3tts_launch_count(self._h))
+
+
+def _pack_utterances(utterances: Sequence[np.ndarray], Q: int):
+    n = len(utterances)
+    offs = np.zeros(n + 1, dtype=np.int64)
+    for i, u in enumerate(utterances):
+        u = np.asarray(u)
+        if u.ndim != 2 or u.shape[1] != Q:
+            raise AudioDecodingFailed(1, f"utterance {i} must be [T,{Q}]")
+        offs[i + 1] = offs[i] + u.shape[0]
+    total = int(offs[-1])
+    packed = (np.concatenate([np.asarray(u, dtype=np.int32) for u in utterances], axis=0)
+              if total else np.zeros((0, Q), np.int32))
+    return np.ascontiguousarray(packed, dtype=np.int32), offs
+
+
+class Qwen3TTSDecoderPool:
+    """One decoder replica + worker thread per GPU of this box; a batch of utterances is LPT-sharded by utterance
+    (q3tts_pool_*).  The reference decodes one utterance at a time on one device (Qwen3.swift:744, 951, 1186)."""
+
+    def __init__(self, speech_tokenizer_dir: str, devices: Optional[Sequence[int]] = None, n_devices: int = 0,
+                 precision: int = PREC_FP16, attn_mode: int = ATTN_REFERENCE, workspace_bytes: int = 0,
+                 max_frames_per_launch: int = 0):
+        L = lib()
+        opts = Options()
+        L.q3tts_options_default(C.byref(opts))
+        opts.precision, opts.attn_mode = precision, attn_mode
+        opts.workspace_bytes, opts.max_frames_per_launch = workspace_bytes, max_frames_per_launch
+        h = C.c_void_p()
+        if devices is not None:
+            arr = (C.c_int32 * len(devices))(*devices)
+            _check(L.q3tts_pool_open(speech_tokenizer_dir.encode(), C.byref(opts), arr, len(devices), C.byref(h)))
+        else:
+            _check(L.q3tts_pool_open(speech_tokenizer_dir.encode(), C.byref(opts), None, n_devices, C.byref(h)))
+        self._h = h
+        self.config = checkpoint_inspect(speech_tokenizer_dir)
+        self.size = int(L.q3tts_pool_size(self._h))
+
+    def decode_varlen(self, utterances: Sequence[np.ndarray], int16: bool = False, out: Optional[np.ndarray] = None):
+        """List of [T_i,16] code arrays -> (list of PCM arrays, lengths [N]); `out` = optional preallocated flat PCM buffer."""
+        packed, offs = _pack_utterances(utterances, self.config.num_quantizers)
+        return self.decode_packed(packed, offs, int16, out)
+
+    def decode_packed(self, packed: np.ndarray, offs: np.ndarray, int16: bool = False, out: Optional[np.ndarray] = None):
+        n, up = len(offs) - 1, self.config.total_upsample
+        total = int(offs[-1])
+        pcm = out if out is not None else np.empty(total * up, dtype=np.int16 if int16 else np.float32)
+        assert pcm.size >= total * up and pcm.dtype == (np.int16 if int16 else np.float32)
+        lengths = np.zeros(n, dtype=np.int32)
+        fn = lib().q3tts_pool_decode_varlen_int16 if int16 else lib().q3tts_pool_decode_varlen
+        _check(fn(self._h, packed.ctypes.data, offs.ctypes.data, n, pcm.ctypes.data, lengths.ctypes.data))
+        return [pcm[offs[i] * up: offs[i + 1] * up] for i in range(n)], lengths
+
+    def decode(self, audio_codes: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+        """audio_codes [B,T,16] -> (audio [B, T*1920], audio_lengths [B]), rows sharded over the GPUs."""
+        ac = np.ascontiguousarray(audio_codes, dtype=np.int32)
+        B, T, _ = ac.shape
+        audio = np.empty((B, T * self.config.total_upsample), dtype=np.float32)
+        lengths = np.zeros(B, dtype=np.int32)
+        _check(lib().q3tts_pool_decode(self._h, ac.ctypes.data, B, T, CODES_BTQ, audio.ctypes.data, lengths.ctypes.data))
+        return audio, lengths
+
+    def last_stats(self):
+        ms = (C.c_float * 64)()
+        fr = (C.c_int64 * 64)()
+        n = lib().q3tts_pool_last_stats(self._h, ms, fr, 64)
+        return [dict(ms=float(ms[i]), frames=int(fr[i])) for i in range(min(n, 64))]
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            lib().q3tts_pool_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

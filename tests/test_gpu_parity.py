@@ -318,3 +318,63 @@ def test_full_size_properties_config1(full_dir):
     single, _ = tok.decode(bt16[1:2])
     assert np.abs(single[0] - a1[1]).max() <= 1e-6
     tok.close()
+
+
+def test_device_decodes_on_two_streams_share_the_workspace_safely(full_dir, full_oracle):
+    # q3tts_decode_device is asynchronous on the CALLER's stream while arena / metadata / error flag belong to the model: two
+    # back-to-back decodes on different streams must be ordered on the device (chain_done event), not just on the host.
+    cfg, _, _ = full_oracle
+    tok = q.Qwen3TTSSpeechTokenizer(full_dir, precision=q.PREC_FP16)
+    ca, cb = _nct_codes(cfg, 4, 60, 11), _nct_codes(cfg, 3, 45, 12)      # different shapes: metadata and plan change between the calls
+    want_a, want_b = tok.decoder(ca)[:, 0], tok.decoder(cb)[:, 0]
+    sa, sb = torch.cuda.Stream(), torch.cuda.Stream()
+    da, db = torch.from_numpy(ca).cuda(), torch.from_numpy(cb).cuda()
+    pa = torch.empty((4, 60 * cfg.total_upsample), dtype=torch.float32, device="cuda")
+    pb = torch.empty((3, 45 * cfg.total_upsample), dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    for _ in range(3):
+        pa.zero_(); pb.zero_()
+        torch.cuda.synchronize()
+        tok.decode_device(da.data_ptr(), 4, 60, pa.data_ptr(), 0, sa.cuda_stream)
+        tok.decode_device(db.data_ptr(), 3, 45, pb.data_ptr(), 0, sb.cuda_stream)   # enqueued while A is still running
+        tok.decode_device(da.data_ptr(), 4, 60, pa.data_ptr(), 0, 0)                 # and once more on the legacy default stream
+        tok.sync(sb.cuda_stream)
+        tok.sync(0)
+        torch.cuda.synchronize()
+        assert np.array_equal(pa.cpu().numpy(), want_a)
+        assert np.array_equal(pb.cpu().numpy(), want_b)
+    tok.close()
+
+
+def test_two_models_on_one_device_do_not_share_kernel_state(tiny_cfg):
+    # the tiny architecture's last block has 72 channels: the 16-bit tail fallback, whose weights used to live in ONE process-wide
+    # __constant__ symbol -- two models interleaved on different streams must each decode with their own outConv
+    dirs = [os.path.join(checkpoint_dir(tiny_cfg, seed=sd), "speech_tokenizer") for sd in (7, 8)]
+    toks = [q.Qwen3TTSSpeechTokenizer(d, precision=q.PREC_FP16) for d in dirs]
+    codes = _nct_codes(tiny_cfg, 6, 40, 3)
+    want = [t.decoder(codes) for t in toks]
+    assert not np.array_equal(want[0], want[1])
+    d_codes = torch.from_numpy(codes).cuda()
+    outs = [torch.empty((6, 40 * tiny_cfg.total_upsample), dtype=torch.float32, device="cuda") for _ in toks]
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    torch.cuda.synchronize()
+    for _ in range(5):
+        for t, o, s in zip(toks, outs, streams):
+            t.decode_device(d_codes.data_ptr(), 6, 40, o.data_ptr(), 0, s.cuda_stream)
+    torch.cuda.synchronize()
+    for t, o, w in zip(toks, outs, want):
+        assert np.array_equal(o.cpu().numpy(), w[:, 0])
+        t.close()
+
+
+@pytest.mark.skipif(q.device_count() < 2, reason="needs two GPUs in one process")
+def test_one_process_two_devices(full_dir, full_oracle):
+    # one handle per GPU.  The >48 KB dynamic-smem opt-in of the tcgen05 kernels is per device.
+    cfg, _, _ = full_oracle
+    codes = _nct_codes(cfg, 2, 30, 21)
+    outs = []
+    for dev in (0, 1):
+        tok = q.Qwen3TTSSpeechTokenizer(full_dir, precision=q.PREC_FP16, device=dev)
+        outs.append(tok.decoder(codes))
+        tok.close()
+    assert np.array_equal(outs[0], outs[1])

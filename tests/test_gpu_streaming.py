@@ -99,3 +99,45 @@ def test_fp16_full_model_chunked_snr(full_dir, full_oracle):
     for s in streams:
         s.close()
     tok.close()
+
+
+def test_bad_code_in_a_batched_push_advances_no_stream(tiny_dir, tiny_oracle):
+    # a push commits KV / conv state for every stream of its batch: a bad code id must be rejected BEFORE anything is committed,
+    # for the offending stream and for the innocent ones pushed with it
+    cfg, _, _ = tiny_oracle
+    tok = q.Qwen3TTSSpeechTokenizer(tiny_dir, precision=q.PREC_FP32, attn_mode=q.ATTN_CAUSAL_SW)
+    T = 18
+    codes = synth_codes(cfg, 2, T, 31)
+    frames = [np.ascontiguousarray(codes[s].T) for s in range(2)]
+    want = [tok.decoder(codes[s:s + 1])[0, 0] for s in range(2)]
+    streams = [tok.open_stream(), tok.open_stream()]
+    got = [[], []]
+    outs = tok.push_streams(streams, [frames[0][:5], frames[1][:5]])
+    got[0].append(outs[0]); got[1].append(outs[1])
+    bad = frames[1][5:11].copy()
+    bad[3, 2] = cfg.codebook_size                              # acoustic id out of range in the middle of the chunk
+    with pytest.raises(q.AudioDecodingFailed) as e:
+        tok.push_streams(streams, [frames[0][5:11], bad])
+    assert e.value.status == 1
+    assert [s.frames for s in streams] == [5, 5]              # nobody moved
+    outs = tok.push_streams(streams, [frames[0][5:], frames[1][5:]])   # the same frames again, valid this time
+    got[0].append(outs[0]); got[1].append(outs[1])
+    for s in range(2):
+        assert np.abs(np.concatenate(got[s]) - want[s]).max() <= 2e-5, s
+        streams[s].close()
+    tok.close()
+
+
+def test_model_freed_before_its_streams(tiny_dir, tiny_oracle):
+    # the Swift wrapper's deinit order is not under the caller's control: a model freed while streams are open stays alive
+    # until the last stream closes (q3tts_model_free only marks it)
+    cfg, _, _ = tiny_oracle
+    tok = q.Qwen3TTSSpeechTokenizer(tiny_dir, precision=q.PREC_FP32, attn_mode=q.ATTN_CAUSAL_SW)
+    codes = synth_codes(cfg, 1, 9, 5)
+    want = tok.decoder(codes)[0, 0]
+    st1, st2 = tok.open_stream(), tok.open_stream()
+    tok.close()                                                # q3tts_model_free with two open streams
+    pcm = st1.push(np.ascontiguousarray(codes[0].T))           # still works: the model is alive
+    assert np.abs(pcm - want).max() <= 2e-5
+    st1.close()
+    st2.close()                                                # the last close deletes the model
