@@ -43,16 +43,20 @@ public enum Qwen3TTSCUDAError: Error, LocalizedError {
     }
 }
 
+// The header's status / option constants are integer-literal macros (`#define Q3TTS_OK 0`), which Swift imports as Int32
+// constants: they compare directly with the `Int32` every entry point returns.
 @inline(__always)
 private func check(_ status: Int32) throws {
-    if status != Q3TTS_OK.rawValue.toInt32 {
+    if status != Q3TTS_OK {
         throw Qwen3TTSCUDAError.audioDecodingFailed(String(cString: q3tts_last_error()))
     }
 }
 
-private extension UInt32 { var toInt32: Int32 { Int32(self) } }
-
 public enum Qwen3TTSPrecision: Int32 { case fp32 = 0, fp16 = 1, bf16 = 2 }
+
+/// `.reference`: full, unmasked attention without RoPE -- what SpeechTokenizer.swift:512-528, 763 computes.
+/// `.causalSlidingWindow`: causal, `sliding_window` keys (Config.swift:401) -- required by `Qwen3TTSDecodeStream`.
+public enum Qwen3TTSAttentionMode: Int32 { case reference = 0, causalSlidingWindow = 1 }
 
 /// Main decoder: codes -> audio waveform (SpeechTokenizer.swift:696-785).
 public final class Qwen3TTSSpeechTokenizerDecoder {
@@ -75,7 +79,7 @@ public final class Qwen3TTSSpeechTokenizerDecoder {
         var pcm = [Float](repeating: 0, count: b * t * totalUpsample)
         try codes.data.withUnsafeBufferPointer { c in
             try pcm.withUnsafeMutableBufferPointer { p in
-                try check(q3tts_decode(handle, c.baseAddress, Int32(b), Int32(t), Int32(Q3TTS_CODES_BQT.rawValue),
+                try check(q3tts_decode(handle, c.baseAddress, Int32(b), Int32(t), Q3TTS_CODES_BQT,
                                        p.baseAddress, nil))
             }
         }
@@ -91,10 +95,12 @@ public final class Qwen3TTSSpeechTokenizer {
 
     /// Replaces the speech-tokenizer half of `postLoadHook(modelDir:)` (Qwen3.swift:1461-1494):
     /// `speechTokenizerDir` = `<modelDir>/speech_tokenizer` (config.json + *.safetensors).
-    public init(speechTokenizerDir: URL, precision: Qwen3TTSPrecision = .fp16, device: Int32 = -1) throws {
+    public init(speechTokenizerDir: URL, precision: Qwen3TTSPrecision = .fp16,
+                attentionMode: Qwen3TTSAttentionMode = .reference, device: Int32 = -1) throws {
         var opts = q3tts_options()
         q3tts_options_default(&opts)
         opts.precision = precision.rawValue
+        opts.attn_mode = attentionMode.rawValue
         opts.device = device
         var h: OpaquePointer?
         try check(q3tts_model_load(speechTokenizerDir.path, &opts, &h))
@@ -122,7 +128,7 @@ public final class Qwen3TTSSpeechTokenizer {
         try audioCodes.data.withUnsafeBufferPointer { c in
             try pcm.withUnsafeMutableBufferPointer { p in
                 try lengths.withUnsafeMutableBufferPointer { l in
-                    try check(q3tts_decode(handle, c.baseAddress, Int32(b), Int32(t), Int32(Q3TTS_CODES_BTQ.rawValue),
+                    try check(q3tts_decode(handle, c.baseAddress, Int32(b), Int32(t), Q3TTS_CODES_BTQ,
                                            p.baseAddress, l.baseAddress))
                 }
             }
@@ -140,7 +146,7 @@ public final class Qwen3TTSSpeechTokenizer {
         try audioCodes.data.withUnsafeBufferPointer { c in
             try pcm.withUnsafeMutableBufferPointer { p in
                 try lengths.withUnsafeMutableBufferPointer { l in
-                    try check(q3tts_decode_int16(handle, c.baseAddress, Int32(b), Int32(t), Int32(Q3TTS_CODES_BTQ.rawValue),
+                    try check(q3tts_decode_int16(handle, c.baseAddress, Int32(b), Int32(t), Q3TTS_CODES_BTQ,
                                                  p.baseAddress, l.baseAddress))
                 }
             }
@@ -211,13 +217,14 @@ public final class Qwen3TTSCodecEmbedder {
 }
 
 /// Chunked streaming decode: feed codec frames as the Talker emits them (Qwen3.swift:640-729 produces one
-/// 16-code vector per step), get the matching 1920·n samples back.  The model must have been loaded with the
-/// causal sliding-window attention mode (`q3tts_options.attn_mode = Q3TTS_ATTN_CAUSAL_SW`); per-stream state is the
-/// transformer KV window plus ten frames of convolution context.  No counterpart in the reference, whose
-/// `generateStream` decodes once at the end (Qwen3+Streaming.swift:19-120).
+/// 16-code vector per step), get the matching 1920·n samples back.  The tokenizer must have been created with
+/// `attentionMode: .causalSlidingWindow`; per-stream state is the transformer KV window plus 1-3 frames of input
+/// per haloed convolution.  No counterpart in the reference, whose `generateStream` decodes once at the end
+/// (Qwen3+Streaming.swift:19-120).
 public final class Qwen3TTSDecodeStream {
     private var stream: OpaquePointer
-    private let samplesPerFrame: Int
+    private let tokenizer: Qwen3TTSSpeechTokenizer      // keeps the model alive for the stream's life
+    private let samplesPerFrame: Int                    // what the library writes per frame: total_upsample
     private let numQuantizers: Int
 
     public init(_ tokenizer: Qwen3TTSSpeechTokenizer) throws {
@@ -225,7 +232,8 @@ public final class Qwen3TTSDecodeStream {
         try check(q3tts_stream_open(tokenizer.handle, &s))
         guard let opened = s else { throw Qwen3TTSCUDAError.audioDecodingFailed("q3tts_stream_open returned NULL") }
         stream = opened
-        samplesPerFrame = tokenizer.decodeUpsampleRate
+        self.tokenizer = tokenizer
+        samplesPerFrame = Int(q3tts_output_samples(tokenizer.handle, 1))
         numQuantizers = tokenizer.decoder.numQuantizers
     }
 
@@ -246,5 +254,64 @@ public final class Qwen3TTSDecodeStream {
             }
         }
         return pcm
+    }
+}
+
+/// One decoder replica + worker thread per GPU of the box; utterances are sharded by length
+/// (longest-processing-time-first) with no collective.  The reference decodes one utterance at a time on one device
+/// (Qwen3.swift:744, 951, 1186); this is the batch scheduler of the CUDA path.
+public final class Qwen3TTSDecoderPool {
+    private let pool: OpaquePointer
+    private let totalUpsample: Int
+    private let numQuantizers: Int
+    public let gpuCount: Int
+
+    public init(speechTokenizerDir: URL, precision: Qwen3TTSPrecision = .fp16, devices: [Int32]? = nil) throws {
+        var opts = q3tts_options()
+        q3tts_options_default(&opts)
+        opts.precision = precision.rawValue
+        var cfg = q3tts_config()
+        try check(q3tts_checkpoint_inspect(speechTokenizerDir.path, &cfg))
+        totalUpsample = Int(cfg.total_upsample)
+        numQuantizers = Int(cfg.num_quantizers)
+        var p: OpaquePointer?
+        if let devs = devices {
+            try devs.withUnsafeBufferPointer { d in
+                try check(q3tts_pool_open(speechTokenizerDir.path, &opts, d.baseAddress, Int32(devs.count), &p))
+            }
+        } else {
+            try check(q3tts_pool_open(speechTokenizerDir.path, &opts, nil, 0, &p))
+        }
+        guard let opened = p else { throw Qwen3TTSCUDAError.audioDecodingFailed("q3tts_pool_open returned NULL") }
+        pool = opened
+        gpuCount = Int(q3tts_pool_size(opened))
+    }
+
+    deinit { q3tts_pool_close(pool) }
+
+    /// Utterances of different lengths, each [T_i, 16]; every result equals its own single-utterance decode.
+    public func decodeBatch(_ utterances: [Int32Tensor]) throws -> (audio: [[Float]], audioLengths: [Int32]) {
+        var offsets = [Int64](repeating: 0, count: utterances.count + 1)
+        var packed = [Int32]()
+        for (i, u) in utterances.enumerated() {
+            precondition(u.shape.count == 2 && u.shape[1] == numQuantizers)
+            offsets[i + 1] = offsets[i] + Int64(u.shape[0])
+            packed.append(contentsOf: u.data)
+        }
+        var pcm = [Float](repeating: 0, count: Int(offsets.last!) * totalUpsample)
+        var lengths = [Int32](repeating: 0, count: utterances.count)
+        try packed.withUnsafeBufferPointer { c in
+            try offsets.withUnsafeBufferPointer { o in
+                try pcm.withUnsafeMutableBufferPointer { p in
+                    try lengths.withUnsafeMutableBufferPointer { l in
+                        try check(q3tts_pool_decode_varlen(pool, c.baseAddress, o.baseAddress, Int32(utterances.count),
+                                                           p.baseAddress, l.baseAddress))
+                    }
+                }
+            }
+        }
+        let up = totalUpsample
+        let audio = (0..<utterances.count).map { i in Array(pcm[(Int(offsets[i]) * up)..<(Int(offsets[i + 1]) * up)]) }
+        return (audio, lengths)
     }
 }
