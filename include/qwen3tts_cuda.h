@@ -163,6 +163,9 @@ int q3tts_codec_embed_sum_device(q3tts_codec_embedder* e, const int32_t* d_codes
  * q3tts_sync().                                                                                */
 int q3tts_decode_device(q3tts_model* m, const int32_t* d_codes, int32_t B, int32_t T, int32_t layout,
                         float* d_pcm_out, int32_t* d_lengths_out, void* stream);
+/* q3tts_decode_varlen with the packed codes / PCM / lengths in HBM; frame_offsets is a HOST array [n+1].           */
+int q3tts_decode_varlen_device(q3tts_model* m, const int32_t* d_codes_packed, const int64_t* frame_offsets,
+                               int32_t n_utterances, float* d_pcm_out, int32_t* d_lengths_out, void* stream);
 int q3tts_sync(q3tts_model* m, void* stream);
 
 /* ---- stage taps (debug / parity) --------------------------------------------------------------

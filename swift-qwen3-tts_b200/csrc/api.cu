@@ -394,6 +394,36 @@ int q3tts_decode_device(q3tts_model* h, const int32_t* d_codes, int32_t B, int32
   return decode_common(h, d_codes, B, T, layout, d_pcm_out, d_lengths_out, true, (cudaStream_t)stream);
 }
 
+// Mixed-length batch with the packed codes and the PCM already in HBM; frame_offsets stays a HOST array (it sizes the launch chain).
+int q3tts_decode_varlen_device(q3tts_model* h, const int32_t* d_codes_packed, const int64_t* frame_offsets, int32_t n,
+                               float* d_pcm_out, int32_t* d_lengths_out, void* stream) {
+  return guarded([&]() {
+    if (!h) return fail(Q3TTS_EINVAL, "model is NULL");
+    if (n < 0) return fail(Q3TTS_EINVAL, "negative utterance count");
+    if (n == 0) return (int)Q3TTS_OK;
+    if (!frame_offsets) return fail(Q3TTS_EINVAL, "frame_offsets is NULL");
+    if (frame_offsets[0] != 0) return fail(Q3TTS_EINVAL, "frame_offsets[0] must be 0");
+    for (int i = 0; i < n; ++i)
+      if (frame_offsets[i + 1] < frame_offsets[i] || frame_offsets[i + 1] - frame_offsets[i] > INT32_MAX)
+        return fail(Q3TTS_EINVAL, "frame_offsets must be non-decreasing");
+    if (frame_offsets[n] > 0 && (!d_codes_packed || !d_pcm_out)) return fail(Q3TTS_EINVAL, "NULL buffer");
+    Model& m = *h->m;
+    std::lock_guard<std::mutex> lock(m.mu);
+    CUDA_OK(cudaSetDevice(m.device));
+    PcmFormat fmt(m, false);
+    const int Q = m.cfg.num_quantizers;
+    const int64_t up = m.cfg.total_upsample;
+    cudaStream_t s = (cudaStream_t)stream;
+    chain_begin(m, s);
+    std::vector<Utt> utts((size_t)n);
+    for (int i = 0; i < n; ++i)
+      utts[(size_t)i] = Utt{frame_offsets[i] * Q, frame_offsets[i] * up, (int)(frame_offsets[i + 1] - frame_offsets[i]), i};
+    decode_core(m, d_codes_packed, utts, 1, Q, d_pcm_out, d_lengths_out, s);
+    chain_end(m, s);
+    return (int)Q3TTS_OK;
+  });
+}
+
 int q3tts_sync(q3tts_model* h, void* stream) {
   return guarded([&]() {
     if (!h) return fail(Q3TTS_EINVAL, "model is NULL");

@@ -106,6 +106,7 @@ def lib() -> C.CDLL:
         "q3tts_decode_int16": (C.c_int, [vp, vp, i32, i32, i32, vp, vp]),
         "q3tts_decode_varlen_int16": (C.c_int, [vp, vp, vp, i32, vp, vp]),
         "q3tts_decode_device": (C.c_int, [vp, vp, i32, i32, i32, vp, vp, vp]),
+        "q3tts_decode_varlen_device": (C.c_int, [vp, vp, vp, i32, vp, vp, vp]),
         "q3tts_codec_embedder_load": (C.c_int, [cp, i32, C.POINTER(vp)]),
         "q3tts_codec_embedder_free": (None, [vp]),
         "q3tts_codec_embedder_info": (C.c_int, [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), vp]),
@@ -425,6 +426,12 @@ class Qwen3TTSSpeechTokenizer:
                       stream: int = 0, layout: int = CODES_BQT) -> None:
         _check(lib().q3tts_decode_device(self._h, d_codes_ptr, B, T, layout, d_pcm_ptr,
                                          d_lengths_ptr or None, stream or None))
+
+    def decode_varlen_device(self, d_codes_ptr: int, frame_offsets: np.ndarray, d_pcm_ptr: int, d_lengths_ptr: int = 0,
+                             stream: int = 0) -> None:
+        offs = np.ascontiguousarray(frame_offsets, dtype=np.int64)
+        _check(lib().q3tts_decode_varlen_device(self._h, d_codes_ptr, offs.ctypes.data, len(offs) - 1, d_pcm_ptr,
+                                                d_lengths_ptr or None, stream or None))
 
     def sync(self, stream: int = 0) -> None:
         _check(lib().q3tts_sync(self._h, stream or None))
