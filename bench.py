@@ -461,16 +461,19 @@ def run_config5(cx, q, cfg, st_dir, prec, n_chunks=C5_CHUNKS, streams_per_gpu=C5
     streams = [tok.open_stream() for _ in range(S)]
     lat, pos = [], 0
     launches0 = tok.launch_count()
+    sampler = None
     cx.barrier()
     for i, n in enumerate(sizes):
         chunk = [f[pos:pos + n] for f in frames]
         if i == warm:
             cx.barrier()
             launches0 = tok.launch_count()
+            sampler = ClockSampler(cx.local_rank).start()
         t0 = time.perf_counter()
         tok.push_streams(streams, chunk)
         lat.append(time.perf_counter() - t0)
         pos += n
+    clocks = sampler.stop() if sampler else None
     steady = np.array(lat[warm:]) * 1e3
     launches = tok.launch_count() - launches0
     audio_s = S * sum(sizes[warm:]) * SEC_PER_FRAME
@@ -481,7 +484,7 @@ def run_config5(cx, q, cfg, st_dir, prec, n_chunks=C5_CHUNKS, streams_per_gpu=C5
                                 "max": cx.allmax(float(steady.max())), "note": "host codes in -> host PCM out per batched push; max over ranks"},
            "streams_per_gpu": S, "streams_total": S * cx.world, "chunk_frames": list(pattern), "context_frames_per_push": 3,
            "realtime_factor": cx.world * audio_s / total_time / (S * cx.world),
-           "gpu_launches_per_push": int(launches // n_chunks),
+           "gpu_launches_per_push": int(launches // n_chunks), "gpu_launches_total": int(launches), "clocks": clocks,
            "e2e": {"value": cx.world * audio_s / total_time, "unit": UNIT,
                    "h2d_bytes_per_step": int(S * cx.world * 6.25 * 16 * 4), "d2h_bytes_per_step": int(S * cx.world * 6.25 * 1920 * 4)}}
     for s in streams:
@@ -570,7 +573,8 @@ def main():
                 "dtype": dtype, "data": "synthetic",
                 "config": {"workload": workload_text(args.workload, args), "parallelism": f"utterance-sharded x{cx.world}, no data-path collective",
                            "l2": "per-step activation working set >> 126 MB L2 (no flush needed)"},
-                "clocks": r.pop("clocks", None), "gpu_launches": r.get("gpu_launches_per_step_rank0", r.get("gpu_launches_per_push", 0)) * K,
+                "clocks": r.pop("clocks", None),
+                "gpu_launches": r.get("gpu_launches_total", r.get("gpu_launches_per_step_rank0", 0) * K),
                 "e2e": r.pop("e2e"), "roofline": r.pop("roofline", None)}
         line.update(r)
         if cx.rank == 0 and cx.world == 1 and not args.no_cpu_baseline:

@@ -834,12 +834,12 @@ int q3tts_debug_resunit(int32_t B, int32_t rows, int32_t dil, int32_t out_snake,
     if (d_dbg) {
       std::vector<long long> h(16 * 32);
       CUDA_OK(cudaMemcpy(h.data(), d_dbg, h.size() * 8, cudaMemcpyDeviceToHost));
-      static const char* kEv[12] = {"prod:slot_free", "P:before_wait", "P:t_full", "P:done", "MMA:a_ready", "MMA:c7_issued", "MMA:c_ready", "MMA:c1_issued",
-                                    "E1:acc1_full", "E1:done", "E2:acc2_full", "E2:done"};
+      static const char* kEv[16] = {"prod:slot_free", "P:before_wait", "P:t_full", "P:done", "MMA:a_ready", "MMA:c7_issued", "MMA:c_ready", "MMA:c1_issued",
+                                    "E1:acc1_full", "E1:done", "E2:acc2_full", "E2:done", "P2:done", "P3:done", "P4:done", "P5:done"};
       const long long t0 = h[0 * 32 + 8];
       for (int tile = 8; tile < 20; ++tile) {
         std::printf("tile %2d:", tile);
-        for (int ev = 0; ev < 12; ++ev) std::printf(" %s=%lld", kEv[ev], h[(size_t)ev * 32 + tile] - t0);
+        for (int ev = 0; ev < 16; ++ev) std::printf(" %s=%lld", kEv[ev], h[(size_t)ev * 32 + tile] - t0);
         std::printf("\n");
       }
       rp.dbg = nullptr;

@@ -41,14 +41,15 @@ using namespace tc;
 
 #define R_STAMP(ev, tile) do { if (p.dbg && blockIdx.x == 0 && (tile) < 32 && lane == 0) p.dbg[(ev) * 32 + (tile)] = clock64(); } while (0)
 
-constexpr int R_C = 96, R_SUB = 3, R_BM = 128, R_SLOTS = 4, R_CTRL = 2, R_PW = 6, R_E1W = 8, R_E2W = 8;   // control (producer, MMA), pass-1, epilogue-1, epilogue-2 warps
+constexpr int R_C = 96, R_SUB = 3, R_BM = 128, R_SLOTS = 4, R_CTRL = 2, R_PW = 9, R_E1W = 8, R_E2W = 8;   // control (producer, MMA), pass-1, epilogue-1, epilogue-2 warps
 constexpr int R_THREADS = (R_CTRL + R_PW + R_E1W + R_E2W) * 32;
 constexpr uint32_t R_WBLK = 48 * 64;                 // one (tap, 32-channel block) of this CTA's weight half: 48 rows x 64 B
 constexpr uint32_t R_W7_BYTES = 7 * R_SUB * R_WBLK;  // 64512
 constexpr uint32_t R_W1_BYTES = R_SUB * R_WBLK;      // 9216
-constexpr uint32_t R_CST = 6 * R_C * 4;              // b7, ea2, ib2, b1, ea3, ib3
+constexpr uint32_t R_CST = 3 * R_C * 4;              // b1, ea3, ib3 (epilogue 2; epilogue 1 keeps b7, ea2, ib2 in registers)
 constexpr uint32_t R_TMEM_COLS = 512;
-constexpr uint32_t R_STG_WARP = 32 * 48 * 2;         // epilogue 2: one warp's 32 rows x 48 channels (residual in, X' out)
+constexpr uint32_t R_STG_TILE = 32 * 48 * 2;         // epilogue 2: one warp's 32 rows x 48 channels (residual in, X' out)
+constexpr uint32_t R_STG_WARP = 2 * R_STG_TILE;      // two buffers per warp, alternating by tile
 constexpr uint32_t R_STG_BYTES = R_E2W * R_STG_WARP;
 
 struct Res96Params {
@@ -64,7 +65,15 @@ struct Res96Params {
   int out_snake;                  // write snake3(X') instead of X' (last unit of the block)
   const void* x_in; long long x_bstride;   // residual rows (elements)
   long long* dbg;                 // optional [16 events][32 tiles] clock64 stamps of CTA 0 (pipeline debugging)
+  uint32_t sleep_ns;              // back-off of the waiting role warps (Q3TTS_RES_SLEEP; 0 = poll)
+  int bridge;                     // 1: the epilogue warps block on named barriers released by warp 0 (see the producer role)
 };
+
+// Named barriers (id 0 is __syncthreads): the 8 warps of an epilogue role block in bar.sync -- a blocked warp issues nothing -- and
+// warp 0, which polls the accumulator mbarriers anyway, releases them with bar.arrive.  Two ids per role: accumulators are
+// double-buffered, so arrivals for tile t + 2 cannot start before every warp has left the barrier of tile t.
+constexpr int R_BAR_E1 = 1, R_BAR_E2 = 3, R_BAR_E1_COUNT = (R_E1W + 1) * 32, R_BAR_E2_COUNT = (R_E2W + 1) * 32;
+__device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
 // Position of a CTA in its strip of valid tiles (warp-uniform).
 struct Walker {
@@ -122,8 +131,8 @@ resunit96_kernel(const __grid_constant__ CUtensorMap map_main, const __grid_cons
   uint8_t* t_ring = smem;                                    // [3 blocks][4 slots][hb halo rows + 128 rows][64 B]
   uint8_t* w7s = t_ring + (size_t)R_SUB * p.tsub_bytes;      // [7 taps][3 blocks][48 rows][64 B]
   uint8_t* w1s = w7s + R_W7_BYTES;                           // [3 blocks][48 rows][64 B]
-  uint8_t* stg = w1s + R_W1_BYTES;                           // [8 epilogue-2 warps][32 rows][96 B]
-  float* cst = (float*)(stg + R_STG_BYTES);
+  uint8_t* stg = w1s + R_W1_BYTES;                           // [8 epilogue-2 warps][2 buffers][32 rows][96 B]
+  float* cst = (float*)(stg + R_STG_BYTES);                  // b1, ea3, ib3
   uint64_t* bars = (uint64_t*)((uint8_t*)cst + R_CST);
   uint64_t* w_full = bars;              // 1
   uint64_t* t_full = bars + 1;          // [4] local: X tile landed
@@ -133,8 +142,8 @@ resunit96_kernel(const __grid_constant__ CUtensorMap map_main, const __grid_cons
   uint64_t* c_ready = bars + 19;        // [2] leader: epilogue 1 done in both CTAs (conv1 operand written, acc1 drained)
   uint64_t* acc2_full = bars + 21;      // [2] both: conv1 has completed
   uint64_t* acc2_free = bars + 23;      // [2] leader: epilogue 2 has drained acc2 in both CTAs
-  uint64_t* xbar = bars + 25;           // [8] local: an epilogue-2 warp's residual rows have landed
-  uint32_t* tmem_ptr = (uint32_t*)(bars + 33);
+  uint64_t* xbar = bars + 25;           // [8][2] local: an epilogue-2 warp's residual rows have landed (per staging buffer)
+  uint32_t* tmem_ptr = (uint32_t*)(bars + 25 + 2 * R_E2W);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -155,7 +164,7 @@ resunit96_kernel(const __grid_constant__ CUtensorMap map_main, const __grid_cons
     mbar_init(w_full, 1);
     for (int i = 0; i < R_SLOTS; ++i) { mbar_init(&t_full[i], 1); mbar_init(&a_ready[i], 2 * R_PW); mbar_init(&c7_done[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc1_full[i], 1); mbar_init(&c_ready[i], 2 * R_E1W); mbar_init(&acc2_full[i], 1); mbar_init(&acc2_free[i], 2 * R_E2W); }
-    for (int i = 0; i < R_E2W; ++i) mbar_init(&xbar[i], 1);
+    for (int i = 0; i < 2 * R_E2W; ++i) mbar_init(&xbar[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -164,9 +173,8 @@ resunit96_kernel(const __grid_constant__ CUtensorMap map_main, const __grid_cons
   }
   if (warp >= R_CTRL) {
     for (int i = (int)threadIdx.x - R_CTRL * 32; i < R_C; i += (R_PW + R_E1W + R_E2W) * 32) {
-      cst[i] = __ldg(p.b7 + i); cst[R_C + i] = __ldg(p.ea2 + i); cst[2 * R_C + i] = __ldg(p.ib2 + i);
-      cst[3 * R_C + i] = __ldg(p.b1 + i);
-      cst[4 * R_C + i] = p.out_snake ? __ldg(p.ea3 + i) : 0.f; cst[5 * R_C + i] = p.out_snake ? __ldg(p.ib3 + i) : 0.f;
+      cst[i] = __ldg(p.b1 + i);
+      cst[R_C + i] = p.out_snake ? __ldg(p.ea3 + i) : 0.f; cst[2 * R_C + i] = p.out_snake ? __ldg(p.ib3 + i) : 0.f;
     }
   }
   tc_fence_before();
@@ -187,9 +195,8 @@ resunit96_kernel(const __grid_constant__ CUtensorMap map_main, const __grid_cons
     __syncwarp();
     Walker w;
     w.init(p, g0);
-    for (int j = 0; j < q; ++j) {
+    auto issue_tile = [&](int j) {          // TMA of tile j into slot j % ns (the walker stands at tile j)
       const int slot = j % ns;
-      if (j >= ns) mbar_wait_sleep(&c7_done[slot], (uint32_t)(((j - ns) / ns) & 1));   // conv7 of the slot's previous tile is over (conv1 reads tensor memory)
       R_STAMP(0, j);
       if (elect_one()) {
         if (w.live(p)) {
@@ -205,6 +212,31 @@ resunit96_kernel(const __grid_constant__ CUtensorMap map_main, const __grid_cons
       }
       __syncwarp();
       w.next(p);
+    };
+    if (p.bridge) {
+      // This warp is also the BRIDGE between the tensor pipe's completion mbarriers and the epilogue warps.  Sixteen epilogue warps
+      // polling acc1_full / acc2_full took a third of all issued instructions (ncu, profiles/r2_resunit.md) -- away from the pass-1
+      // warps, which are the critical role -- and neither try_wait's suspend hint nor nanosleep really parks a warp at these time
+      // scales.  So ONE warp polls, in the order the tensor pipe completes things (c7(0) c7(1) c1(0) c7(2) c1(1) ...), and releases
+      // the role's warps from a named barrier.  conv7(i) complete also means ring slot i % ns may be refilled.
+      const int pre = q < ns ? q : ns;
+      for (int j = 0; j < pre; ++j) issue_tile(j);
+      for (int i = 0; i <= q; ++i) {
+        if (i < q) {
+          mbar_wait(&acc1_full[i & 1], (uint32_t)((i >> 1) & 1));
+          named_bar_arrive(R_BAR_E1 + (i & 1), R_BAR_E1_COUNT);
+          if (i + ns < q) issue_tile(i + ns);
+        }
+        if (i >= 1) {
+          mbar_wait(&acc2_full[(i - 1) & 1], (uint32_t)(((i - 1) >> 1) & 1));
+          named_bar_arrive(R_BAR_E2 + ((i - 1) & 1), R_BAR_E2_COUNT);
+        }
+      }
+    } else {
+      for (int j = 0; j < q; ++j) {
+        if (j >= ns) mbar_wait_backoff(&c7_done[j % ns], (uint32_t)(((j - ns) / ns) & 1), p.sleep_ns);   // conv7 of the slot's previous tile is over
+        issue_tile(j);
+      }
     }
   } else if (warp == 1) {
     // ================= MMA issuer (leader CTA only) =================
@@ -214,11 +246,11 @@ resunit96_kernel(const __grid_constant__ CUtensorMap map_main, const __grid_cons
       const uint32_t idesc = p.idesc7;
       const uint64_t dTap = (uint64_t)(p.dil * 4);             // dil rows x 64 B, in 16-byte units
       const uint32_t tsub16 = p.tsub_bytes >> 4;
-      mbar_wait_sleep(w_full, 0);
+      mbar_wait(w_full, 0);
       for (int i = 0; i <= q; ++i) {
         if (i < q) {
           const int slot = i % ns;
-          mbar_wait_sleep(&a_ready[slot], (uint32_t)((i / ns) & 1));
+          mbar_wait(&a_ready[slot], (uint32_t)((i / ns) & 1));
           tc_fence_after();
           R_STAMP(4, i);
           if (elect_one()) {
@@ -246,8 +278,8 @@ resunit96_kernel(const __grid_constant__ CUtensorMap map_main, const __grid_cons
         }
         if (i >= 1) {
           const int t = i - 1;
-          mbar_wait_sleep(&c_ready[t & 1], (uint32_t)((t >> 1) & 1));
-          if (t >= 2) mbar_wait_sleep(&acc2_free[t & 1], (uint32_t)(((t - 2) >> 1) & 1));
+          mbar_wait(&c_ready[t & 1], (uint32_t)((t >> 1) & 1));
+          if (t >= 2) mbar_wait(&acc2_free[t & 1], (uint32_t)(((t - 2) >> 1) & 1));
           tc_fence_after();
           R_STAMP(6, t);
           if (elect_one()) {
@@ -272,50 +304,47 @@ resunit96_kernel(const __grid_constant__ CUtensorMap map_main, const __grid_cons
       }
     }
   } else if (warp >= R_CTRL && warp < R_CTRL + R_PW) {
-    // ================= pass-1 warps (6): snake1 in place on every freshly landed tile =================
-    // Two warps per 32-channel block; a warp takes every other 8-row group, two groups per iteration (independent chunks:
-    // ILP).  A lane's 8 channels are fixed, so its 16 SnakeBeta constants live in registers.  A quarter warp touches
-    // 2 rows x 64 B = 128 contiguous bytes: conflict-free.  The last hb rows of a tile are also written into the halo rows
+    // ================= pass-1 warps: snake1 in place on every freshly landed tile =================
+    // NP warps per 32-channel block, each a contiguous range of the tile's sixteen 8-row groups, two groups per iteration
+    // (independent chunks: ILP).  A lane's 8 channels are fixed, so its 16 SnakeBeta constants live in registers.  A quarter warp
+    // touches 2 rows x 64 B = 128 contiguous bytes: conflict-free.  The last hb rows of a tile are also written into the halo rows
     // of the NEXT slot (unless the next tile opens a strip and brings its halo by TMA).
     const int pw = warp - R_CTRL, pc = pw % R_SUB, par = pw / R_SUB, kch = lane & 3;
+    constexpr int NP = R_PW / R_SUB;                              // warps per 32-channel block
+    const int tg_lo = (par * (R_BM / 8)) / NP, tg_hi = ((par + 1) * (R_BM / 8)) / NP;
     float ea1[8], ib1[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) { ea1[e] = __ldg(p.ea1 + pc * 32 + kch * 8 + e); ib1[e] = __ldg(p.ib1 + pc * 32 + kch * 8 + e); }
-    const uint32_t sub_u32 = smem_u32(t_ring) + (uint32_t)pc * p.tsub_bytes;
-    const int ngroups = rs / 8;
+    // slot rows and 128 are multiples of 8, so the 64-byte swizzle term ((row >> 1) & 3) depends on the lane only
+    const uint32_t lane_off = (uint32_t)(lane >> 2) * 64u + (uint32_t)((kch ^ ((lane >> 3) & 3)) << 4);
+    const uint32_t sub_u32 = smem_u32(t_ring) + (uint32_t)pc * p.tsub_bytes + lane_off;
+    int slot = 0, cnt = 0;                                          // j % ns, j / ns
     Walker w;
     w.init(p, g0);
     for (int j = 0; j < q; ++j) {
-      const int slot = j % ns, nslot = (j + 1) % ns;
+      int nslot = slot + 1, ncnt = cnt;
+      if (nslot == ns) { nslot = 0; ++ncnt; }
       const bool live = w.live(p), first = w.first;
       w.next(p);                                                  // now describes tile j+1
       const bool copy_tail = live && j + 1 < q && w.live(p) && !w.first;
       if (pw == 0) R_STAMP(1, j);
-      mbar_wait_sleep(&t_full[slot], (uint32_t)((j / ns) & 1));
+      mbar_wait_backoff(&t_full[slot], (uint32_t)(cnt & 1), p.sleep_ns);
       if (pw == 0) R_STAMP(2, j);
       bool tail_ok = !(copy_tail && j >= ns - 1);          // else: conv7 of the next slot's previous tile may still read its halo rows
       if (live) {
-        constexpr int NP = R_PW / R_SUB;                            // warps per 32-channel block
-        for (int G = (first ? 0 : hb / 8) + par; G < ngroups; G += 2 * NP) {
-          const int G2 = G + NP;
-          const bool two = G2 < ngroups;
-          if (!tail_ok && (two ? G2 : G) * 8 >= R_BM) {            // first iteration that touches the tail (groups ascend)
-            mbar_wait_sleep(&c7_done[nslot], (uint32_t)(((j - (ns - 1)) / ns) & 1));
+        const uint32_t slot_u32 = sub_u32 + (uint32_t)(slot * rs) * 64u;
+        const uint32_t nslot_u32 = sub_u32 + (uint32_t)(nslot * rs - R_BM) * 64u;
+        const int G_end = hb / 8 + tg_hi;
+        for (int G = (par == 0 && first) ? 0 : hb / 8 + tg_lo; G < G_end; G += 2) {
+          const bool two = G + 1 < G_end;
+          if (!tail_ok && (G + 2) * 8 > R_BM) {                     // first iteration that touches the tail (groups ascend)
+            mbar_wait_backoff(&c7_done[nslot], (uint32_t)((ncnt ^ 1) & 1), p.sleep_ns);
             tail_ok = true;
           }
-          uint32_t addr[2], naddr[2];
-          bool tail[2];
-#pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            const int rin = (g == 0 ? G : G2) * 8 + (lane >> 2);     // row inside the slot (halo rows first)
-            const int row = slot * rs + rin, nrow = nslot * rs + rin - R_BM;
-            addr[g] = sub_u32 + (uint32_t)row * 64u + (uint32_t)((kch ^ ((row >> 1) & 3)) << 4);
-            naddr[g] = sub_u32 + (uint32_t)nrow * 64u + (uint32_t)((kch ^ ((nrow >> 1) & 3)) << 4);
-            tail[g] = copy_tail && rin >= R_BM;                     // the last hb rows of the tile
-          }
+          const uint32_t addr0 = slot_u32 + (uint32_t)G * 512u, naddr0 = nslot_u32 + (uint32_t)G * 512u;
           uint4 u[2];
-          u[0] = lds128(addr[0]);
-          if (two) u[1] = lds128(addr[1]); else u[1] = make_uint4(0, 0, 0, 0);
+          u[0] = lds128(addr0);
+          if (two) u[1] = lds128(addr0 + 512u); else u[1] = make_uint4(0, 0, 0, 0);
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
             const uint32_t in[4] = {u[g].x, u[g].y, u[g].z, u[g].w};
@@ -328,8 +357,8 @@ resunit96_kernel(const __grid_constant__ CUtensorMap map_main, const __grid_cons
             }
             const uint4 v = make_uint4(o[0], o[1], o[2], o[3]);
             if (g == 0 || two) {
-              sts128(addr[g], v);
-              if (tail[g]) sts128(naddr[g], v);
+              sts128(addr0 + 512u * g, v);
+              if (copy_tail && (G + g) * 8 >= R_BM) sts128(naddr0 + 512u * g, v);   // the last hb rows of the tile (an 8-row group is all tail or none)
             }
           }
         }
@@ -337,50 +366,56 @@ resunit96_kernel(const __grid_constant__ CUtensorMap map_main, const __grid_cons
       fence_async_smem();
       __syncwarp();
       if (pw == 0) R_STAMP(3, j);
+      if (pw >= 2 && pw < 6) R_STAMP(10 + pw, j);       // debug: when do the other pass-1 warps finish?
       if (lane == 0) arrive_leader(&a_ready[slot], rank);
+      slot = nslot; cnt = ncnt;
     }
   } else if (warp >= R_CTRL + R_PW && warp < R_CTRL + R_PW + R_E1W) {
     // ================= epilogue-1 warps (two per TMEM lane quarter, 48 channels each): acc1 + b7 -> snake2 -> conv1's operand =================
-    // The operand is written over the tile's own rows in the ring (dead once conv7 has completed).
-    const int quarter = warp & 3, col_base = ((warp - R_CTRL - R_PW) >> 2) * 48;
-    const uint32_t cst_u32 = smem_u32(cst);
+    // Column-sliced TMEM access (16x256b): a lane sees columns {2(lane%4), +1, +8, +9} of every 16, so its 12 x (b7, ea2, ib2) stay in
+    // registers for the whole kernel.  The packed operand is written (16x128b) over accumulator columns that have already been read.
+    const int quarter = warp & 3, col_base = ((warp - R_CTRL - R_PW) >> 2) * 48, c0 = 2 * (lane & 3);
+    float kb[3][4], ke[3][4], ki[3][4];
+#pragma unroll
+    for (int m = 0; m < 3; ++m)
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int col = col_base + 16 * m + c0 + (jj & 1) + 8 * (jj >> 1);
+        kb[m][jj] = __ldg(p.b7 + col); ke[m][jj] = __ldg(p.ea2 + col); ki[m][jj] = __ldg(p.ib2 + col);
+      }
     Walker w;
     w.init(p, g0);
     for (int t = 0; t < q; ++t) {
       const bool live = w.live(p);
-      mbar_wait_sleep(&acc1_full[t & 1], (uint32_t)((t >> 1) & 1));
+      if (p.bridge) named_bar_sync(R_BAR_E1 + (t & 1), R_BAR_E1_COUNT);
+      else mbar_wait_backoff(&acc1_full[t & 1], (uint32_t)((t >> 1) & 1), p.sleep_ns);
       tc_fence_after();
       if (warp == R_CTRL + R_PW) R_STAMP(8, t);
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((t & 1) * 128 + col_base);
-      uint32_t r[2][16];
-      tc_ld16(taddr, r[0]);
+      const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((t & 1) * 128 + col_base);
 #pragma unroll
       for (int m = 0; m < 3; ++m) {
+        uint32_t a[2][8];
+        tc_ld_16x256b_x2(tbase + 16u * (uint32_t)m, a[0]);                    // lanes +0 .. +15 of the quarter
+        tc_ld_16x256b_x2(tbase + (16u << 16) + 16u * (uint32_t)m, a[1]);      // lanes +16 .. +31
         tc_wait_ld();
-        if (m + 1 < 3) tc_ld16(taddr + 16u * (uint32_t)(m + 1), r[(m + 1) & 1]);   // next chunk in flight during the math
         if (live) {
-          const int col = col_base + 16 * m;
-          const uint32_t sb = cst_u32 + 4u * (uint32_t)col, se = sb + 4u * R_C, si = se + 4u * R_C;
-          uint32_t pk[8];
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const float4 b0 = lds4f(sb + 32u * h), b1 = lds4f(sb + 32u * h + 16u);
-            const float4 e0 = lds4f(se + 32u * h), e1 = lds4f(se + 32u * h + 16u);
-            const float4 i0 = lds4f(si + 32u * h), i1 = lds4f(si + 32u * h + 16u);
-            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-            const float ee[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
-            const float ii[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
-            float v[8];
+          for (int lh = 0; lh < 2; ++lh) {
+            uint32_t pk[4];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const float x = __uint_as_float(r[m & 1][8 * h + e]) + bb[e];
-              const float sn = __sinf(x * ee[e]);
-              v[e] = fmaf(ii[e], sn * sn, x);
+            for (int pr = 0; pr < 4; ++pr) {          // pr = 2 * (column group j) + (row + 8): registers a[4j + 2 (row+8) + {0, 1}]
+              const int j = pr >> 1;
+              float v[2];
+#pragma unroll
+              for (int k = 0; k < 2; ++k) {
+                const float x = __uint_as_float(a[lh][4 * j + 2 * (pr & 1) + k]) + kb[m][2 * j + k];
+                const float sn = __sinf(x * ke[m][2 * j + k]);
+                v[k] = fmaf(ki[m][2 * j + k], sn * sn, x);
+              }
+              pk[pr] = Cvt<T16>::pack(v[0], v[1]);    // store order: {row, col grp 0}, {row+8, grp 0}, {row, grp 1}, {row+8, grp 1}
             }
-#pragma unroll
-            for (int e = 0; e < 4; ++e) pk[4 * h + e] = Cvt<T16>::pack(v[2 * e], v[2 * e + 1]);
+            tc_st_16x128b_x2(tbase + ((uint32_t)(16 * lh) << 16) + 8u * (uint32_t)m, pk);
           }
-          tc_st8(taddr + 8u * (uint32_t)m, pk);   // columns of chunks already in registers (chunk m+1 at most in flight, further right)
         }
       }
       tc_wait_st();
@@ -392,51 +427,52 @@ resunit96_kernel(const __grid_constant__ CUtensorMap map_main, const __grid_cons
     }
   } else if (warp >= R_CTRL + R_PW + R_E1W) {
     // ================= epilogue-2 warps (two per TMEM lane quarter, 48 channels each): acc2 + b1 + X -> X' (or snake3(X')) =================
-    // The residual rows (L2 hits: the tile went through L2 a few microseconds ago) come in by TMA into the warp's staging
-    // buffer before the accumulator is waited for; X' is written over them and leaves by TMA.  (Direct 16-byte global
-    // accesses with a 192-byte row pitch cost 32 LSU wavefronts per instruction and slowed every other role by 15-20 %.)
+    // The residual rows (L2 hits: the tile went through L2 a few microseconds ago) come in by TMA into the warp's staging buffer, X' is
+    // written over them and leaves by TMA: ONE load and ONE store of a 32 x 48 box per warp and tile.  (Direct 16-byte global accesses
+    // with a 192-byte row pitch cost 32 LSU wavefronts per instruction; splitting the box into 16- or 24-channel boxes made the
+    // staging conflict-free but the 3-6x TMA instructions per tile cost the warp more than the conflicts: profiles/r2_resunit.md.)
+    // TWO buffers per warp, alternating by tile.  With one, the chain [X' store drains the buffer (~2000 cycles in the TMA queue) ->
+    // residual load of the next tile -> compute] was serial: the warps worked 2300 cycles and stalled 2100 per tile, and that chain --
+    // not the tensor pipe, not pass 1 -- set the kernel's pace (clock64 timeline).  Now the next tile's residual is requested right
+    // after this tile's math, into the buffer whose store -- a whole tile ago -- has drained meanwhile.
     const int e2w = warp - R_CTRL - R_PW - R_E1W;
     const int quarter = warp & 3, col_base = (e2w >> 2) * 48;
     const uint32_t cst_u32 = smem_u32(cst);
     uint8_t* my_stg = stg + (size_t)e2w * R_STG_WARP;
-    const uint32_t my_row = smem_u32(my_stg) + (uint32_t)lane * 96u;
-    uint32_t xpar = 0;
+    uint64_t* my_xbar = xbar + 2 * e2w;
     Walker w;
     w.init(p, g0);
+    if (q > 0 && w.live(p) && lane == 0) {
+      mbar_expect_tx(&my_xbar[0], R_STG_TILE);
+      tma_load_3d(my_stg, &map_res, &my_xbar[0], col_base, w.t0 + quarter * 32, w.b);
+    }
     for (int u = 0; u < q; ++u) {
       const bool row_ok = w.live(p);                                // warp-uniform
-      const int row0 = w.t0 + quarter * 32;
-      if (row_ok && lane == 0) {
-        tma_store_wait_read0();                                      // my previous store has drained the buffer
-        mbar_expect_tx(&xbar[e2w], R_STG_WARP);
-        tma_load_3d(my_stg, &map_res, &xbar[e2w], col_base, row0, w.b);
-      }
-      mbar_wait_sleep(&acc2_full[u & 1], (uint32_t)((u >> 1) & 1));
+      const int row0 = w.t0 + quarter * 32, wb = w.b, bf = u & 1;
+      w.next(p);                                                    // now describes tile u + 1
+      const bool next_ok = u + 1 < q && w.live(p);
+      const uint32_t my_row = smem_u32(my_stg) + (uint32_t)(R_STG_TILE * bf) + (uint32_t)lane * 96u;
+      if (p.bridge) named_bar_sync(R_BAR_E2 + (u & 1), R_BAR_E2_COUNT);
+      else mbar_wait_backoff(&acc2_full[u & 1], (uint32_t)((u >> 1) & 1), p.sleep_ns);
       tc_fence_after();
       if (warp == R_CTRL + R_PW + R_E1W) R_STAMP(10, u);
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(256 + (u & 1) * 128 + col_base);
-      uint32_t r[2][16];
-      tc_ld16(taddr, r[0]);
-      uint4 rr[6];
-      if (row_ok) {
-        mbar_wait_sleep(&xbar[e2w], xpar);
-        xpar ^= 1;
-#pragma unroll
-        for (int c = 0; c < 6; ++c) rr[c] = lds128(my_row + 16u * (uint32_t)c);
-      }
+      if (row_ok) mbar_wait_backoff(&my_xbar[bf], (uint32_t)((u >> 1) & 1), p.sleep_ns);
 #pragma unroll
       for (int m = 0; m < 3; ++m) {
+        uint32_t r[1][16];
+        uint4 rr[6];
+        tc_ld16(taddr + 16u * (uint32_t)m, r[0]);
+        if (row_ok) { rr[2 * m] = lds128(my_row + 32u * (uint32_t)m); rr[2 * m + 1] = lds128(my_row + 32u * (uint32_t)m + 16u); }
         tc_wait_ld();
-        if (m + 1 < 3) {
-          tc_ld16(taddr + 16u * (uint32_t)(m + 1), r[(m + 1) & 1]);
-        } else {   // the accumulator has been read completely
+        if (m == 2) {   // the accumulator has been read completely
           tc_fence_before();
           __syncwarp();
           if (lane == 0) arrive_leader(&acc2_free[u & 1], rank);
         }
         if (row_ok) {
           const int col = col_base + 16 * m;
-          const uint32_t sb = cst_u32 + 4u * (uint32_t)(3 * R_C + col), se = sb + 4u * R_C, si = se + 4u * R_C;
+          const uint32_t sb = cst_u32 + 4u * (uint32_t)col, se = sb + 4u * R_C, si = se + 4u * R_C;
           uint32_t o[8];
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
@@ -453,8 +489,8 @@ resunit96_kernel(const __grid_constant__ CUtensorMap map_main, const __grid_cons
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const float2 f = Cvt<T16>::unpack(rw[e]);
-                v[2 * e] = __uint_as_float(r[m & 1][8 * h + 2 * e]) + bb[2 * e] + f.x;
-                v[2 * e + 1] = __uint_as_float(r[m & 1][8 * h + 2 * e + 1]) + bb[2 * e + 1] + f.y;
+                v[2 * e] = __uint_as_float(r[0][8 * h + 2 * e]) + bb[2 * e] + f.x;
+                v[2 * e + 1] = __uint_as_float(r[0][8 * h + 2 * e + 1]) + bb[2 * e + 1] + f.y;
               }
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
@@ -467,8 +503,8 @@ resunit96_kernel(const __grid_constant__ CUtensorMap map_main, const __grid_cons
               // the branch output is rounded to 16 bits, then added to the 16-bit stream with a packed add
 #pragma unroll
               for (int e = 0; e < 4; ++e)
-                o[4 * h + e] = Cvt<T16>::add2(Cvt<T16>::pack(__uint_as_float(r[m & 1][8 * h + 2 * e]) + bb[2 * e],
-                                                             __uint_as_float(r[m & 1][8 * h + 2 * e + 1]) + bb[2 * e + 1]), rw[e]);
+                o[4 * h + e] = Cvt<T16>::add2(Cvt<T16>::pack(__uint_as_float(r[0][8 * h + 2 * e]) + bb[2 * e],
+                                                             __uint_as_float(r[0][8 * h + 2 * e + 1]) + bb[2 * e + 1]), rw[e]);
             }
           }
           sts128(my_row + 32u * (uint32_t)m, make_uint4(o[0], o[1], o[2], o[3]));
@@ -478,10 +514,17 @@ resunit96_kernel(const __grid_constant__ CUtensorMap map_main, const __grid_cons
       if (row_ok) {
         fence_async_smem();
         __syncwarp();
-        if (lane == 0) { tma_store_3d(&map_out, my_stg, col_base, row0, w.b); tma_store_commit(); }
+        if (lane == 0) {
+          if (next_ok) {
+            tma_store_wait_read0();                                  // the store of tile u - 1 (issued a whole tile ago) has drained the other buffer
+            mbar_expect_tx(&my_xbar[bf ^ 1], R_STG_TILE);
+            tma_load_3d(my_stg + R_STG_TILE * (bf ^ 1), &map_res, &my_xbar[bf ^ 1], col_base, w.t0 + quarter * 32, w.b);
+          }
+          tma_store_3d(&map_out, my_stg + R_STG_TILE * bf, col_base, row0, wb);
+          tma_store_commit();
+        }
       }
       if (warp == R_CTRL + R_PW + R_E1W) R_STAMP(11, u);
-      w.next(p);
     }
     if (lane == 0) tma_store_wait_all();
   }
@@ -526,10 +569,12 @@ cudaError_t launch_resunit96(const ResUnitParams& p, const BatchGeom& g, int op_
   Res96Params q{};
   q.B = g.B; q.Tmax = g.Tmax; q.rows_per_frame = p.rows_per_frame; q.len_frames = g.len_frames;
   q.dil = p.dil; q.halo = 6 * p.dil; q.hb = (q.halo + 7) & ~7;
-  static const int slots_env = []() { const char* e = getenv("Q3TTS_RES_SLOTS"); return e ? atoi(e) : 0; }();
   const size_t fixed = R_W7_BYTES + R_W1_BYTES + R_STG_BYTES + R_CST + 512 + 1024;
-  auto tsub = [&](int n) { return ((uint32_t)(n * (q.hb + R_BM)) * 64u + 1023u) & ~1023u; };
-  q.nslots = (slots_env == 3 || (size_t)R_SUB * tsub(R_SLOTS) + fixed > 227 * 1024) ? 3 : R_SLOTS;   // dil 9: three slots
+  auto tsub = [&](int n) { return ((uint32_t)(n * (q.hb + R_BM)) * 64u + 511u) & ~511u; };   // SWIZZLE_64B repeats every 512 B
+  // Three ring slots: a slot is busy from the TMA issue to the end of conv7 of its tile (load ~1.5 k + pass 1 ~2.7 k + conv7 ~2 k cycles),
+  // about two tile periods.  The fourth slot's 26-35 KB now hold the second epilogue-2 staging buffer.
+  static const int slots_env = []() { const char* e = getenv("Q3TTS_RES_SLOTS"); return e ? atoi(e) : 3; }();
+  q.nslots = (slots_env == 4 && (size_t)R_SUB * tsub(4) + fixed <= 227 * 1024) ? 4 : 3;
   q.tsub_bytes = tsub(q.nslots);
   q.out = p.out;
   const uint32_t fmt = op_dtype == DT_F16 ? 0u : 1u;
@@ -538,6 +583,10 @@ cudaError_t launch_resunit96(const ResUnitParams& p, const BatchGeom& g, int op_
   q.out_snake = p.ea3 != nullptr;
   q.x_in = p.x_in; q.x_bstride = (long long)slot_rows * R_C;
   q.dbg = (long long*)p.dbg;
+  static const int sleep_env = []() { const char* e = getenv("Q3TTS_RES_SLEEP"); return e ? atoi(e) : 100; }();
+  q.sleep_ns = (uint32_t)sleep_env;
+  static const int bridge_env = []() { const char* e = getenv("Q3TTS_RES_BRIDGE"); return e ? atoi(e) : 1; }();
+  q.bridge = bridge_env;
   int sms = 0, dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -552,7 +601,7 @@ cudaError_t launch_resunit96(const ResUnitParams& p, const BatchGeom& g, int op_
     cuuint32_t box[3] = {cols, rows, 1};
     cuuint32_t es[3] = {1, 1, 1};
     return enc(m, dt, 3, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               cols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE,
+               cols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : (cols == 16 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE),
                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
   };
   auto w_map = [&](CUtensorMap* m, const void* base, int rows) -> bool {

@@ -56,6 +56,7 @@ struct Tc2Params {
   int cst_staged;                                // bias / snake constants of all N columns live in smem
   int tma_y, tma_a;                              // 16-bit outputs leave through smem staging + TMA store
   uint32_t staging_bytes;                        // smem reserved for the output staging buffers
+  int stg_bufs;                                  // block epilogue: staging buffers per warp (2: a chunk is staged while the previous one drains)
   uint32_t div_nt_m, div_nt_s, div_tpu_m, div_tpu_s;   // magic numbers: x / n_tiles, x / tiles_per_utt (x < 2^31)
   const float* bias; int act;
   const void* res; int ldres; long long res_bstride;
@@ -415,6 +416,8 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     // Epilogue 2 of the previous tile, N half h: acc2 = conv1(...); + b1 + X -> X' [, snake_next(X')].  The residual chunk
     // (32 rows x 32 columns of X) comes in by TMA into this warp's staging buffer, X' is written over it and leaves by TMA,
     // then the operand reuses the buffer: no scattered 16-byte global accesses (they cost 32 LSU wavefronts per instruction).
+    // (A second 2 KB buffer for the operand -- so that it need not wait for the X' store to drain this one -- measured SLOWER: the
+    // 24 KB come out of the A / W rings, 957 vs 1041-1107 TFLOP/s on block 2.)
     const uint32_t buf = smem_u32(staging) + (uint32_t)ew * 2048u, my_row = buf + (uint32_t)lane * 64u;
     const uint32_t sw64 = (uint32_t)((lane >> 1) & 3);
     uint32_t xpar = 0;
@@ -515,8 +518,12 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     const int ew = warp - 4, quarter = warp & 3, grp = ew >> 2;          // grp 0..2 takes chunks grp, grp+3, ...
     const int nch = p.BN / 32;
     const bool has_res = p.res != nullptr, has_y = p.out_y != nullptr, has_a = p.out_a != nullptr;
-    uint8_t* buf_a = staging + (size_t)ew * ((has_y && has_a) ? 4096 : 2048);   // this warp's 32 rows x 64 B: a, then y
-    uint8_t* buf_y = buf_a + (has_a ? 2048 : 0);
+    // This warp's staging: 32 rows x 64 B for a, then for y -- times stg_bufs.  With ONE buffer every chunk began by waiting until the
+    // TMA engine had read the previous chunk's stores out of it (queued behind the producer's loads: ~1-2 k cycles), which is why the
+    // HBM-bound GEMMs (1x1 convs, transposed convs) sat at 55-60 % of the HBM roofline; two buffers take that wait off the chain.
+    const uint32_t stg_one = (has_y && has_a) ? 4096u : 2048u;
+    uint8_t* const stg_base = staging + (size_t)ew * stg_one * (uint32_t)p.stg_bufs;
+    uint32_t chunk_ctr = 0;
     const int slot_rows = p.Tmax * p.rows_per_frame;
     const uint32_t cst_u32 = smem_u32(cst);
     const uint32_t sw64 = (uint32_t)((lane >> 1) & 3);                    // SWIZZLE_64B staging rows
@@ -543,7 +550,10 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             for (int c = 0; c < 4; ++c) rres[c] = __ldg((const uint4*)(res_row + ch * 32 + 8 * c));
           }
           tc_wait_ld();
-          if (lane == 0) tma_store_wait_read0();                          // my previous stores have drained the staging rows
+          uint8_t* buf_a = stg_base + (p.stg_bufs == 2 ? (chunk_ctr & 1u) * stg_one : 0u);
+          uint8_t* buf_y = buf_a + (has_a ? 2048 : 0);
+          ++chunk_ctr;
+          if (lane == 0) { if (p.stg_bufs == 2) tma_store_wait_read1(); else tma_store_wait_read0(); }   // the stores that last used this buffer have drained it
           __syncwarp();
           const int n = n0 + ch * 32;
           const uint32_t sb = cst_u32 + 4u * (uint32_t)n, se = sb + 4u * (uint32_t)p.N, si = se + 4u * (uint32_t)p.N;
@@ -939,7 +949,9 @@ static cudaError_t launch_tc2_impl(const ConvGemmParams& p, const BatchGeom& g, 
     if (q.tma_y && !out_map(&map_y, q.out_y, q.ldy, q.y_bstride)) return cudaErrorInvalidValue;
     if (q.tma_a && !out_map(&map_o, q.out_a, q.lda_out, q.ao_bstride)) return cudaErrorInvalidValue;
   }
-  q.staging_bytes = !(q.tma_y || q.tma_a) ? 0u : (epi_block ? (uint32_t)T2_EPI_WARPS_BLOCK * ((q.tma_y && q.tma_a && !fuse) ? 4096u : 2048u) : T2_STAGING_BYTES);
+  static const int stg2_env = env_int("Q3TTS_TC_STG2", 0);   // measured: the second buffer costs ring depth and the transposed convs lose more than the 1x1 convs gain
+  q.stg_bufs = (epi_block && !fuse && stg2_env) ? 2 : 1;
+  q.staging_bytes = !(q.tma_y || q.tma_a) ? 0u : (epi_block ? (uint32_t)T2_EPI_WARPS_BLOCK * ((q.tma_y && q.tma_a && !fuse) ? 4096u : 2048u) * (uint32_t)q.stg_bufs : T2_STAGING_BYTES);
   const size_t fixed = q.staging_bytes + (fuse ? (size_t)q.ncb2 * ((q.a_tmem ? 0 : 16384) + 2 * q.w1_blk_bytes) : 0) + (q.cst_staged ? (size_t)(fuse ? 6 : 3) * p.N * 4 : 0) + 640 + 1024;
   auto magic = [](uint32_t d, uint32_t* m, uint32_t* sh) {   // x / d == umulhi(x, m) >> sh for 0 <= x < 2^31
     uint32_t lg = 0;

@@ -70,6 +70,27 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, 
         : "=r"(done) : "r"(addr), "r"(parity), "r"(hint_ns) : "memory");
   } while (!done);
 }
+// Wait for roles that expect to wait LONG (epilogue / element-wise warps of a pipeline whose tensor work runs for microseconds).
+// ncu on the fused residual unit (profiles/r2_resunit.md): with `try_wait ..., suspendTimeHint` ptxas emits
+// TRYWAIT + NANOSLEEP.SYNCS + PHASECHK + BRA and the sleep returns on ANY barrier event of the CTA -- 79 iterations per wait, 32 % of
+// all issued warp-instructions were these four.  Here a waiting warp really sleeps (nanosleep.u32 is not woken by barrier traffic)
+// and polls with the non-blocking test_wait: a few instructions per microsecond per waiting warp.
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return done != 0;
+}
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  if (mbar_test(bar, parity)) return;
+  if (ns == 0) { mbar_wait(bar, parity); return; }
+  do {
+    asm volatile("nanosleep.u32 %0;" ::"r"(ns) : "memory");
+  } while (!mbar_test(bar, parity));
+}
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
@@ -99,6 +120,29 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// Column-sliced TMEM access (the mma.m16n8 accumulator layout): 16 lanes x 256 bits, twice along the columns.  With taddr = (lane l0,
+// column c), thread t of the warp holds, for j = 0, 1:
+//   r[4j+0], r[4j+1] = (lane l0 + t/4,     columns c + 8j + 2(t%4), + 1)
+//   r[4j+2], r[4j+3] = (lane l0 + t/4 + 8, same columns)
+// A thread sees 4 of every 16 columns, so per-column constants of a 48-column slice are 12 values per thread: they live in registers.
+// (With .32x32b a thread holds a whole row, needs every column's constants, and re-reads them from shared memory for every tile.)
+__device__ __forceinline__ void tc_ld_16x256b_x2(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr) : "memory");
+}
+// The matching store of 16-bit pairs: 16 lanes x 128 bits, twice.  Thread t holds r[2j] = (lane l0 + t/4, 32-bit column c + 4j + t%4),
+// r[2j+1] = (lane l0 + t/4 + 8, same column): two adjacent fp32 columns of the load above, packed, land in one 32-bit column.
+__device__ __forceinline__ void tc_st_16x128b_x2(uint32_t taddr, const uint32_t (&r)[4]) {
+  asm volatile("tcgen05.st.sync.aligned.16x128b.x2.b32 [%0], {%1, %2, %3, %4};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t saddr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts32(uint32_t saddr, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory"); }
 
 // K-major, 128-byte-swizzled operand tile: rows are 128 B apart, 8-row groups 1024 B apart (SBO), descriptor v1.
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
@@ -181,6 +225,9 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void*
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+// all but the 2 most recent bulk groups of this thread have finished READING shared memory
+__device__ __forceinline__ void tma_store_wait_read2() { asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }

@@ -152,3 +152,21 @@ def test_16bit_numeric_model(tiny_oracle, operand, floor):
     ref = dec.forward(codes).numpy()
     lo = decoder.OracleDecoder(cfg, w, torch.float32, operand=operand, store=operand).forward(codes).numpy()
     assert decoder.snr_db(ref, lo) >= floor
+
+
+def test_full_size_operand_precision_bf16_cannot_meet_40_db(full_oracle):
+    # DESIGN.md section 4, as evidence instead of prose: on the FULL-size decoder, rounding only the GEMM / conv / attention OPERANDS to
+    # bf16 -- fp32 accumulation, fp32 residual stream, fp32 activations, i.e. better than any bf16 engine can do -- already lands far
+    # below north_star's 40 dB; the same experiment with fp16 operands clears it.  The 16-bit headline mode is therefore fp16 (same
+    # tensor-core rate, `kind::f16`), and bf16 is reported beside it, not instead of it.
+    cfg, w, dec32 = full_oracle
+    codes = synth_codes(cfg, 1, 20, 1001)
+    ref = dec32.forward(codes).numpy()
+    snr = {}
+    for operand in ("bf16", "fp16"):
+        lo = decoder.OracleDecoder(cfg, w, torch.float32, operand=operand).forward(codes).numpy()
+        snr[operand] = decoder.snr_db(ref, lo)
+    print(f"full-size operand rounding only: bf16 {snr['bf16']:.1f} dB, fp16 {snr['fp16']:.1f} dB")
+    assert snr["bf16"] < 32.0          # measured 27 dB: 13 dB short of the bar with everything else ideal
+    assert snr["fp16"] >= 42.0         # measured 44.9 dB
+    assert snr["fp16"] - snr["bf16"] >= 12.0   # three mantissa bits = 18 dB in theory
