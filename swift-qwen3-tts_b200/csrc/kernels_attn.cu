@@ -9,6 +9,8 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
+#include <algorithm>
+#include <cstdlib>
 #include <type_traits>
 
 #include "kernels.cuh"
@@ -170,32 +172,14 @@ template <typename T16, int C>
 __global__ void __launch_bounds__(128)
 tail_mma_kernel(const T16* __restrict__ a, int64_t a_bstride, const float* __restrict__ w /*[7][C]*/, float bias, float* __restrict__ pcm,
                 const int64_t* __restrict__ pcm_base, float* __restrict__ tap, int64_t tap_bstride, BatchGeom g, int rows_per_frame,
-                int tiles_per_utt) {
+                int tiles_per_utt, int tiles_per_cta) {
   constexpr int STRIDE = C + 8, V = C / 8, KS = C / 16;
   __shared__ __align__(16) T16 tile[TT_IN * STRIDE];
   __shared__ float P[TT_IN][8];
-  const int b = blockIdx.x / tiles_per_utt;
-  const int64_t t0 = (int64_t)(blockIdx.x % tiles_per_utt) * TT_ROWS;
-  const int64_t slot_rows = (int64_t)g.Tmax * rows_per_frame, valid = (int64_t)g.len_frames[b] * rows_per_frame;
-  if (t0 >= valid) return;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tg = lane & 3;
-  const T16* ab = a + (int64_t)b * a_bstride;
-  // all of a thread's 16-byte loads are issued before the first store: one HBM round trip per CTA instead of one per chunk
-  constexpr int NLD = (TT_IN * V + 127) / 128;
-  uint4 ld[NLD];
-#pragma unroll
-  for (int i = 0; i < NLD; ++i) {
-    const int idx = tid + i * 128, row = idx / V, c8 = idx % V;
-    const int64_t tin = t0 - TT_HALO + row;
-    ld[i] = make_uint4(0, 0, 0, 0);
-    if (idx < TT_IN * V && tin >= 0 && tin < slot_rows && row < TT_ROWS + TT_HALO) ld[i] = __ldg((const uint4*)(ab + tin * C + c8 * 8));
-  }
-#pragma unroll
-  for (int i = 0; i < NLD; ++i) {
-    const int idx = tid + i * 128, row = idx / V, c8 = idx % V;
-    if (idx < TT_IN * V) *(uint4*)&tile[row * STRIDE + c8 * 8] = ld[i];
-  }
-  // B fragments (col-major [K][8]): b0 = W[k = 2tg, 2tg+1][n = gq], b1 = W[k = 2tg+8, +9][n = gq]; tap 7 is a zero column
+  // B fragments (col-major [K][8]): b0 = W[k = 2tg, 2tg+1][n = gq], b1 = W[k = 2tg+8, +9][n = gq]; tap 7 is a zero column.
+  // Built ONCE per CTA: a CTA walks `tiles_per_cta` consecutive tiles (the set-up is ~150 instructions per thread, as much as the
+  // work on one tile).
   uint32_t bh[KS][2], bl[KS][2];
 #pragma unroll
   for (int kk = 0; kk < KS; ++kk)
@@ -210,27 +194,54 @@ tail_mma_kernel(const T16* __restrict__ a, int64_t a_bstride, const float* __res
       bh[kk][h] = hi;
       bl[kk][h] = Mma<T16>::pack(w0 - hf.x, w1 - hf.y);
     }
-  __syncthreads();
-  for (int grp = warp; grp < TT_IN / 16; grp += 4) {
-    float c4[4] = {0.f, 0.f, 0.f, 0.f};
+  const int64_t slot_rows = (int64_t)g.Tmax * rows_per_frame;
+  const long long total_tiles = (long long)g.B * tiles_per_utt;
+  for (int it = 0; it < tiles_per_cta; ++it) {
+    const long long tile_id = (long long)blockIdx.x * tiles_per_cta + it;
+    if (tile_id >= total_tiles) break;
+    const int b = (int)(tile_id / tiles_per_utt);
+    const int64_t t0 = (int64_t)(tile_id % tiles_per_utt) * TT_ROWS;
+    const int64_t valid = (int64_t)g.len_frames[b] * rows_per_frame;
+    if (t0 >= valid) continue;                                   // block-uniform
+    const T16* ab = a + (int64_t)b * a_bstride;
+    // all of a thread's 16-byte loads are issued before the first store: one HBM round trip per tile instead of one per chunk
+    constexpr int NLD = (TT_IN * V + 127) / 128;
+    uint4 ld[NLD];
 #pragma unroll
-    for (int kk = 0; kk < KS; ++kk) {
-      uint32_t af[4];
-      ldsm_x4(af, smem_addr(&tile[(grp * 16 + (lane & 15)) * STRIDE + kk * 16 + (lane >> 4) * 8]));
-      Mma<T16>::run(c4, af, bh[kk][0], bh[kk][1]);
-      Mma<T16>::run(c4, af, bl[kk][0], bl[kk][1]);
+    for (int i = 0; i < NLD; ++i) {
+      const int idx = tid + i * 128, row = idx / V, c8 = idx % V;
+      const int64_t tin = t0 - TT_HALO + row;
+      ld[i] = make_uint4(0, 0, 0, 0);
+      if (idx < TT_IN * V && tin >= 0 && tin < slot_rows && row < TT_ROWS + TT_HALO) ld[i] = __ldg((const uint4*)(ab + tin * C + c8 * 8));
     }
-    *(float2*)&P[grp * 16 + gq][2 * tg] = make_float2(c4[0], c4[1]);
-    *(float2*)&P[grp * 16 + gq + 8][2 * tg] = make_float2(c4[2], c4[3]);
-  }
-  __syncthreads();
-  const int64_t t = t0 + tid;
-  if (t < valid) {
-    float v = bias;
+    __syncthreads();                                             // the previous tile's reads of `tile` and `P` are over
 #pragma unroll
-    for (int j = 0; j < 7; ++j) v += P[tid + j][j];      // input row t-6+j sits at tile row (t - t0) + j
-    if (tap) tap[(int64_t)b * tap_bstride + t] = v;
-    store_pcm(pcm, pcm_base[b] + t, v, g.pcm_i16);
+    for (int i = 0; i < NLD; ++i) {
+      const int idx = tid + i * 128, row = idx / V, c8 = idx % V;
+      if (idx < TT_IN * V) *(uint4*)&tile[row * STRIDE + c8 * 8] = ld[i];
+    }
+    __syncthreads();
+    for (int grp = warp; grp < TT_IN / 16; grp += 4) {
+      float c4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int kk = 0; kk < KS; ++kk) {
+        uint32_t af[4];
+        ldsm_x4(af, smem_addr(&tile[(grp * 16 + (lane & 15)) * STRIDE + kk * 16 + (lane >> 4) * 8]));
+        Mma<T16>::run(c4, af, bh[kk][0], bh[kk][1]);
+        Mma<T16>::run(c4, af, bl[kk][0], bl[kk][1]);
+      }
+      *(float2*)&P[grp * 16 + gq][2 * tg] = make_float2(c4[0], c4[1]);
+      *(float2*)&P[grp * 16 + gq + 8][2 * tg] = make_float2(c4[2], c4[3]);
+    }
+    __syncthreads();
+    const int64_t t = t0 + tid;
+    if (t < valid) {
+      float v = bias;
+#pragma unroll
+      for (int j = 0; j < 7; ++j) v += P[tid + j][j];      // input row t-6+j sits at tile row (t - t0) + j
+      if (tap) tap[(int64_t)b * tap_bstride + t] = v;
+      store_pcm(pcm, pcm_base[b] + t, v, g.pcm_i16);
+    }
   }
 }
 }  // namespace
@@ -250,8 +261,11 @@ bool tail_mma_supported(int dtype, int C) { return (dtype == DT_F16 || dtype == 
 void launch_tail_mma(const void* a, int dtype, int64_t a_bstride, const float* w, float bias, int C, float* pcm, const int64_t* pcm_base,
                      float* tap, int64_t tap_bstride, const BatchGeom& g, int rows_per_frame, cudaStream_t s) {
   const int tiles = (int)(((int64_t)g.Tmax * rows_per_frame + TT_ROWS - 1) / TT_ROWS);
-  const unsigned blocks = (unsigned)(g.B * tiles);
-#define Q3_TAILM(T, CC) tail_mma_kernel<T, CC><<<blocks, 128, 0, s>>>((const T*)a, a_bstride, w, bias, pcm, pcm_base, tap, tap_bstride, g, rows_per_frame, tiles)
+  const long long total = (long long)g.B * tiles;
+  static const int per_env = [] { const char* e = getenv("Q3TTS_TAIL_TILES"); return e ? atoi(e) : 8; }();
+  const int per_cta = (int)std::max<long long>(1, std::min<long long>(per_env, total / (148 * 12)));   // keep >= 12 CTAs per SM's worth of blocks
+  const unsigned blocks = (unsigned)((total + per_cta - 1) / per_cta);
+#define Q3_TAILM(T, CC) tail_mma_kernel<T, CC><<<blocks, 128, 0, s>>>((const T*)a, a_bstride, w, bias, pcm, pcm_base, tap, tap_bstride, g, rows_per_frame, tiles, per_cta)
   if (dtype == DT_F16) { if (C == 96) Q3_TAILM(__half, 96); else if (C == 64) Q3_TAILM(__half, 64); else Q3_TAILM(__half, 128); }
   else { if (C == 96) Q3_TAILM(__nv_bfloat16, 96); else if (C == 64) Q3_TAILM(__nv_bfloat16, 64); else Q3_TAILM(__nv_bfloat16, 128); }
 #undef Q3_TAILM
