@@ -39,7 +39,9 @@ namespace q3 {
 namespace {
 using namespace tc;
 
-#define R_STAMP(ev, tile) do { if (p.dbg && blockIdx.x == 0 && (tile) < 32 && lane == 0) p.dbg[(ev) * 32 + (tile)] = clock64(); } while (0)
+// clock64 stamps of CTA 0 (pipeline debugging): compiled in only in the kDbg instantiation -- the predicates alone cost every role a
+// few instructions per tile, and the kernel is bound by instruction issue.
+#define R_STAMP(ev, tile) do { if (kDbg && p.dbg && blockIdx.x == 0 && (tile) < 32 && lane == 0) p.dbg[(ev) * 32 + (tile)] = clock64(); } while (0)
 
 constexpr int R_C = 96, R_SUB = 3, R_BM = 128, R_SLOTS = 4, R_CTRL = 2, R_PW = 9, R_E1W = 8, R_E2W = 8;   // control (producer, MMA), pass-1, epilogue-1, epilogue-2 warps
 constexpr int R_THREADS = (R_CTRL + R_PW + R_E1W + R_E2W) * 32;
@@ -121,7 +123,7 @@ __device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t (&r)[8]) {
                ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
 }
 
-template <typename T16>
+template <typename T16, bool kDbg>
 __global__ void __launch_bounds__(R_THREADS, 1)
 resunit96_kernel(const __grid_constant__ CUtensorMap map_main, const __grid_constant__ CUtensorMap map_halo,
                  const __grid_constant__ CUtensorMap map_w7, const __grid_constant__ CUtensorMap map_w1,
@@ -629,13 +631,19 @@ cudaError_t launch_resunit96(const ResUnitParams& p, const BatchGeom& g, int op_
   cfg.numAttrs = 1;
   static tc::PerDeviceOnce optin;
   const cudaError_t oe = optin.ensure([]() {
-    cudaError_t e = cudaFuncSetAttribute(resunit96_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(resunit96_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(resunit96_kernel<__half, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(resunit96_kernel<__nv_bfloat16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(resunit96_kernel<__half, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(resunit96_kernel<__nv_bfloat16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     return e;
   });
   if (oe != cudaSuccess) return oe;
-  if (op_dtype == DT_F16) return cudaLaunchKernelEx(&cfg, resunit96_kernel<__half>, map_main, map_halo, map_w7, map_w1, map_res, map_out, q);
-  return cudaLaunchKernelEx(&cfg, resunit96_kernel<__nv_bfloat16>, map_main, map_halo, map_w7, map_w1, map_res, map_out, q);
+  if (q.dbg) {
+    if (op_dtype == DT_F16) return cudaLaunchKernelEx(&cfg, resunit96_kernel<__half, true>, map_main, map_halo, map_w7, map_w1, map_res, map_out, q);
+    return cudaLaunchKernelEx(&cfg, resunit96_kernel<__nv_bfloat16, true>, map_main, map_halo, map_w7, map_w1, map_res, map_out, q);
+  }
+  if (op_dtype == DT_F16) return cudaLaunchKernelEx(&cfg, resunit96_kernel<__half, false>, map_main, map_halo, map_w7, map_w1, map_res, map_out, q);
+  return cudaLaunchKernelEx(&cfg, resunit96_kernel<__nv_bfloat16, false>, map_main, map_halo, map_w7, map_w1, map_res, map_out, q);
 }
 
 }  // namespace q3
