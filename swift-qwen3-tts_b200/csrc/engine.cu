@@ -286,6 +286,18 @@ Model* model_create(const Checkpoint& ck, const q3tts_options& opts) {
     const HostTensor& w = T(ck, dd + "outConv.conv.weight");   // [1,7,C]
     m.tail_w = upload(m, w.data);
     m.tail_bias = T(ck, dd + "outConv.conv.bias").data[0];
+    // outConv inside the last residual unit (kernels_res96.cu tail mode): possible when that unit runs as the fused kernel
+    static const int tail_env = []() { const char* e = getenv("Q3TTS_FUSED_TAIL"); return e ? atoi(e) : 1; }();
+    const BlockW& B3 = m.blocks[3];
+    ResUnitParams probe{};
+    probe.C = B3.cout; probe.dil = 1;
+    if (tail_env && m.op_dtype != DT_F32 && m.st_dtype == m.op_dtype && B3.conv7[0].taps == 7 && resunit96_supported(probe, m.op_dtype)) {
+      CUDA_OK(cudaMalloc(&m.tail_w16, (size_t)16 * B3.cout * 2));
+      m.allocs.push_back(m.tail_w16);
+      launch_tail_tile(m.tail_w, B3.cout, m.tail_w16, m.op_dtype, m.stream);
+      CUDA_OK(cudaStreamSynchronize(m.stream));
+      m.fused_tail = true;
+    }
   }
   {  // default activation budget: 64 GiB (a batch of 64 x 30 s in one launch chain) or 45 % of what is free now
     size_t free_b = 0, total_b = 0;
@@ -573,9 +585,12 @@ static void run_back(Ctx& x, Plan& P, const void* to, const int64_t* d_pcm_base,
         rp.ea1 = Bk.act_in_next[j].ea; rp.ib1 = Bk.act_in_next[j].ib; rp.ea2 = Bk.act2[j].ea; rp.ib2 = Bk.act2[j].ib;
         rp.ea3 = j == 2 ? block_out->ea : nullptr; rp.ib3 = j == 2 ? block_out->ib : nullptr;
         rp.dil = Bk.conv7[j].dil;
+        const bool tail = i == 3 && j == 2 && m.fused_tail;        // the decoder's last unit: outConv's products instead of activations
+        rp.wout = tail ? m.tail_w16 : nullptr; rp.p_out = tail ? (float*)P.blk[i].C : nullptr;
         halo_in(x, bufs[j], rate, Bk.cout, (int)dt_size(op));
         const double rows = (double)valid_frames * rate, C = (double)Bk.cout;
-        const double fl = 2.0 * rows * 8.0 * C * C, by = rows * C * 2.0 * 2.0 + 8.0 * C * C * 2.0;   // X in, X' out (the halo stays on chip), weights once
+        // X in, X' out (the halo stays on chip), weights once; tail mode: 16 fp32 partial products per row go out instead
+        const double fl = 2.0 * rows * (8.0 * C * C + (tail ? 16.0 * C : 0.0)), by = rows * (C * 2.0 + (tail ? 64.0 : C * 2.0)) + 8.0 * C * C * 2.0;
         launch_begin(x, "resunit", fl, by);
         cudaError_t err = launch_resunit96(rp, x.g, op, s);
         if (err != cudaSuccess) throw Error(Q3TTS_ECUDA, std::string("fused residual unit launch: ") + cudaGetErrorString(err));
@@ -587,7 +602,7 @@ static void run_back(Ctx& x, Plan& P, const void* to, const int64_t* d_pcm_base,
       if (taps) {
         // Stage tap with the fused kernels ON: the block's last unit only writes snake_next(X'), so the tap re-runs that unit
         // without the consumer's activation into the (now free) A buffer.  One extra launch, in tap mode only.
-        rp.x_in = bufs[2]; rp.out = P.blk[i].A; rp.ea3 = nullptr; rp.ib3 = nullptr;
+        rp.x_in = bufs[2]; rp.out = P.blk[i].A; rp.ea3 = nullptr; rp.ib3 = nullptr; rp.wout = nullptr; rp.p_out = nullptr;
         cudaError_t err = launch_resunit96(rp, x.g, op, s);
         if (err != cudaSuccess) throw Error(Q3TTS_ECUDA, std::string("fused residual unit launch (tap): ") + cudaGetErrorString(err));
         count_launch(x);
@@ -640,12 +655,23 @@ static void run_back(Ctx& x, Plan& P, const void* to, const int64_t* d_pcm_base,
   {
     const int C = m.blocks[3].cout;
     float* tp = taps ? tap_buffer(m, "out_conv", B, 1, (int64_t)Tmax * rate) : nullptr;
-    halo_in(x, a_in, rate, C, (int)dt_size(op));
-    launch_begin(x, "conv7_clip", 2.0 * 7 * C * (double)valid_frames * rate, (double)valid_frames * rate * (C * (double)dt_size(op) + 4.0));
-    launch_tail(a_in, op, (int64_t)Tmax * rate * C, m.tail_w, m.tail_bias, C, d_pcm, d_pcm_base, tp, (int64_t)Tmax * rate, x.g, rate, s);
-    launch_end(x);
-    count_launch(x);
-    account(x, 2.0 * 7 * C * (double)valid_frames * rate, (double)valid_frames * rate * (C * (double)dt_size(op) + 4.0));
+    if (m.fused_tail) {
+      // a_in holds P[row][16] fp32, the outConv partial products block 3's last unit computed on chip
+      const double fl = 14.0 * (double)valid_frames * rate, by = (double)valid_frames * rate * (64.0 + 4.0);
+      halo_in(x, a_in, rate, 16, 4);
+      launch_begin(x, "tap_sum_clip", fl, by);
+      launch_tail_from_partials((const float*)a_in, (int64_t)Tmax * rate * 16, m.tail_bias, d_pcm, d_pcm_base, tp, (int64_t)Tmax * rate, x.g, rate, s);
+      launch_end(x);
+      count_launch(x);
+      account(x, fl, by);
+    } else {
+      halo_in(x, a_in, rate, C, (int)dt_size(op));
+      launch_begin(x, "conv7_clip", 2.0 * 7 * C * (double)valid_frames * rate, (double)valid_frames * rate * (C * (double)dt_size(op) + 4.0));
+      launch_tail(a_in, op, (int64_t)Tmax * rate * C, m.tail_w, m.tail_bias, C, d_pcm, d_pcm_base, tp, (int64_t)Tmax * rate, x.g, rate, s);
+      launch_end(x);
+      count_launch(x);
+      account(x, 2.0 * 7 * C * (double)valid_frames * rate, (double)valid_frames * rate * (C * (double)dt_size(op) + 4.0));
+    }
   }
   stage_end(x);
 }
@@ -764,7 +790,8 @@ std::vector<HaloStage> conv_state_layout(const Model& m) {
     rate *= Bk.rate;
     for (int j = 0; j < 3; ++j) push((Bk.conv7[j].taps - 1) * Bk.conv7[j].dil, rate, Bk.cout, ops);
   }
-  push(6, rate, m.blocks[3].cout, ops);                                      // outConv k = 7
+  if (m.fused_tail) push(6, rate, 16, 4);                                    // outConv k = 7 on the partial products (fp32 [row][16])
+  else push(6, rate, m.blocks[3].cout, ops);                                 // outConv k = 7
   return v;
 }
 

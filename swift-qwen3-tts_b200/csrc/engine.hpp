@@ -85,6 +85,8 @@ struct Model {
   SnakeW out_snake;
   float* tail_w = nullptr;                // [7][C]
   float tail_bias = 0.f;
+  void* tail_w16 = nullptr;               // [16][C] hi / lo tap tile in the operand type (launch_tail_tile)
+  bool fused_tail = false;                // block 3's last residual unit multiplies its output with tail_w16 and stores 16 partial products per row
   std::map<std::string, std::vector<int64_t>> weight_shapes;  // Swift key -> MLX shape
 
   // workspace

@@ -112,6 +112,11 @@ void launch_tail(const void* a, int a_dtype, int64_t a_bstride, const float* w /
 
 // Same op on the warp-level tensor path for 16-bit operands (kernels_attn.cu): [rows x C] . [C x 8] with HMMA, then the 7-tap diagonal sum.
 bool tail_mma_supported(int dtype, int C);
+// outConv split in two: the last residual unit (tail mode) multiplies its on-chip output with the [16][C] hi/lo tap tile and stores
+// 16 partial products per row; this kernel adds the seven that belong to each sample, then bias + clip (ST.swift:687-688, 781)
+void launch_tail_tile(const float* w /*[7][C]*/, int C, void* out16 /*[16][C]*/, int dtype, cudaStream_t s);
+void launch_tail_from_partials(const float* P, int64_t p_bstride, float bias, float* pcm, const int64_t* pcm_base, float* tap,
+                               int64_t tap_bstride, const BatchGeom& g, int rows_per_frame, cudaStream_t s);
 void launch_tail_mma(const void* a, int dtype, int64_t a_bstride, const float* w, float bias, int C, float* pcm,
                      const int64_t* pcm_base, float* tap, int64_t tap_bstride, const BatchGeom& g, int rows_per_frame, cudaStream_t s);
 
@@ -157,6 +162,9 @@ struct ResUnitParams {
   const float *ea1, *ib1, *ea2, *ib2;   // snake before conv7, between the convs
   const float *ea3, *ib3;               // optional: activation of the consumer, applied to the output
   int C, dil, rows_per_frame;
+  // tail mode (the decoder's last unit, ea3 = outSnake): instead of `out`, the unit writes the outConv partial products
+  // P[row][16] fp32 = snake3(X')[row] . wout[n] (wout: [16][C] 16-bit, launch_tail_tile) -- `out` is not written
+  const void* wout = nullptr; float* p_out = nullptr;
   void* dbg;                            // optional device buffer [16][32] of clock64 stamps (pipeline debugging)
 };
 bool resunit96_supported(const ResUnitParams& p, int op_dtype);

@@ -244,7 +244,73 @@ tail_mma_kernel(const T16* __restrict__ a, int64_t a_bstride, const float* __res
     }
   }
 }
+
+// ---- outConv from the partial products the last residual unit left (kernels_res96.cu, tail mode) -----------------------------
+// P[row][16] fp32: columns 0..6 = a[row] . hi(w[j]), 8..14 = a[row] . lo(w[j]) (w = hi + lo in the operand type: the 16-bit
+// tensor-core product keeps fp32 weights).  out[t] = bias + sum_j (P[t-6+j][j] + P[t-6+j][8+j]); rows before the utterance are
+// the causal zero padding.  64 B per row come in, 4 B (or 2) go out: the 192-byte activation row never exists in HBM.
+constexpr int TP_ROWS = 256, TP_IN = TP_ROWS + 6, TP_LD = 17;
+__global__ void __launch_bounds__(TP_ROWS)
+tail_from_partials_kernel(const float* __restrict__ P, int64_t p_bstride, float bias, float* __restrict__ pcm, const int64_t* __restrict__ pcm_base,
+                          float* __restrict__ tap, int64_t tap_bstride, BatchGeom g, int rows_per_frame, int tiles_per_utt) {
+  __shared__ float sp[TP_IN * TP_LD];
+  const int b = blockIdx.x / tiles_per_utt, tid = threadIdx.x;
+  const int64_t t0 = (int64_t)(blockIdx.x % tiles_per_utt) * TP_ROWS;
+  const int64_t valid = (int64_t)g.len_frames[b] * rows_per_frame;
+  if (t0 >= valid) return;
+  const float* pb = P + (int64_t)b * p_bstride;
+  for (int idx = tid; idx < TP_IN * 4; idx += TP_ROWS) {
+    const int row = idx >> 2, c4 = idx & 3;
+    const int64_t tin = t0 - 6 + row;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tin >= 0 && tin < valid) v = __ldg((const float4*)(pb + tin * 16) + c4);
+    float* d = &sp[row * TP_LD + 4 * c4];
+    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+  }
+  __syncthreads();
+  const int64_t t = t0 + tid;
+  if (t < valid) {
+    float v = bias;
+#pragma unroll
+    for (int j = 0; j < 7; ++j) v += sp[(tid + j) * TP_LD + j] + sp[(tid + j) * TP_LD + 8 + j];
+    if (tap) tap[(int64_t)b * tap_bstride + t] = v;
+    store_pcm(pcm, pcm_base[b] + t, v, g.pcm_i16);
+  }
+}
+
+// [16][C] operand tile for that product: rows 0..6 the taps rounded to the operand type, rows 8..14 the rounding residues, 7 and 15 zero
+template <typename T16>
+__global__ void tail_tile_kernel(const float* __restrict__ w, int C, T16* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 8 * C) return;
+  const int j = i / C, c = i % C;
+  float hi = 0.f, lo = 0.f;
+  if (j < 7) {
+    const float v = w[j * C + c];
+    const uint32_t pk = Mma<T16>::pack(v, 0.f);
+    float2 hf;
+    if (std::is_same<T16, __half>::value) hf = __half22float2(*(const __half2*)&pk);
+    else hf = __bfloat1622float2(*(const __nv_bfloat162*)&pk);
+    hi = hf.x; lo = v - hf.x;
+  }
+  const uint32_t ph = Mma<T16>::pack(hi, 0.f), pl = Mma<T16>::pack(lo, 0.f);
+  out[j * C + c] = *(const T16*)&ph;
+  out[(8 + j) * C + c] = *(const T16*)&pl;
+}
 }  // namespace
+
+void launch_tail_tile(const float* w, int C, void* out16, int dtype, cudaStream_t s) {
+  const unsigned blocks = (unsigned)((8 * C + 127) / 128);
+  if (dtype == DT_F16) tail_tile_kernel<__half><<<blocks, 128, 0, s>>>(w, C, (__half*)out16);
+  else tail_tile_kernel<__nv_bfloat16><<<blocks, 128, 0, s>>>(w, C, (__nv_bfloat16*)out16);
+}
+
+void launch_tail_from_partials(const float* P, int64_t p_bstride, float bias, float* pcm, const int64_t* pcm_base, float* tap,
+                               int64_t tap_bstride, const BatchGeom& g, int rows_per_frame, cudaStream_t s) {
+  const int tiles = (int)(((int64_t)g.Tmax * rows_per_frame + TP_ROWS - 1) / TP_ROWS);
+  tail_from_partials_kernel<<<(unsigned)((long long)g.B * tiles), TP_ROWS, 0, s>>>(P, p_bstride, bias, pcm, pcm_base, tap, tap_bstride, g,
+                                                                                     rows_per_frame, tiles);
+}
 
 bool attention_mma_supported(int dtype, int hd) { return (dtype == DT_F16 || dtype == DT_BF16) && hd == 64; }
 

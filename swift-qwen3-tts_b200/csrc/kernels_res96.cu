@@ -53,6 +53,7 @@ constexpr uint32_t R_TMEM_COLS = 512;
 constexpr uint32_t R_STG_TILE = 32 * 48 * 2;         // epilogue 2: one warp's 32 rows x 48 channels (residual in, X' out)
 constexpr uint32_t R_STG_WARP = 2 * R_STG_TILE;      // two buffers per warp, alternating by tile
 constexpr uint32_t R_STG_BYTES = R_E2W * R_STG_WARP;
+constexpr uint32_t R_WOUT_BYTES = R_SUB * 8 * 64;     // tail mode: this CTA's 8 rows of the [16][96] hi / lo outConv tile
 
 struct Res96Params {
   int B, Tmax, rows_per_frame;
@@ -69,6 +70,14 @@ struct Res96Params {
   long long* dbg;                 // optional [16 events][32 tiles] clock64 stamps of CTA 0 (pipeline debugging)
   uint32_t sleep_ns;              // back-off of the waiting role warps (Q3TTS_RES_SLEEP; 0 = poll)
   int bridge;                     // 1: the epilogue warps block on named barriers released by warp 0 (see the producer role)
+  // Fused tail (last unit of the last block): the unit's output a = snake3(X') is NOT written.  Epilogue 2 packs it back into tensor
+  // memory and a third MMA multiplies it with outConv's 7 taps (ST.swift:674-678), split into hi + lo 16-bit halves:
+  // P[row][0..6] = sum_c w_hi[j][c] a[row][c], P[row][8..14] = the same with w_lo.  Only P (64 B per row instead of 192 B of
+  // activations) goes to HBM; the tail kernel adds the 7 shifted rows.  0: off.
+  int tail;
+  int stg_bufs;                   // staging buffers per epilogue-2 warp (tail mode needs one: nothing is stored from it)
+  uint32_t idesc3;                // M = 256, N = 16
+  float* p_out; long long p_bstride; int slot_rows;   // P [B, slot_rows, 16] fp32
 };
 
 // Named barriers (id 0 is __syncthreads): the 8 warps of an epilogue role block in bar.sync -- a blocked warp issues nothing -- and
@@ -123,18 +132,20 @@ __device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t (&r)[8]) {
                ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
 }
 
-template <typename T16, bool kDbg>
+template <typename T16, bool kDbg, bool kTail>
 __global__ void __launch_bounds__(R_THREADS, 1)
 resunit96_kernel(const __grid_constant__ CUtensorMap map_main, const __grid_constant__ CUtensorMap map_halo,
                  const __grid_constant__ CUtensorMap map_w7, const __grid_constant__ CUtensorMap map_w1,
-                 const __grid_constant__ CUtensorMap map_res, const __grid_constant__ CUtensorMap map_out, Res96Params p) {
+                 const __grid_constant__ CUtensorMap map_res, const __grid_constant__ CUtensorMap map_out,
+                 const __grid_constant__ CUtensorMap map_wout, Res96Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* t_ring = smem;                                    // [3 blocks][4 slots][hb halo rows + 128 rows][64 B]
   uint8_t* w7s = t_ring + (size_t)R_SUB * p.tsub_bytes;      // [7 taps][3 blocks][48 rows][64 B]
   uint8_t* w1s = w7s + R_W7_BYTES;                           // [3 blocks][48 rows][64 B]
-  uint8_t* stg = w1s + R_W1_BYTES;                           // [8 epilogue-2 warps][2 buffers][32 rows][96 B]
-  float* cst = (float*)(stg + R_STG_BYTES);                  // b1, ea3, ib3
+  uint8_t* wout_s = w1s + R_W1_BYTES;                        // tail mode: [3 blocks][8 rows (hi taps in CTA 0, lo taps in CTA 1)][64 B]
+  uint8_t* stg = wout_s + (kTail ? R_WOUT_BYTES : 0u);      // [8 epilogue-2 warps][stg_bufs buffers][32 rows][96 B]
+  float* cst = (float*)(stg + (size_t)R_E2W * R_STG_TILE * (kTail ? 1u : 2u));   // b1, ea3, ib3
   uint64_t* bars = (uint64_t*)((uint8_t*)cst + R_CST);
   uint64_t* w_full = bars;              // 1
   uint64_t* t_full = bars + 1;          // [4] local: X tile landed
@@ -145,7 +156,9 @@ resunit96_kernel(const __grid_constant__ CUtensorMap map_main, const __grid_cons
   uint64_t* acc2_full = bars + 21;      // [2] both: conv1 has completed
   uint64_t* acc2_free = bars + 23;      // [2] leader: epilogue 2 has drained acc2 in both CTAs
   uint64_t* xbar = bars + 25;           // [8][2] local: an epilogue-2 warp's residual rows have landed (per staging buffer)
-  uint32_t* tmem_ptr = (uint32_t*)(bars + 25 + 2 * R_E2W);
+  uint64_t* a3_ready = xbar + 2 * R_E2W;   // [2] leader: tail mode, epilogue 2 has packed a = snake3(X') into tensor memory (both CTAs)
+  uint64_t* acc3_full = a3_ready + 2;      // [2] both: the outConv partial products of the tile are in tensor memory
+  uint32_t* tmem_ptr = (uint32_t*)(acc3_full + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -161,12 +174,14 @@ resunit96_kernel(const __grid_constant__ CUtensorMap map_main, const __grid_cons
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w1) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_res) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_out) : "memory");
+    if (kTail) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wout) : "memory");
   }
   if (warp == 1 && lane == 0) {
     mbar_init(w_full, 1);
     for (int i = 0; i < R_SLOTS; ++i) { mbar_init(&t_full[i], 1); mbar_init(&a_ready[i], 2 * R_PW); mbar_init(&c7_done[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc1_full[i], 1); mbar_init(&c_ready[i], 2 * R_E1W); mbar_init(&acc2_full[i], 1); mbar_init(&acc2_free[i], 2 * R_E2W); }
     for (int i = 0; i < 2 * R_E2W; ++i) mbar_init(&xbar[i], 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&a3_ready[i], 2 * R_E2W); mbar_init(&acc3_full[i], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -189,10 +204,12 @@ resunit96_kernel(const __grid_constant__ CUtensorMap map_main, const __grid_cons
   if (warp == 0) {
     // ================= producer: weights once, then one X tile per step =================
     if (elect_one()) {
-      if (rank == 0) mbar_expect_tx(w_full, 2u * (R_W7_BYTES + R_W1_BYTES));
+      if (rank == 0) mbar_expect_tx(w_full, 2u * (R_W7_BYTES + R_W1_BYTES + (kTail ? R_WOUT_BYTES : 0u)));
       for (int blk = 0; blk < 7 * R_SUB; ++blk)
         tma_load_2d_2sm(w7s + (size_t)blk * R_WBLK, &map_w7, w_full, (blk % R_SUB) * 32, (blk / R_SUB) * R_C + (int)rank * 48);
       for (int c = 0; c < R_SUB; ++c) tma_load_2d_2sm(w1s + (size_t)c * R_WBLK, &map_w1, w_full, c * 32, (int)rank * 48);
+      if (kTail)
+        for (int c = 0; c < R_SUB; ++c) tma_load_2d_2sm(wout_s + (size_t)c * 512, &map_wout, w_full, c * 32, (int)rank * 8);
     }
     __syncwarp();
     Walker w;
@@ -249,7 +266,8 @@ resunit96_kernel(const __grid_constant__ CUtensorMap map_main, const __grid_cons
       const uint64_t dTap = (uint64_t)(p.dil * 4);             // dil rows x 64 B, in 16-byte units
       const uint32_t tsub16 = p.tsub_bytes >> 4;
       mbar_wait(w_full, 0);
-      for (int i = 0; i <= q; ++i) {
+      const uint32_t wo_u32 = smem_u32(wout_s);
+      for (int i = 0; i <= q + (kTail ? 2 : 0); ++i) {
         if (i < q) {
           const int slot = i % ns;
           mbar_wait(&a_ready[slot], (uint32_t)((i / ns) & 1));
@@ -278,10 +296,34 @@ resunit96_kernel(const __grid_constant__ CUtensorMap map_main, const __grid_cons
           __syncwarp();
           R_STAMP(5, i);
         }
-        if (i >= 1) {
+        if (kTail && i >= 3) {
+          // outConv partial products of tile t = i - 3: P[256 x 16] = a[256 x 96] (tensor memory, packed by epilogue 2 over the drained
+          // conv1 accumulator) x [hi taps | lo taps]^T, into the 16 spare columns behind that accumulator.  Issued three tiles late --
+          // epilogue 2 of tile t finished long ago, so this wait never stalls the issuer -- and right BEFORE conv1 of tile t + 2, which
+          // overwrites the slot: the tensor pipe executes in order, so conv1 needs no "slot drained" hand-shake in tail mode.
+          const int t = i - 3;
+          mbar_wait(&a3_ready[t & 1], (uint32_t)((t >> 1) & 1));
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t slot_t = tmem_base + 256u + (uint32_t)((t & 1) * 128);
+            const uint64_t wd = desc_fixed | (uint64_t)(wo_u32 >> 4);
+#pragma unroll
+            for (int c = 0; c < R_SUB; ++c) {
+#pragma unroll
+              for (int k = 0; k < 2; ++k) {
+                const int j16 = 2 * c + k;
+                const uint32_t a_col = (uint32_t)(j16 < 3 ? 8 * j16 : 48 + 8 * (j16 - 3));
+                tc_mma_f16_2sm_ts(slot_t + 96u, slot_t + a_col, wd + (uint64_t)(c * (512 >> 4) + 2 * k), p.idesc3, (uint32_t)(c | k));
+              }
+            }
+            tc_commit_2sm(&acc3_full[t & 1], mc_mask);
+          }
+          __syncwarp();
+        }
+        if (i >= 1 && i <= q) {
           const int t = i - 1;
           mbar_wait(&c_ready[t & 1], (uint32_t)((t >> 1) & 1));
-          if (t >= 2) mbar_wait(&acc2_free[t & 1], (uint32_t)(((t - 2) >> 1) & 1));
+          if (t >= 2 && !kTail) mbar_wait(&acc2_free[t & 1], (uint32_t)(((t - 2) >> 1) & 1));
           tc_fence_after();
           R_STAMP(6, t);
           if (elect_one()) {
@@ -440,8 +482,28 @@ resunit96_kernel(const __grid_constant__ CUtensorMap map_main, const __grid_cons
     const int e2w = warp - R_CTRL - R_PW - R_E1W;
     const int quarter = warp & 3, col_base = (e2w >> 2) * 48;
     const uint32_t cst_u32 = smem_u32(cst);
-    uint8_t* my_stg = stg + (size_t)e2w * R_STG_WARP;
+    uint8_t* my_stg = stg + (size_t)e2w * R_STG_TILE * (kTail ? 1u : 2u);
     uint64_t* my_xbar = xbar + 2 * e2w;
+    // Tail mode (the decoder's last unit): the output a = snake3(X') stays on chip.  It is packed back into tensor memory over the
+    // conv1 accumulator columns just read (as epilogue 1 does for conv1's operand); the issuer multiplies it with outConv's taps three
+    // tiles later, and the 16 partial products per row -- 64 B instead of the 192 B of activations -- are stored from here, two
+    // tiles late, straight from registers (a warp's 32 rows are 2 KB contiguous in P).
+    long long h_off[2] = {-1, -1};                                  // where this lane's row of tiles u - 1, u - 2 goes in P (< 0: nowhere)
+    auto store_partials = [&](int t, long long off) {               // P of tile t (its MMA was issued at issuer step t + 3)
+      if (col_base != 0) return;                                    // the two warps of a lane quarter share the rows: one of them stores
+      mbar_wait_backoff(&acc3_full[t & 1], (uint32_t)((t >> 1) & 1), p.sleep_ns);
+      tc_fence_after();
+      uint32_t r[1][16];
+      tc_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(256 + (t & 1) * 128 + 96), r[0]);
+      tc_wait_ld();
+      tc_fence_before();
+      if (off >= 0) {
+        float4* dst = (float4*)(p.p_out + off);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          dst[c] = make_float4(__uint_as_float(r[0][4 * c]), __uint_as_float(r[0][4 * c + 1]), __uint_as_float(r[0][4 * c + 2]), __uint_as_float(r[0][4 * c + 3]));
+      }
+    };
     Walker w;
     w.init(p, g0);
     if (q > 0 && w.live(p) && lane == 0) {
@@ -453,13 +515,15 @@ resunit96_kernel(const __grid_constant__ CUtensorMap map_main, const __grid_cons
       const int row0 = w.t0 + quarter * 32, wb = w.b, bf = u & 1;
       w.next(p);                                                    // now describes tile u + 1
       const bool next_ok = u + 1 < q && w.live(p);
-      const uint32_t my_row = smem_u32(my_stg) + (uint32_t)(R_STG_TILE * bf) + (uint32_t)lane * 96u;
+      const int sb_ = !kTail ? bf : 0;                      // staging buffer of this tile
+      const uint32_t my_row = smem_u32(my_stg) + (uint32_t)(R_STG_TILE * sb_) + (uint32_t)lane * 96u;
       if (p.bridge) named_bar_sync(R_BAR_E2 + (u & 1), R_BAR_E2_COUNT);
       else mbar_wait_backoff(&acc2_full[u & 1], (uint32_t)((u >> 1) & 1), p.sleep_ns);
       tc_fence_after();
       if (warp == R_CTRL + R_PW + R_E1W) R_STAMP(10, u);
+      if (kTail && u >= 2) store_partials(u - 2, h_off[1]);
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(256 + (u & 1) * 128 + col_base);
-      if (row_ok) mbar_wait_backoff(&my_xbar[bf], (uint32_t)((u >> 1) & 1), p.sleep_ns);
+      if (row_ok) mbar_wait_backoff(&my_xbar[sb_], !kTail ? (uint32_t)((u >> 1) & 1) : (uint32_t)(u & 1), p.sleep_ns);
 #pragma unroll
       for (int m = 0; m < 3; ++m) {
         uint32_t r[1][16];
@@ -467,7 +531,7 @@ resunit96_kernel(const __grid_constant__ CUtensorMap map_main, const __grid_cons
         tc_ld16(taddr + 16u * (uint32_t)m, r[0]);
         if (row_ok) { rr[2 * m] = lds128(my_row + 32u * (uint32_t)m); rr[2 * m + 1] = lds128(my_row + 32u * (uint32_t)m + 16u); }
         tc_wait_ld();
-        if (m == 2) {   // the accumulator has been read completely
+        if (m == 2 && !kTail) {   // the accumulator has been read completely (tail mode: the issuer orders the slot's reuse itself)
           tc_fence_before();
           __syncwarp();
           if (lane == 0) arrive_leader(&acc2_free[u & 1], rank);
@@ -509,11 +573,29 @@ resunit96_kernel(const __grid_constant__ CUtensorMap map_main, const __grid_cons
                                                              __uint_as_float(r[0][8 * h + 2 * e + 1]) + bb[2 * e + 1]), rw[e]);
             }
           }
-          sts128(my_row + 32u * (uint32_t)m, make_uint4(o[0], o[1], o[2], o[3]));
-          sts128(my_row + 32u * (uint32_t)m + 16u, make_uint4(o[4], o[5], o[6], o[7]));
+          if (kTail) {
+            // packed a, over accumulator columns that are already in registers: channels col_base + 16 m .. + 15 -> columns col_base + 8 m .. + 7
+            tc_st8(taddr + 8u * (uint32_t)m, o);
+          } else {
+            sts128(my_row + 32u * (uint32_t)m, make_uint4(o[0], o[1], o[2], o[3]));
+            sts128(my_row + 32u * (uint32_t)m + 16u, make_uint4(o[4], o[5], o[6], o[7]));
+          }
         }
       }
-      if (row_ok) {
+      if (kTail) {
+        tc_wait_st();
+        tc_fence_before();
+        __syncwarp();                                              // every lane has read its residual row and written its operand row
+        if (lane == 0) {
+          arrive_leader(&a3_ready[u & 1], rank);
+          if (next_ok) {                                           // nothing is stored from the staging buffer: one buffer, refilled at once
+            mbar_expect_tx(&my_xbar[0], R_STG_TILE);
+            tma_load_3d(my_stg, &map_res, &my_xbar[0], col_base, w.t0 + quarter * 32, w.b);
+          }
+        }
+        h_off[1] = h_off[0];
+        h_off[0] = (row_ok && row0 + lane < p.slot_rows) ? (long long)wb * p.p_bstride + (long long)(row0 + lane) * 16 : -1;
+      } else if (row_ok) {
         fence_async_smem();
         __syncwarp();
         if (lane == 0) {
@@ -527,6 +609,10 @@ resunit96_kernel(const __grid_constant__ CUtensorMap map_main, const __grid_cons
         }
       }
       if (warp == R_CTRL + R_PW + R_E1W) R_STAMP(11, u);
+    }
+    if (kTail) {
+      if (q >= 2) store_partials(q - 2, h_off[1]);
+      if (q >= 1) store_partials(q - 1, h_off[0]);
     }
     if (lane == 0) tma_store_wait_all();
   }
@@ -571,7 +657,12 @@ cudaError_t launch_resunit96(const ResUnitParams& p, const BatchGeom& g, int op_
   Res96Params q{};
   q.B = g.B; q.Tmax = g.Tmax; q.rows_per_frame = p.rows_per_frame; q.len_frames = g.len_frames;
   q.dil = p.dil; q.halo = 6 * p.dil; q.hb = (q.halo + 7) & ~7;
-  const size_t fixed = R_W7_BYTES + R_W1_BYTES + R_STG_BYTES + R_CST + 512 + 1024;
+  const bool tail = p.p_out != nullptr;
+  if (tail && (!p.wout || !p.ea3)) return cudaErrorInvalidValue;
+  q.tail = tail ? 1 : 0;
+  q.stg_bufs = tail ? 1 : 2;
+  q.p_out = p.p_out; q.slot_rows = slot_rows; q.p_bstride = (long long)slot_rows * 16;
+  const size_t fixed = R_W7_BYTES + R_W1_BYTES + (tail ? R_WOUT_BYTES : 0) + (size_t)R_E2W * R_STG_TILE * q.stg_bufs + R_CST + 512 + 1024;
   auto tsub = [&](int n) { return ((uint32_t)(n * (q.hb + R_BM)) * 64u + 511u) & ~511u; };   // SWIZZLE_64B repeats every 512 B
   // Three ring slots: a slot is busy from the TMA issue to the end of conv7 of its tile (load ~1.5 k + pass 1 ~2.7 k + conv7 ~2 k cycles),
   // about two tile periods.  The fourth slot's 26-35 KB now hold the second epilogue-2 staging buffer.
@@ -581,6 +672,7 @@ cudaError_t launch_resunit96(const ResUnitParams& p, const BatchGeom& g, int op_
   q.out = p.out;
   const uint32_t fmt = op_dtype == DT_F16 ? 0u : 1u;
   q.idesc7 = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(R_C >> 3) << 17) | ((uint32_t)((2 * R_BM) >> 4) << 24);
+  q.idesc3 = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)((2 * R_BM) >> 4) << 24);
   q.b7 = p.b7; q.ea1 = p.ea1; q.ib1 = p.ib1; q.ea2 = p.ea2; q.ib2 = p.ib2; q.b1 = p.b1; q.ea3 = p.ea3; q.ib3 = p.ib3;
   q.out_snake = p.ea3 != nullptr;
   q.x_in = p.x_in; q.x_bstride = (long long)slot_rows * R_C;
@@ -596,7 +688,7 @@ cudaError_t launch_resunit96(const ResUnitParams& p, const BatchGeom& g, int op_
   int grid = (int)std::min<long long>(sms / 2 * 2, (tiles_bound + 1) / 2 * 2);
   grid = std::max(grid, 2);
   q.tiles_per_cta = (int)((tiles_bound + grid - 1) / grid);
-  CUtensorMap map_main, map_halo, map_w7, map_w1, map_res, map_out;
+  CUtensorMap map_main, map_halo, map_w7, map_w1, map_res, map_out, map_wout;
   auto act_map = [&](CUtensorMap* m, const void* base, cuuint32_t cols, cuuint32_t rows) -> bool {
     cuuint64_t dims[3] = {(cuuint64_t)R_C, (cuuint64_t)slot_rows, (cuuint64_t)g.B};
     cuuint64_t strides[2] = {(cuuint64_t)R_C * 2, (cuuint64_t)slot_rows * R_C * 2};
@@ -606,17 +698,18 @@ cudaError_t launch_resunit96(const ResUnitParams& p, const BatchGeom& g, int op_
                cols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : (cols == 16 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE),
                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
   };
-  auto w_map = [&](CUtensorMap* m, const void* base, int rows) -> bool {
+  auto w_map = [&](CUtensorMap* m, const void* base, int rows, cuuint32_t box_rows) -> bool {
     cuuint64_t dims[2] = {(cuuint64_t)R_C, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)R_C * 2};
-    cuuint32_t box[2] = {32, 48};
+    cuuint32_t box[2] = {32, box_rows};
     cuuint32_t es[2] = {1, 1};
     return enc(m, dt, 2, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
   };
   if (!act_map(&map_main, p.x_in, 32, R_BM) || !act_map(&map_halo, p.x_in, 32, (cuuint32_t)q.hb) ||
-      !w_map(&map_w7, p.w7, 7 * R_C) || !w_map(&map_w1, p.w1, R_C) ||
-      !act_map(&map_res, p.x_in, 48, 32) || !act_map(&map_out, p.out, 48, 32))
+      !w_map(&map_w7, p.w7, 7 * R_C, 48) || !w_map(&map_w1, p.w1, R_C, 48) ||
+      !act_map(&map_res, p.x_in, 48, 32) || !act_map(&map_out, tail ? p.x_in : p.out, 48, 32) ||   // tail mode stores no activations: any valid map
+      !w_map(&map_wout, tail ? p.wout : p.w1, 16, 8))
     return cudaErrorInvalidValue;
   const size_t smem = (size_t)R_SUB * q.tsub_bytes + fixed;
   cudaLaunchConfig_t cfg{};
@@ -629,21 +722,23 @@ cudaError_t launch_resunit96(const ResUnitParams& p, const BatchGeom& g, int op_
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
+                            const CUtensorMap, Res96Params);
+  static const KernelFn kFns[2][2][2] = {   // [bf16][debug stamps][tail mode]
+      {{resunit96_kernel<__half, false, false>, resunit96_kernel<__half, false, true>},
+       {resunit96_kernel<__half, true, false>, resunit96_kernel<__half, true, true>}},
+      {{resunit96_kernel<__nv_bfloat16, false, false>, resunit96_kernel<__nv_bfloat16, false, true>},
+       {resunit96_kernel<__nv_bfloat16, true, false>, resunit96_kernel<__nv_bfloat16, true, true>}}};
   static tc::PerDeviceOnce optin;
   const cudaError_t oe = optin.ensure([]() {
-    cudaError_t e = cudaFuncSetAttribute(resunit96_kernel<__half, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(resunit96_kernel<__nv_bfloat16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(resunit96_kernel<__half, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(resunit96_kernel<__nv_bfloat16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i < 8 && e == cudaSuccess; ++i)
+      e = cudaFuncSetAttribute((const void*)kFns[i >> 2][(i >> 1) & 1][i & 1], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     return e;
   });
   if (oe != cudaSuccess) return oe;
-  if (q.dbg) {
-    if (op_dtype == DT_F16) return cudaLaunchKernelEx(&cfg, resunit96_kernel<__half, true>, map_main, map_halo, map_w7, map_w1, map_res, map_out, q);
-    return cudaLaunchKernelEx(&cfg, resunit96_kernel<__nv_bfloat16, true>, map_main, map_halo, map_w7, map_w1, map_res, map_out, q);
-  }
-  if (op_dtype == DT_F16) return cudaLaunchKernelEx(&cfg, resunit96_kernel<__half, false>, map_main, map_halo, map_w7, map_w1, map_res, map_out, q);
-  return cudaLaunchKernelEx(&cfg, resunit96_kernel<__nv_bfloat16, false>, map_main, map_halo, map_w7, map_w1, map_res, map_out, q);
+  return cudaLaunchKernelEx(&cfg, kFns[op_dtype == DT_F16 ? 0 : 1][q.dbg ? 1 : 0][tail ? 1 : 0], map_main, map_halo, map_w7, map_w1, map_res, map_out,
+                            map_wout, q);
 }
 
 }  // namespace q3
