@@ -1,0 +1,82 @@
+"""The kernel-selection switches (environment variables read once per process) pick alternative CUDA kernels for the same
+stage: the default 16-bit path folds outConv into block 3's last fused residual unit; with the switches off the decoder
+runs the stand-alone tensor-core tail, the unfused conv7/conv1 GEMMs or the SIMT tail.  Every variant must meet the same
+parity bar against the oracle, and they must agree with each other far inside it.  One subprocess per variant."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import decoder as od
+from tools.synth_checkpoint import synth_codes
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+CHILD = r"""
+import sys, numpy as np
+sys.path.insert(0, sys.argv[4]); sys.path.insert(0, sys.argv[4] + "/swift-qwen3-tts_b200/python")
+import qwen3tts_cuda as q
+codes = np.load(sys.argv[2])
+tok = q.Qwen3TTSSpeechTokenizer(sys.argv[1], precision=q.PREC_FP16)
+out = tok.decoder(codes)
+tok2 = q.Qwen3TTSSpeechTokenizer(sys.argv[1], precision=q.PREC_FP16, attn_mode=q.ATTN_CAUSAL_SW)
+one = tok2.decoder(codes[:1])[0, 0]
+st = tok2.open_stream()
+bt = np.ascontiguousarray(codes[0].T)
+parts = [st.push(bt[a:b]) for a, b in ((0, 7), (7, 8), (8, 20))]
+st.close()
+np.savez(sys.argv[3], out=out, one=one, chunked=np.concatenate(parts))
+"""
+
+VARIANTS = {
+    "default": {},
+    "standalone_tail": {"Q3TTS_FUSED_TAIL": "0"},
+    "unfused_units": {"Q3TTS_FUSED_RES": "0"},
+    "simt_tail": {"Q3TTS_FUSED_RES": "0", "Q3TTS_NO_MMA_TAIL": "1"},
+}
+
+
+@pytest.fixture(scope="module")
+def variant_outputs(full_dir, full_cfg, tmp_path_factory):
+    tmp = tmp_path_factory.mktemp("variants")
+    codes = synth_codes(full_cfg, 2, 20, 4242)
+    np.save(tmp / "codes.npy", codes)
+    outs = {}
+    for name, env in VARIANTS.items():
+        e = dict(os.environ)
+        for k in ("Q3TTS_FUSED_TAIL", "Q3TTS_FUSED_RES", "Q3TTS_NO_MMA_TAIL"):
+            e.pop(k, None)
+        e.update(env)
+        r = subprocess.run([sys.executable, "-c", CHILD, full_dir, str(tmp / "codes.npy"), str(tmp / f"{name}.npz"), ROOT],
+                           env=e, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, (name, r.stderr[-2000:])
+        outs[name] = dict(np.load(tmp / f"{name}.npz"))
+    return codes, outs
+
+
+def test_every_kernel_variant_meets_the_parity_bar(variant_outputs, full_oracle):
+    codes, outs = variant_outputs
+    ref = full_oracle[2].forward(codes).numpy()
+    for name, o in outs.items():
+        snr = od.snr_db(ref, o["out"])
+        print(f"{name}: SNR {snr:.1f} dB")
+        assert snr >= 40.0, (name, snr)
+
+
+def test_kernel_variants_agree_with_each_other(variant_outputs):
+    _, outs = variant_outputs
+    base = outs["default"]["out"]
+    for name, o in outs.items():
+        assert od.snr_db(base, o["out"]) >= 46.0, name      # same 16-bit operands, different summation order / fusion points
+
+
+def test_chunked_streaming_is_chunk_invariant_in_every_variant(variant_outputs):
+    # the stream state between chunks holds different things per variant (activations, or outConv partial products)
+    _, outs = variant_outputs
+    for name, o in outs.items():
+        assert o["chunked"].shape == o["one"].shape, name
+        # two 16-bit runs with different tile boundaries carry independent rounding noise: same bar as test_gpu_streaming
+        assert od.snr_db(o["one"], o["chunked"]) >= 40.0, (name, od.snr_db(o["one"], o["chunked"]))
