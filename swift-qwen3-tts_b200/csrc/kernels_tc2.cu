@@ -186,6 +186,10 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   // item -> (n tile, this CTA's M tile).  Returns "some CTA of the cluster has rows to produce"; the result and `mine`
   // go through a vote so that the callers' control flow is warp-uniform by construction.  Divisions are multiplications
   // by host-computed magic numbers: every warp of the CTA walks the item list, so this runs 16 times per tile.
+  // The rows of utterances vb0 and vb0 + 1 stay in registers: a cluster's consecutive items sit in the same one or two utterances for
+  // hundreds of items, and a dependent global load per item and warp was a third of the producer warp's time -- whose instruction
+  // stream, not the memory system, set the pace of the transposed convs (profiles/r2_gemm_experiments.md section 3).
+  int vb0 = -2, vrows0 = 0, vrows1 = 0, last_nt = 0;
   auto coords = [&](int item, int& b, int& t0, int& n0, bool& mine) -> bool {
     int g = item, nt = 0;
     if (p.n_tiles > 1) {
@@ -193,9 +197,15 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
       nt = item - g * p.n_tiles;
     }
     n0 = nt * p.BN;
+    last_nt = nt;
     const int mg0 = g * cs;
     const int b0 = p.tiles_per_utt == 1 ? mg0 : (int)(__umulhi((uint32_t)mg0, p.div_tpu_m) >> p.div_tpu_s);
     const int i0 = mg0 - b0 * p.tiles_per_utt;                    // M tile index inside its utterance
+    if (b0 != vb0) {
+      vb0 = b0;
+      vrows0 = b0 < p.B ? __ldg(p.len_frames + b0) * p.rows_per_frame : 0;
+      vrows1 = b0 + 1 < p.B ? __ldg(p.len_frames + b0 + 1) * p.rows_per_frame : 0;
+    }
     bool any = false;
     mine = false;
     b = p.B; t0 = 0;                 // out-of-range utterance: TMA zero-fills, epilogue stores nothing
@@ -203,7 +213,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
       if (mg0 + r >= p.m_tiles_total) continue;
       const bool wrap = i0 + r >= p.tiles_per_utt;                // cs <= 2: the pair's second tile may open the next utterance
       const int bb = wrap ? b0 + 1 : b0, tt = (wrap ? 0 : i0 + r) * T2_BM;
-      const bool ok = tt < __ldg(p.len_frames + bb) * p.rows_per_frame;
+      const bool ok = tt < (wrap ? vrows1 : vrows0);
       any |= ok;
       if (r == (int)rank) { b = bb; t0 = tt; mine = ok; }
     }
@@ -217,6 +227,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     // turns the epilogue's residual reads from HBM-latency loads into L2 hits.
     int sa = 0, sw = 0;
     uint32_t pa = 0, pw = 0, w_loaded = 0;      // w_loaded: bit s = resident W stage s has been requested
+    const uint32_t w_all = p.w_resident ? (uint32_t)((1ull << T2_NW) - 1) : 0xffffffffu;   // non-resident: w_loaded stays 0, never equal
     const int wrows = p.BN / cs;
     const int res_es = y_is_f32 ? 4 : 2;
     const int stages_per_tile = p.ncb * p.ngroups;
@@ -244,7 +255,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         }
         __syncwarp();
       }
-      if (p.w_resident) sw = (item % p.n_tiles) * stages_per_tile;
+      if (p.w_resident) sw = last_nt * stages_per_tile;
       for (int cb = 0; cb < p.ncb; ++cb) {
         mbar_wait(&a_empty[sa], pa ^ 1);
         if (elect_one()) {
@@ -257,6 +268,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
           }
         }
         if (++sa == T2_NA) { sa = 0; pa ^= 1; }
+        if (w_loaded == w_all) continue;            // resident weights: every stage has been requested
         for (int tap0 = 0; tap0 < p.taps; tap0 += p.wg) {
           const int ntap = min(p.wg, p.taps - tap0);
           bool load = true;
@@ -353,7 +365,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         mbar_wait(&tmem_empty[acc], pacc ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_stride);
-        if (w_resident) sw = (item % p.n_tiles) * stages_per_tile;
+        if (w_resident) sw = last_nt * stages_per_tile;
         for (int cb = 0; cb < ncb; ++cb) {
           mbar_wait(&a_full[sa], pa);
           const uint64_t ad_cb = desc_fixed | (uint64_t)((a_ring_u32 + (uint32_t)sa * p.a_stage_bytes) >> 4);
