@@ -691,6 +691,8 @@ void run_microbatch(Model& m, const int32_t* d_codes, const int64_t* d_code_base
   }
   Plan P = make_plan(m, m.arena, B, Tmax);
   Ctx x{m, BatchGeom{B, Tmax, d_len, (long long)valid_frames, nullptr, m.pcm_i16 ? 1 : 0}, s, valid_frames};
+  // per-launch / per-stage event timing brackets serialised kernels: no programmatic overlap between them while profiling
+  struct PdlGuard { bool on; explicit PdlGuard(bool o) : on(o) { if (on) pdl_suspend(true); } ~PdlGuard() { if (on) pdl_suspend(false); } } pdl_guard(m.profile_enabled);
   const int op = m.op_dtype;
   const int64_t R = (int64_t)B * Tmax;
   const int half = c.codebook_dim / 2;

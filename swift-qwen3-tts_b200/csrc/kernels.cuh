@@ -111,6 +111,17 @@ void launch_tail(const void* a, int a_dtype, int64_t a_bstride, const float* w /
                  int rows_per_frame, cudaStream_t s);
 
 // Same op on the warp-level tensor path for 16-bit operands (kernels_attn.cu): [rows x C] . [C x 8] with HMMA, then the 7-tap diagonal sum.
+// Programmatic dependent launch (one decode = ~95 launches in one stream).  Every kernel of the chain calls pdl_trigger() early, which
+// lets the NEXT kernel of the stream -- if it was launched with the programmatic-serialization attribute (pdl_enabled()) -- get its
+// CTAs resident and run its prologue (barrier init, tensor-memory allocation, tensor-map prefetch, constants) under this kernel's
+// tail; such a kernel calls pdl_wait() before it first touches memory an earlier kernel wrote (pdl_wait returns when the preceding
+// grid has completed and its writes are visible; without the attribute both are no-ops).  Q3TTS_PDL=0 switches the attribute off.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
+bool pdl_enabled();
+void pdl_suspend(bool on);   // this thread's launches: plain stream order while suspended (per-launch event timing measures serialised kernels)
 bool tail_mma_supported(int dtype, int C);
 // outConv split in two: the last residual unit (tail mode) multiplies its on-chip output with the [16][C] hi/lo tap tile and stores
 // 16 partial products per row; this kernel adds the seven that belong to each sample, then bias + clip (ST.swift:687-688, 781)

@@ -49,6 +49,7 @@ attention_mma_kernel(const T16* __restrict__ qkv, T16* __restrict__ out, BatchGe
   __shared__ __align__(16) T16 Qs[AQ * APAD];
   __shared__ __align__(16) T16 Ks[AK * APAD];
   __shared__ __align__(16) T16 Vs[AK * APAD];
+  pdl_trigger();
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * AQ;
   const int len = g.len_frames[b], beg = g.row_begin ? g.row_begin[b] : 0;
   if (q0 >= len) return;
@@ -254,6 +255,7 @@ __global__ void __launch_bounds__(TP_ROWS)
 tail_from_partials_kernel(const float* __restrict__ P, int64_t p_bstride, float bias, float* __restrict__ pcm, const int64_t* __restrict__ pcm_base,
                           float* __restrict__ tap, int64_t tap_bstride, BatchGeom g, int rows_per_frame, int tiles_per_utt) {
   __shared__ float sp[TP_IN * TP_LD];
+  pdl_trigger();
   const int b = blockIdx.x / tiles_per_utt, tid = threadIdx.x;
   const int64_t t0 = (int64_t)(blockIdx.x % tiles_per_utt) * TP_ROWS;
   const int64_t valid = (int64_t)g.len_frames[b] * rows_per_frame;

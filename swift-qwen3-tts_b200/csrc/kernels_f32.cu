@@ -12,6 +12,14 @@
 
 namespace q3 {
 
+static thread_local int g_pdl_suspended = 0;
+void pdl_suspend(bool on) { g_pdl_suspended += on ? 1 : -1; }
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("Q3TTS_PDL"); return !(e && e[0] == '0'); }();
+  return on && g_pdl_suspended == 0;
+}
+
+
 // ---- typed element access ---------------------------------------------------------------------
 __device__ __forceinline__ float ldf(const float* p, int64_t i) { return p[i]; }
 __device__ __forceinline__ float ldf(const __half* p, int64_t i) { return __half2float(p[i]); }
@@ -189,6 +197,7 @@ void launch_conv_gemm_simt(const ConvGemmParams& p, const BatchGeom& g, int op_d
 // ================================================================================================
 template <typename TO>
 __global__ void __launch_bounds__(256) rvq_kernel(RvqParams p, BatchGeom g) {
+  pdl_trigger();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int rows = g.B * g.Tmax;
   if (warp >= rows) return;
@@ -227,6 +236,7 @@ void launch_rvq(const RvqParams& p, const BatchGeom& g, cudaStream_t s) {
 // ================================================================================================
 template <typename TO>
 __global__ void __launch_bounds__(256) rmsnorm_kernel(const float* x, const float* w, float eps, TO* out, int64_t rows, int C) {
+  pdl_trigger();
   const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -265,6 +275,7 @@ __global__ void __launch_bounds__(256)
 dwconv_ln_warp_kernel(const float* __restrict__ x, const float* __restrict__ w7, const float* __restrict__ wb,
                       const float* __restrict__ ln_w, const float* __restrict__ ln_b, float eps, TO* __restrict__ out, BatchGeom g,
                       int rows_per_frame) {
+  pdl_trigger();
   constexpr int C = KC * 128;
   const int slot_rows = g.Tmax * rows_per_frame;
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -667,6 +678,7 @@ void launch_codec_embed_sum(const CodecEmbedParams& p, cudaStream_t s) {
 // Batched block copy: one CTA per item, 16-byte chunks (the streaming API's state shuffles).
 // ================================================================================================
 __global__ void __launch_bounds__(256) block_copy_kernel(const CopyItem* items) {
+  pdl_trigger();
   const CopyItem it = items[blockIdx.x];
   const long long n = it.bytes >> 4;
   uint4* d = (uint4*)it.dst;

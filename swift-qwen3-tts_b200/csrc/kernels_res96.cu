@@ -199,6 +199,8 @@ resunit96_kernel(const __grid_constant__ CUtensorMap map_main, const __grid_cons
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_trigger();   // programmatic dependent launch (kernels.cuh): the prologue above touched no activations
+  if (warp != 0) pdl_wait();   // (the producer requests the weights first)
   const long long g0 = (long long)blockIdx.x * q;
 
   if (warp == 0) {
@@ -212,6 +214,7 @@ resunit96_kernel(const __grid_constant__ CUtensorMap map_main, const __grid_cons
         for (int c = 0; c < R_SUB; ++c) tma_load_2d_2sm(wout_s + (size_t)c * 512, &map_wout, w_full, c * 32, (int)rank * 8);
     }
     __syncwarp();
+    pdl_wait();
     Walker w;
     w.init(p, g0);
     auto issue_tile = [&](int j) {          // TMA of tile j into slot j % ns (the walker stands at tile j)
@@ -717,11 +720,13 @@ cudaError_t launch_resunit96(const ResUnitParams& p, const BatchGeom& g, int op_
   cfg.blockDim = dim3(R_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
                             const CUtensorMap, Res96Params);
   static const KernelFn kFns[2][2][2] = {   // [bf16][debug stamps][tail mode]

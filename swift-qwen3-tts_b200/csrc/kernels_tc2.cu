@@ -182,6 +182,10 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   if (cs > 1) cluster_sync_all();   // every CTA's barriers are initialised before any remote arrive / multicast lands
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  // Everything above touched only shared / tensor memory and weights.  The next kernel of the stream may start its own prologue now;
+  // this one must not read activations before the previous kernel has completed (kernels.cuh, programmatic dependent launch).
+  pdl_trigger();
+  pdl_wait();
 
   // item -> (n tile, this CTA's M tile).  Returns "some CTA of the cluster has rows to produce"; the result and `mine`
   // go through a vote so that the callers' control flow is warp-uniform by construction.  Divisions are multiplications
@@ -1026,11 +1030,13 @@ static cudaError_t launch_tc2_impl(const ConvGemmParams& p, const BatchGeom& g, 
   cfg.blockDim = dim3(epi_block ? T2_THREADS_BLOCK : T2_THREADS_GENERIC);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = (unsigned)cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   if (op_dtype == DT_F16) return launch_variant<__half>(cfg, pair, epi_block, map_a, map_w, map_y, map_o, map_w2, q, yf);
   return launch_variant<__nv_bfloat16>(cfg, pair, epi_block, map_a, map_w, map_y, map_o, map_w2, q, yf);
 }

@@ -36,6 +36,7 @@ VARIANTS = {
     "standalone_tail": {"Q3TTS_FUSED_TAIL": "0"},
     "unfused_units": {"Q3TTS_FUSED_RES": "0"},
     "simt_tail": {"Q3TTS_FUSED_RES": "0", "Q3TTS_NO_MMA_TAIL": "1"},
+    "no_pdl": {"Q3TTS_PDL": "0"},          # plain stream order instead of programmatic dependent launch: same kernels, same bits
 }
 
 
@@ -47,7 +48,7 @@ def variant_outputs(full_dir, full_cfg, tmp_path_factory):
     outs = {}
     for name, env in VARIANTS.items():
         e = dict(os.environ)
-        for k in ("Q3TTS_FUSED_TAIL", "Q3TTS_FUSED_RES", "Q3TTS_NO_MMA_TAIL"):
+        for k in ("Q3TTS_FUSED_TAIL", "Q3TTS_FUSED_RES", "Q3TTS_NO_MMA_TAIL", "Q3TTS_PDL"):
             e.pop(k, None)
         e.update(env)
         r = subprocess.run([sys.executable, "-c", CHILD, full_dir, str(tmp / "codes.npy"), str(tmp / f"{name}.npz"), ROOT],
@@ -80,3 +81,10 @@ def test_chunked_streaming_is_chunk_invariant_in_every_variant(variant_outputs):
         assert o["chunked"].shape == o["one"].shape, name
         # two 16-bit runs with different tile boundaries carry independent rounding noise: same bar as test_gpu_streaming
         assert od.snr_db(o["one"], o["chunked"]) >= 40.0, (name, od.snr_db(o["one"], o["chunked"]))
+
+
+def test_programmatic_dependent_launch_changes_no_bit(variant_outputs):
+    # the overlap of a kernel's prologue with its predecessor's tail must never let it read stale activations
+    _, outs = variant_outputs
+    for key in ("out", "one", "chunked"):
+        assert np.array_equal(outs["default"][key], outs["no_pdl"][key]), key
