@@ -1,0 +1,130 @@
+"""CPU tests of the encoder oracle: the restatement against definition-level arithmetic, the reference's
+padding rule, its key remap, and the properties the architecture guarantees (frame count, causality).  The reference has no
+test or golden vector for ``encode``; parity at the MLX boundary is unpinned (oracle/encoder.py header)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import encoder as oe
+from tools.fixtures import checkpoint_dir
+from tools.q3cfg import DecoderConfig, EncoderConfig
+from tools.synth_checkpoint import encoder_tensor_specs, make_encoder_state, synth_audio
+
+
+@pytest.fixture(scope="module")
+def tiny_enc():
+    ec = EncoderConfig.tiny()
+    d = os.path.join(checkpoint_dir(DecoderConfig.tiny(), seed=7, encoder_cfg=ec), "speech_tokenizer")
+    cfg, w = oe.load_encoder(d)
+    return cfg, w, oe.OracleEncoder(cfg, w, torch.float64)
+
+
+def test_extra_padding_rule_known_answers():
+    # STE.swift:115-119 by hand: frames = ceil((L + pad - k) / s + 1); ideal = (frames - 1) s + k - pad
+    assert oe.extra_padding(10, 4, 2, 2) == 0          # 10 -> 5 frames exactly
+    assert oe.extra_padding(11, 4, 2, 2) == 1          # 11 -> 6 frames, one zero on the right
+    assert oe.extra_padding(1, 16, 8, 8) == 7          # a single sample still yields one frame
+    assert oe.extra_padding(7, 3, 1, 2) == 0           # stride 1 never pads on the right
+    assert oe.extra_padding(1441, 12, 6, 6) == 5
+
+
+@pytest.mark.parametrize("samples", [1, 47, 48, 49, 1000, 1921])
+def test_frame_count_is_the_ceil_chain(tiny_enc, samples):
+    cfg, _, enc = tiny_enc
+    codes = enc.encode(synth_audio(1, samples, 3))
+    assert codes.shape == (1, 16, oe.encode_frames(cfg, samples))
+    assert int(codes.min()) >= 0 and int(codes.max()) < cfg.codebook_size
+
+
+def test_full_config_frame_rate_is_12_5_hz():
+    cfg = EncoderConfig()
+    assert cfg.seanet_stride == 960 and cfg.downsample_stride == 2
+    assert oe.encode_frames(cfg, 24000 * 10) == 125 and oe.encode_frames(cfg, 24000 * 10 + 1) == 126
+
+
+def test_streamable_conv_matches_the_definition(tiny_enc):
+    # strided and dilated cases written out tap by tap (cross-correlation, zeros left, extra zeros right)
+    cfg, w, enc = tiny_enc
+    rng = np.random.default_rng(0)
+    for (cin, cout, k, s, d, L) in [(3, 5, 4, 2, 1, 11), (4, 2, 3, 1, 2, 9), (2, 3, 6, 3, 1, 7)]:
+        W = rng.normal(size=(cout, k, cin))
+        b = rng.normal(size=(cout,))
+        x = rng.normal(size=(1, cin, L))
+        enc.w["t.conv.conv.weight"] = torch.from_numpy(W)
+        enc.w["t.conv.conv.bias"] = torch.from_numpy(b)
+        got = enc.sconv(torch.from_numpy(x), "t", k, stride=s, dil=d).numpy()
+        eff = (k - 1) * d + 1
+        left = eff - s
+        nfr = -(-L // s)
+        want = np.zeros((1, cout, nfr))
+        for t in range(nfr):
+            for j in range(k):
+                src = t * s + j * d - left
+                if 0 <= src < L:
+                    want[0, :, t] += W[:, j, :] @ x[0, :, src]
+            want[0, :, t] += b
+        assert got.shape == want.shape and np.abs(got - want).max() < 1e-12
+
+
+def test_sanitize_rules_produce_the_swift_module_tree():
+    cfg = EncoderConfig.tiny()
+    raw = {k: v.numpy() for k, v in make_encoder_state(cfg, 5).items()}
+    w = oe.sanitize_encoder_weights(raw)
+    assert "encoder.encoder.init_conv1d.conv.conv.weight" in w
+    assert w["encoder.encoder.init_conv1d.conv.conv.weight"].shape == (cfg.num_filters, cfg.kernel_size, 1)            # forced [o,k,i]
+    assert w["encoder.encoder.layers.0.residuals.0.block.0.conv.conv.weight"].shape == (2, 3, 4)
+    assert w["encoder.encoder.layers.3.downsample.conv.conv.weight"].shape[1] == 2 * cfg.upsampling_ratios[0]           # ratios reversed
+    assert w["encoder.downsample.conv.conv.conv.weight"].shape == (cfg.hidden_size, 2 * cfg.downsample_stride, cfg.hidden_size)
+    assert w["encoder.quantizer.rvq_first.input_proj.weight"].shape == (cfg.codebook_dim, 1, cfg.hidden_size)
+    assert "encoder.quantizer.rvq_rest.vq.layers.18.codebook.embeddingSum" in w
+    assert "encoder.encoder_transformer.transformer.layers.1.gating.linear2.weight" in w
+    assert "encoder.encoder_transformer.transformer.layers.0.layer_scale_1.scale" in w
+    assert not any("initialized" in k or "semantic_residual" in k or ".mlp." in k for k in w)
+    n_raw = len(encoder_tensor_specs(cfg))
+    assert len(w) == n_raw - cfg.num_quantizers                        # the `initialized` flags are dropped, nothing else
+
+
+def test_encode_is_causal_in_whole_frames(tiny_enc):
+    cfg, _, enc = tiny_enc
+    hop = cfg.seanet_stride * cfg.downsample_stride
+    a = synth_audio(1, hop * 12, 11)
+    b = a.copy()
+    b[..., hop * 7:] = synth_audio(1, hop * 12, 12)[..., hop * 7:]
+    ca, cb = enc.encode(a), enc.encode(b)
+    assert torch.equal(ca[..., :7], cb[..., :7]) and not torch.equal(ca[..., 7:], cb[..., 7:])
+
+
+def test_batch_rows_are_independent(tiny_enc):
+    _, _, enc = tiny_enc
+    a = synth_audio(3, 500, 21)
+    all_codes = enc.encode(a)
+    for b in range(3):
+        assert torch.equal(all_codes[b:b + 1], enc.encode(a[b:b + 1]))
+
+
+def test_fp32_restatement_agrees_with_fp64_except_at_near_ties(tiny_enc):
+    cfg, w, enc64 = tiny_enc
+    enc32 = oe.OracleEncoder(cfg, w, torch.float32)
+    a = synth_audio(2, 2000, 31)
+    margins = []
+    c64 = enc64.encode(a, margins=margins).numpy()
+    c32 = enc32.encode(a).numpy()
+    first_diff = first_mismatch_is_a_near_tie(c64, c32, [m.numpy() for m in margins], tol=1e-4)
+    assert first_diff <= 0.02 * c64.shape[0] * c64.shape[2]
+
+
+def first_mismatch_is_a_near_tie(want, got, margins, tol):
+    """Codes must agree; a frame may leave the reference's path only at a codebook whose two best distances differ by < tol
+    (after that the residuals differ, so the frame's remaining codebooks are not compared).  Returns the number of such frames."""
+    B, Q, T = want.shape
+    bad = 0
+    for b in range(B):
+        for t in range(T):
+            for qi in range(Q):
+                if want[b, qi, t] != got[b, qi, t]:
+                    assert margins[qi][b, t] < tol, (b, t, qi, float(margins[qi][b, t]))
+                    bad += 1
+                    break
+    return bad

@@ -78,6 +78,62 @@ class DecoderConfig:
 
 
 @dataclass
+class EncoderConfig:
+    """Qwen3TTSTokenizerEncoderConfig, Config.swift:419-560 (every field ``decodeIfPresent ?? default``)."""
+    frame_rate: float = 12.5
+    audio_channels: int = 1
+    codebook_dim: int = 256
+    codebook_size: int = 2048
+    compress: int = 2
+    dilation_growth_rate: int = 2
+    head_dim: int = 64
+    hidden_size: int = 512
+    intermediate_size: int = 2048
+    kernel_size: int = 7
+    last_kernel_size: int = 3
+    layer_scale_initial_scale: float = 0.01
+    max_position_embeddings: int = 8000
+    num_attention_heads: int = 8
+    num_filters: int = 64
+    num_hidden_layers: int = 8
+    num_key_value_heads: int = 8
+    num_quantizers: int = 32
+    num_residual_layers: int = 1
+    residual_kernel_size: int = 3
+    rope_theta: float = 10000.0
+    sampling_rate: int = 24000
+    sliding_window: int = 250             # parsed; encode() builds a FULL causal mask (SpeechTokenizerEncoder.swift:1038-1042)
+    upsampling_ratios: List[int] = field(default_factory=lambda: [8, 6, 5, 4])
+    use_causal_conv: bool = True
+    use_conv_shortcut: bool = False
+
+    @property
+    def seanet_stride(self) -> int:
+        r = 1
+        for x in self.upsampling_ratios:
+            r *= x
+        return r
+
+    @property
+    def downsample_stride(self) -> int:   # SpeechTokenizerEncoder.swift:1005-1006
+        return int((self.sampling_rate / self.seanet_stride) / self.frame_rate)
+
+    @classmethod
+    def from_dict(cls, d: dict) -> "EncoderConfig":
+        return cls(**{k: d[k] for k in cls.__dataclass_fields__ if k in d})
+
+    def to_dict(self) -> dict:
+        return asdict(self)
+
+    @classmethod
+    def tiny(cls) -> "EncoderConfig":
+        """Same topology, small widths, for CPU tests (total stride 2*2*3*2 * 2 = 48 samples per code frame)."""
+        return cls(codebook_dim=16, codebook_size=32, head_dim=8, hidden_size=32, intermediate_size=64, num_attention_heads=4,
+                   num_key_value_heads=4, num_filters=4, num_hidden_layers=2, num_quantizers=20, upsampling_ratios=[2, 3, 2, 2],
+                   sampling_rate=24000, frame_rate=500.0)
+
+
+@dataclass
 class TokenizerConfig:
     # Config.swift:586-592 defaults
     encoder_valid_num_quantizers: int = 16

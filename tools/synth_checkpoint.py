@@ -21,7 +21,7 @@ from typing import Dict, Optional
 import numpy as np
 import torch
 
-from .q3cfg import DecoderConfig, TokenizerConfig
+from .q3cfg import DecoderConfig, EncoderConfig, TokenizerConfig
 
 DEFAULT_SEED = 20261018
 # Global scale of outConv, calibrated once with tools in tests (PCM std ~0.15).
@@ -138,9 +138,100 @@ def make_decoder_state(cfg: DecoderConfig, seed: int = DEFAULT_SEED, out_gain: f
     return state
 
 
+def encoder_tensor_specs(cfg: EncoderConfig):
+    """(on-disk key, shape, kind, fan_in) of the speech-tokenizer ENCODER in the PyTorch / HF layout the reference remaps
+    (Qwen3.swift:1514-1527: ``encoder.encoder.layers.N``; 1627-1649 transformer names; 1661-1676 quantizer names)."""
+    specs = []
+    e = "encoder.encoder.layers"
+    nf, mult = cfg.num_filters, 1
+    specs += [(f"{e}.0.conv.weight", (nf, cfg.audio_channels, cfg.kernel_size), "w", cfg.audio_channels * cfg.kernel_size),
+              (f"{e}.0.conv.bias", (nf,), "b", 0)]
+    idx = 1
+    for ratio in reversed(cfg.upsampling_ratios):        # python layers: [res, elu, down] per ratio -> indices 1,3 / 4,6 / ...
+        dim = mult * nf
+        hid = dim // cfg.compress
+        specs += [(f"{e}.{idx}.block.1.conv.weight", (hid, dim, cfg.residual_kernel_size), "wres", dim * cfg.residual_kernel_size),
+                  (f"{e}.{idx}.block.1.conv.bias", (hid,), "b", 0),
+                  (f"{e}.{idx}.block.3.conv.weight", (dim, hid, 1), "wres", hid),
+                  (f"{e}.{idx}.block.3.conv.bias", (dim,), "b", 0),
+                  (f"{e}.{idx + 2}.conv.weight", (2 * dim, dim, 2 * ratio), "w", dim * 2 * ratio),
+                  (f"{e}.{idx + 2}.conv.bias", (2 * dim,), "b", 0)]
+        idx += 3
+        mult *= 2
+    specs += [(f"{e}.{idx + 1}.conv.weight", (cfg.hidden_size, mult * nf, cfg.last_kernel_size), "w", mult * nf * cfg.last_kernel_size),
+              (f"{e}.{idx + 1}.conv.bias", (cfg.hidden_size,), "b", 0)]
+    H, I = cfg.hidden_size, cfg.intermediate_size
+    hd = H // cfg.num_attention_heads
+    KV = cfg.num_key_value_heads * hd
+    for n in range(cfg.num_hidden_layers):
+        p = f"encoder.encoder_transformer.layers.{n}"
+        specs += [(f"{p}.input_layernorm.weight", (H,), "norm", 0), (f"{p}.input_layernorm.bias", (H,), "b", 0),
+                  (f"{p}.post_attention_layernorm.weight", (H,), "norm", 0), (f"{p}.post_attention_layernorm.bias", (H,), "b", 0),
+                  (f"{p}.self_attn.q_proj.weight", (H, H), "w", H), (f"{p}.self_attn.k_proj.weight", (KV, H), "w", H),
+                  (f"{p}.self_attn.v_proj.weight", (KV, H), "w", H), (f"{p}.self_attn.o_proj.weight", (H, H), "w", H),
+                  (f"{p}.mlp.fc1.weight", (I, H), "w", H), (f"{p}.mlp.fc2.weight", (H, I), "w", I),
+                  (f"{p}.self_attn_layer_scale.scale", (H,), "lscale", 0), (f"{p}.mlp_layer_scale.scale", (H,), "lscale", 0)]
+    s = cfg.downsample_stride
+    specs.append(("encoder.downsample.conv.weight", (H, H, 2 * s), "w", H * 2 * s))
+    q = "encoder.quantizer"
+    for part, n in (("semantic_residual_vector_quantizer", 1), ("acoustic_residual_vector_quantizer", cfg.num_quantizers - 1)):
+        specs += [(f"{q}.{part}.input_proj.weight", (cfg.codebook_dim, H, 1), "w", H),
+                  (f"{q}.{part}.output_proj.weight", (H, cfg.codebook_dim, 1), "w", cfg.codebook_dim)]
+        for i in range(n):
+            specs += [(f"{q}.{part}.layers.{i}.codebook.cluster_usage", (cfg.codebook_size,), "usage", 0),
+                      (f"{q}.{part}.layers.{i}.codebook.embed_sum", (cfg.codebook_size, cfg.codebook_dim), "embsum_enc", 0),
+                      (f"{q}.{part}.layers.{i}.codebook.initialized", (1,), "flag", 0)]
+    return specs
+
+
+def make_encoder_state(cfg: EncoderConfig, seed: int = DEFAULT_SEED) -> Dict[str, torch.Tensor]:
+    """Random-init encoder weights of the named architecture (the Swift initialisers give zero biases / tiny uniform weights,
+    STE.swift:243-254; drawn here so that every stage carries signal).  Codebook l of a residual quantizer is drawn at the scale
+    of the residual that reaches it (x 0.8 per layer), so that nearest-neighbour search stays meaningful down the chain."""
+    g = torch.Generator(device="cpu")
+    g.manual_seed(seed + 77)
+    state: Dict[str, torch.Tensor] = {}
+    for key, shape, kind, fan_in in encoder_tensor_specs(cfg):
+        if kind == "usage":
+            t = torch.rand(shape, generator=g, dtype=torch.float32) * 99.0 + 1.0
+        elif kind == "embsum_enc":
+            usage = state[key.replace("embed_sum", "cluster_usage")]
+            layer = int(key.split(".layers.")[1].split(".")[0])
+            t = _normal(g, shape, 0.6 * (0.8 ** layer)) * usage[:, None]
+        elif kind == "flag":
+            t = torch.ones(shape, dtype=torch.float32)
+        elif kind == "w":
+            t = _uniform(g, shape, (3.0 / fan_in) ** 0.5)
+        elif kind == "wres":
+            t = _uniform(g, shape, (1.0 / fan_in) ** 0.5)
+        elif kind == "b":
+            t = _normal(g, shape, 0.02)
+        elif kind == "norm":
+            t = _normal(g, shape, 0.1, mean=1.0)
+        elif kind == "lscale":
+            t = torch.rand(shape, generator=g, dtype=torch.float32) * 0.45 + 0.05
+        else:
+            raise AssertionError(kind)
+        state[key] = t.contiguous()
+    return state
+
+
+def synth_audio(B: int, samples: int, seed: int) -> np.ndarray:
+    """[B, 1, samples] float32: a few decaying sinusoids plus noise, |x| < 1 (speech-like dynamics, deterministic)."""
+    rng = np.random.default_rng(seed)
+    t = np.arange(samples, dtype=np.float64) / 24000.0
+    out = np.zeros((B, 1, samples), dtype=np.float64)
+    for b in range(B):
+        for _ in range(6):
+            f = rng.uniform(80.0, 4000.0)
+            out[b, 0] += rng.uniform(0.02, 0.15) * np.sin(2 * np.pi * f * t + rng.uniform(0, 6.28)) * (0.5 + 0.5 * np.sin(2 * np.pi * rng.uniform(1, 8) * t))
+        out[b, 0] += rng.normal(0, 0.02, size=samples)
+    return np.clip(out, -1.0, 1.0).astype(np.float32)
+
+
 def write_checkpoint(model_dir: str, cfg: Optional[DecoderConfig] = None, seed: int = DEFAULT_SEED,
                      dtype: str = "float32", with_encoder_stub: bool = False,
-                     mlx_layout: bool = False, out_gain: float = 1.0) -> str:
+                     mlx_layout: bool = False, out_gain: float = 1.0, encoder_cfg: Optional[EncoderConfig] = None) -> str:
     """Write ``<model_dir>/speech_tokenizer/`` and return that path.
 
     dtype 'float16' + no encoder == the 'lite' variant's on-disk form.
@@ -169,6 +260,10 @@ def write_checkpoint(model_dir: str, cfg: Optional[DecoderConfig] = None, seed: 
         out["encoder.encoder.layers.0.conv.weight"] = torch.zeros(4, 1, 7, dtype=tdtype)
         out["encoder.quantizer.semantic_residual_vector_quantizer.layers.0.codebook.embed_sum"] = torch.zeros(8, 4, dtype=tdtype)
         tok.encoder_config = {"num_filters": 4}
+    if encoder_cfg is not None:   # a real encoder, in a second shard (the reference merges every *.safetensors of the directory)
+        enc = {k: v.to(tdtype).contiguous() for k, v in make_encoder_state(encoder_cfg, seed).items()}
+        save_file(enc, os.path.join(st_dir, "model-encoder.safetensors"))
+        tok.encoder_config = encoder_cfg.to_dict()
     save_file(out, os.path.join(st_dir, "model.safetensors"))
     with open(os.path.join(st_dir, "config.json"), "w") as f:
         json.dump(tok.to_dict(), f, indent=1)
