@@ -157,6 +157,31 @@ int q3tts_codec_embed_sum(q3tts_codec_embedder* e, const int32_t* codes, int64_t
 int q3tts_codec_embed_sum_device(q3tts_codec_embedder* e, const int32_t* d_codes, int64_t n_frames, void* d_out,
                                  void* stream);
 
+/* ---- speech-tokenizer ENCODER: audio -> codes ----------------------------
+ * Replaces Qwen3TTSSpeechTokenizer.encode / Qwen3TTSSpeechTokenizerEncoder.encode
+ * (SpeechTokenizer.swift:838-852, SpeechTokenizerEncoder.swift:1031-1056; callers: voice cloning, Qwen3.swift:430-440):
+ * Seanet encoder (causal convs, strides 4,5,6,8) -> 8-layer causal transformer with RoPE -> stride-2 conv -> split residual
+ * vector quantizer (nearest codebook entry per layer, float32), first `valid_quantizers` (16) codebooks returned.
+ * q3tts_encoder_load reads <dir>/config.json (`encoder_config`, Config.swift:419-560) and the `encoder.*` tensors of the
+ * directory's .safetensors files with the reference's key remap (Qwen3.swift:1514-1748); a checkpoint without an
+ * encoder (the "lite" variants) is Q3TTS_EFORMAT.  Only opts->device is used (the encoder computes in float32).
+ * audio: float32 [B, samples] (the reference's [B, 1, samples]); codes_out: int32 [B, valid_quantizers, T] with
+ * T = q3tts_encode_frames(samples) = the ceil-division chain of the strides (12.5 frames per second).
+ * Every utterance of a call has the same length (the reference API); encode different lengths in separate calls.     */
+typedef struct q3tts_encoder q3tts_encoder;
+int q3tts_encoder_load(const char* speech_tokenizer_dir, const q3tts_options* opts, q3tts_encoder** out);
+void q3tts_encoder_free(q3tts_encoder* e);
+/* valid_quantizers, codebook_size, hop (input samples per code frame when the length divides evenly), sampling_rate; any may be NULL */
+int q3tts_encoder_info(const q3tts_encoder* e, int32_t* valid_quantizers, int32_t* codebook_size, int32_t* hop,
+                       int32_t* sampling_rate, int64_t* num_parameters);
+int64_t q3tts_encode_frames(const q3tts_encoder* e, int64_t samples);
+int q3tts_encode(q3tts_encoder* e, const float* audio, int32_t B, int64_t samples, int32_t* codes_out);
+/* debug / parity: keep stage outputs of the next encodes; q3tts_encoder_tap copies stage `name` as float32 [B, rows, C]
+ * (channels last) and writes {B, rows, C} to dims; out == NULL only queries dims.  Names: "hid0".."hid3" / "res0".."res3" (the Seanet stages' hidden
+ * activation and stream after the residual block), "layer3" (last strided conv), "seanet", "transformer", "downsample".                                                                   */
+int q3tts_encoder_set_taps(q3tts_encoder* e, int32_t enable);
+int q3tts_encoder_tap(q3tts_encoder* e, const char* name, float* out, int64_t capacity, int64_t dims[3]);
+
 /* ---- decode: device buffers (codes and PCM already in HBM), asynchronous on `stream` ---------
  * Same semantics as q3tts_decode; `stream` is a cudaStream_t (NULL = legacy default stream).
  * Returns after enqueueing; errors detected on device (bad code ids) surface at

@@ -173,10 +173,13 @@ class OracleEncoder:
             dil = 1
             for ri in range(c.num_residual_layers):
                 r = f"{p}.residuals.{ri}"
-                y = self.sconv(self.elu(x), f"{r}.block.0", c.residual_kernel_size, dil=dil)
-                y = self.sconv(self.elu(y), f"{r}.block.1", 1)
-                x = y + x                                                            # trueSkip (use_conv_shortcut = false)
+                y = self.elu(self.sconv(self.elu(x), f"{r}.block.0", c.residual_kernel_size, dil=dil))
+                if taps is not None:
+                    taps[f"hid{li}"] = y
+                x = self.sconv(y, f"{r}.block.1", 1) + x                             # trueSkip (use_conv_shortcut = false)
                 dil *= c.dilation_growth_rate
+            if taps is not None:
+                taps[f"res{li}"] = x
             x = self.sconv(self.elu(x), f"{p}.downsample", 2 * ratio, stride=ratio)
             if taps is not None:
                 taps[f"layer{li}"] = x

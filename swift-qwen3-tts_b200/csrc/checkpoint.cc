@@ -454,4 +454,203 @@ void load_checkpoint(const std::string& dir, Checkpoint* out) {
   out->cfg.num_parameters = params;
 }
 
+// ---- encoder (row N3) ----------------------------------------------------------------------------------------------------
+static void parse_encoder_config(const std::string& dir, EncoderConfig* c) {
+  std::string text = read_file(dir + "/config.json");
+  Json root;
+  try {
+    root = JsonParser(text.data(), text.size()).parse();
+  } catch (const std::exception& e) {
+    throw Error(Q3TTS_EFORMAT, std::string("config.json: ") + e.what());
+  }
+  if (root.kind != Json::Obj) throw Error(Q3TTS_EFORMAT, "config.json: top level is not an object");
+  const Json* ec = root.find("encoder_config");
+  if (!ec || ec->kind != Json::Obj)                                      // Qwen3.swift:433 "Speech tokenizer encoder not available"
+    throw Error(Q3TTS_EFORMAT, "config.json: no encoder_config (this checkpoint has no speech-tokenizer encoder)");
+  const Json& e = *ec;
+  *c = EncoderConfig();
+  c->valid_quantizers = geti(root, "encoder_valid_num_quantizers", 16);
+  c->frame_rate = getf(e, "frame_rate", 12.5f);
+  c->audio_channels = geti(e, "audio_channels", 1);
+  c->codebook_dim = geti(e, "codebook_dim", 256);
+  c->codebook_size = geti(e, "codebook_size", 2048);
+  c->compress = geti(e, "compress", 2);
+  c->dilation_growth_rate = geti(e, "dilation_growth_rate", 2);
+  c->head_dim = geti(e, "head_dim", 64);
+  c->hidden_size = geti(e, "hidden_size", 512);
+  c->intermediate_size = geti(e, "intermediate_size", 2048);
+  c->kernel_size = geti(e, "kernel_size", 7);
+  c->last_kernel_size = geti(e, "last_kernel_size", 3);
+  c->num_attention_heads = geti(e, "num_attention_heads", 8);
+  c->num_filters = geti(e, "num_filters", 64);
+  c->num_hidden_layers = geti(e, "num_hidden_layers", 8);
+  c->num_key_value_heads = geti(e, "num_key_value_heads", 8);
+  c->num_quantizers = geti(e, "num_quantizers", 32);
+  c->num_residual_layers = geti(e, "num_residual_layers", 1);
+  c->residual_kernel_size = geti(e, "residual_kernel_size", 3);
+  c->rope_theta = getf(e, "rope_theta", 10000.0f);
+  c->sampling_rate = geti(e, "sampling_rate", 24000);
+  int32_t n = 0, r[8];
+  get_list(e, "upsampling_ratios", {8, 6, 5, 4}, &n, r);
+  c->n_ratios = n;
+  for (int i = 0; i < n; ++i) c->ratios[i] = r[i];
+  const Json* cz = e.find("use_causal_conv");
+  c->use_causal_conv = (cz && cz->kind == Json::Bool) ? (cz->b ? 1 : 0) : 1;
+  const Json* sc = e.find("use_conv_shortcut");
+  c->use_conv_shortcut = (sc && sc->kind == Json::Bool) ? (sc->b ? 1 : 0) : 0;
+  // what this implementation supports (the shipped checkpoints' values; the reference would build other graphs for the rest)
+  if (!c->use_causal_conv || c->use_conv_shortcut || c->audio_channels != 1 || c->num_residual_layers != 1)
+    throw Error(Q3TTS_EFORMAT, "encoder_config: only causal convs, true skip connections, mono audio and one residual layer per stage are supported");
+  if (c->n_ratios < 1 || c->num_filters % 8 || c->compress != 2 || c->hidden_size % 4 || c->codebook_dim % 4 ||
+      c->num_attention_heads < 1 || c->hidden_size % c->num_attention_heads || c->num_key_value_heads < 1 ||
+      c->num_attention_heads % c->num_key_value_heads || c->num_quantizers < 2 || c->valid_quantizers < 2 ||
+      c->valid_quantizers > c->num_quantizers || c->downsample_stride() < 1 || c->kernel_size < 1 || c->residual_kernel_size < 1)
+    throw Error(Q3TTS_EFORMAT, "encoder_config: inconsistent dimensions");
+}
+
+void load_encoder_checkpoint(const std::string& dir, EncoderCheckpoint* out) {
+  parse_encoder_config(dir, &out->cfg);
+  const EncoderConfig& c = out->cfg;
+  TensorMap raw;
+  for (auto& f : list_safetensors(dir)) read_safetensors(f, &raw, "encoder.");
+  static const std::pair<const char*, const char*> kSeanet[] = {   // Qwen3.swift:1517-1528 (the four-ratio layout of the shipped model)
+      {"encoder.encoder.layers.0.", "encoder.encoder.init_conv1d."},
+      {"encoder.encoder.layers.1.", "encoder.encoder.layers.0.residuals.0."},
+      {"encoder.encoder.layers.3.", "encoder.encoder.layers.0.downsample."},
+      {"encoder.encoder.layers.4.", "encoder.encoder.layers.1.residuals.0."},
+      {"encoder.encoder.layers.6.", "encoder.encoder.layers.1.downsample."},
+      {"encoder.encoder.layers.7.", "encoder.encoder.layers.2.residuals.0."},
+      {"encoder.encoder.layers.9.", "encoder.encoder.layers.2.downsample."},
+      {"encoder.encoder.layers.10.", "encoder.encoder.layers.3.residuals.0."},
+      {"encoder.encoder.layers.12.", "encoder.encoder.layers.3.downsample."},
+      {"encoder.encoder.layers.14.", "encoder.encoder.final_conv1d."}};
+  if (c.n_ratios != 4) throw Error(Q3TTS_EFORMAT, "encoder_config.upsampling_ratios must have 4 entries (the reference's key remap names layers 0..14)");
+  TensorMap& san = out->tensors;
+  std::map<std::string, std::pair<const HostTensor*, const HostTensor*>> books;   // base -> (usage, sum)
+  for (auto& kv : raw) {
+    const std::string& key = kv.first;
+    const HostTensor& value = kv.second;
+    if (starts(key, "encoder.quantizer.") && has(key, ".codebook.")) {
+      const size_t pos = key.find(".codebook.");
+      const std::string base = key.substr(0, pos), fld = key.substr(pos + 10);
+      if (fld == "embed_sum") { books[base].second = &value; continue; }
+      if (fld == "cluster_usage") { books[base].first = &value; continue; }
+      if (has(key, ".initialized")) continue;
+    }
+    std::string nk = key;
+    for (auto& m : kSeanet)
+      if (starts(nk, m.first)) {
+        replace_all(nk, m.first, m.second);
+        break;
+      }
+    if (has(nk, ".residuals.")) {
+      replace_all(nk, ".block.1.", ".block.0.");
+      replace_all(nk, ".block.3.", ".block.1.");
+    }
+    HostTensor nv;
+    bool set = false;
+    const bool is3 = value.shape.size() == 3;
+    const bool seanet_conv = starts(nk, "encoder.encoder.") && !has(nk, "encoder_transformer") && !has(nk, "quantizer") &&
+                             (has(nk, ".conv.weight") || has(nk, ".conv.bias"));
+    if (seanet_conv) {
+      replace_all(nk, ".conv.weight", ".conv.conv.weight");
+      replace_all(nk, ".conv.bias", ".conv.conv.bias");
+      if (nk.size() > 7 && nk.substr(nk.size() - 7) == ".weight" && is3) { nv = permute3(value, 0, 2, 1); set = true; }   // forced
+    }
+    if (has(nk, "encoder.encoder_transformer.layers.")) {
+      replace_all(nk, "encoder.encoder_transformer.layers.", "encoder.encoder_transformer.transformer.layers.");
+      replace_all(nk, ".input_layernorm.", ".norm1.");
+      replace_all(nk, ".post_attention_layernorm.", ".norm2.");
+      replace_all(nk, ".mlp.fc1.", ".gating.linear1.");
+      replace_all(nk, ".mlp.fc2.", ".gating.linear2.");
+      replace_all(nk, ".self_attn_layer_scale.", ".layer_scale_1.");
+      replace_all(nk, ".mlp_layer_scale.", ".layer_scale_2.");
+    }
+    if (starts(nk, "encoder.downsample.conv.") && !has(nk, "encoder.downsample.conv.conv.")) {
+      const bool is_w = nk.size() > 7 && nk.substr(nk.size() - 7) == ".weight";
+      replace_all(nk, "encoder.downsample.conv.", "encoder.downsample.conv.conv.conv.");
+      if (is_w && is3) { nv = permute3(value, 0, 2, 1); set = true; }
+    }
+    if (has(nk, "encoder.quantizer.")) {
+      replace_all(nk, ".semantic_residual_vector_quantizer.", ".rvq_first.");
+      replace_all(nk, ".acoustic_residual_vector_quantizer.", ".rvq_rest.");
+      replace_all(nk, ".rvq_first.layers.", ".rvq_first.vq.layers.");
+      replace_all(nk, ".rvq_rest.layers.", ".rvq_rest.vq.layers.");
+    }
+    const bool was_seanet_w = starts(nk, "encoder.encoder.") && !has(nk, "encoder_transformer") && !has(nk, "quantizer") &&
+                              nk.size() > 17 && nk.substr(nk.size() - 17) == ".conv.conv.weight";
+    const bool is_proj = (has(nk, "input_proj.weight") || has(nk, "output_proj.weight")) && has(nk, "quantizer");
+    if (is_proj && is3) { nv = permute3(value, 0, 2, 1); set = true; }
+    if (has(nk, "conv.weight") && is3 && !is_proj && !was_seanet_w && !is_mlx_conv_layout(value.shape)) {   // generic branch, from the ORIGINAL value
+      nv = permute3(value, 0, 2, 1);
+      set = true;
+    }
+    san[nk] = set ? std::move(nv) : value;
+  }
+  for (auto& b : books) {   // Qwen3.swift:1726-1748: the raw sums are kept, EncoderEuclideanCodebook divides (STE.swift:738-743)
+    if (!b.second.first || !b.second.second) continue;
+    std::string nb = b.first;
+    replace_all(nb, ".semantic_residual_vector_quantizer.", ".rvq_first.");
+    replace_all(nb, ".acoustic_residual_vector_quantizer.", ".rvq_rest.");
+    replace_all(nb, ".rvq_first.layers.", ".rvq_first.vq.layers.");
+    replace_all(nb, ".rvq_rest.layers.", ".rvq_rest.vq.layers.");
+    san[nb + ".codebook.embeddingSum"] = *b.second.second;
+    san[nb + ".codebook.clusterUsage"] = *b.second.first;
+  }
+  // strict validation of what encode() reads
+  std::map<std::string, std::vector<int64_t>> want;
+  const int nf = c.num_filters, H = c.hidden_size, hd = H / c.num_attention_heads;
+  want["encoder.encoder.init_conv1d.conv.conv.weight"] = {nf, c.kernel_size, 1};
+  want["encoder.encoder.init_conv1d.conv.conv.bias"] = {nf};
+  int mult = 1;
+  for (int li = 0; li < c.n_ratios; ++li) {
+    const int ratio = c.ratios[c.n_ratios - 1 - li], dim = mult * nf, hid = dim / c.compress;
+    const std::string p = "encoder.encoder.layers." + std::to_string(li);
+    want[p + ".residuals.0.block.0.conv.conv.weight"] = {hid, c.residual_kernel_size, dim};
+    want[p + ".residuals.0.block.0.conv.conv.bias"] = {hid};
+    want[p + ".residuals.0.block.1.conv.conv.weight"] = {dim, 1, hid};
+    want[p + ".residuals.0.block.1.conv.conv.bias"] = {dim};
+    want[p + ".downsample.conv.conv.weight"] = {2 * dim, 2 * ratio, dim};
+    want[p + ".downsample.conv.conv.bias"] = {2 * dim};
+    mult *= 2;
+  }
+  want["encoder.encoder.final_conv1d.conv.conv.weight"] = {H, c.last_kernel_size, mult * nf};
+  want["encoder.encoder.final_conv1d.conv.conv.bias"] = {H};
+  for (int i = 0; i < c.num_hidden_layers; ++i) {
+    const std::string p = "encoder.encoder_transformer.transformer.layers." + std::to_string(i);
+    for (const char* nrm : {".norm1", ".norm2"}) { want[p + nrm + ".weight"] = {H}; want[p + nrm + ".bias"] = {H}; }
+    want[p + ".self_attn.q_proj.weight"] = {H, H};
+    want[p + ".self_attn.k_proj.weight"] = {c.num_key_value_heads * hd, H};
+    want[p + ".self_attn.v_proj.weight"] = {c.num_key_value_heads * hd, H};
+    want[p + ".self_attn.o_proj.weight"] = {H, H};
+    want[p + ".gating.linear1.weight"] = {c.intermediate_size, H};
+    want[p + ".gating.linear2.weight"] = {H, c.intermediate_size};
+    want[p + ".layer_scale_1.scale"] = {H};
+    want[p + ".layer_scale_2.scale"] = {H};
+  }
+  want["encoder.downsample.conv.conv.conv.weight"] = {H, 2 * c.downsample_stride(), H};
+  for (int part = 0; part < 2; ++part) {
+    const std::string q = std::string("encoder.quantizer.") + (part == 0 ? "rvq_first" : "rvq_rest");
+    want[q + ".input_proj.weight"] = {c.codebook_dim, 1, H};
+    const int n = part == 0 ? 1 : c.valid_quantizers - 1;        // the layers past encoder_valid_num_quantizers are never evaluated
+    for (int i = 0; i < n; ++i) {
+      want[q + ".vq.layers." + std::to_string(i) + ".codebook.embeddingSum"] = {c.codebook_size, c.codebook_dim};
+      want[q + ".vq.layers." + std::to_string(i) + ".codebook.clusterUsage"] = {c.codebook_size};
+    }
+  }
+  int64_t params = 0;
+  for (auto& ex : want) {
+    auto it = san.find(ex.first);
+    if (it == san.end()) throw Error(Q3TTS_EFORMAT, "missing encoder tensor " + ex.first);
+    if (it->second.shape != ex.second) {
+      std::string got, wnt;
+      for (auto d : it->second.shape) got += std::to_string(d) + ",";
+      for (auto d : ex.second) wnt += std::to_string(d) + ",";
+      throw Error(Q3TTS_EFORMAT, "encoder tensor " + ex.first + " has shape [" + got + "] expected [" + wnt + "]");
+    }
+    params += it->second.numel();
+  }
+  out->num_parameters = params;
+}
+
 }  // namespace q3

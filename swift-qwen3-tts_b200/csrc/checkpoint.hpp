@@ -54,6 +54,33 @@ struct CodecEmbeddingTables {
 };
 void load_codec_embeddings(const std::string& model_dir, CodecEmbeddingTables* out);
 
+// Row N3 of SURVEY 8(f): the speech-tokenizer ENCODER (audio -> codes).  Hyper-parameters = Qwen3TTSTokenizerEncoderConfig
+// (Config.swift:419-560, every key optional with the defaults below); tensors keyed by the Swift module path after the reference's
+// remap (Qwen3.swift:1514-1527, 1544-1566, 1590-1679, 1726-1748), conv weights in MLX layout [Cout, K, Cin].
+struct EncoderConfig {
+  float frame_rate = 12.5f;
+  int audio_channels = 1, codebook_dim = 256, codebook_size = 2048, compress = 2, dilation_growth_rate = 2, head_dim = 64;
+  int hidden_size = 512, intermediate_size = 2048, kernel_size = 7, last_kernel_size = 3;
+  int num_attention_heads = 8, num_filters = 64, num_hidden_layers = 8, num_key_value_heads = 8, num_quantizers = 32;
+  int num_residual_layers = 1, residual_kernel_size = 3, sampling_rate = 24000;
+  float rope_theta = 10000.0f;
+  int n_ratios = 4, ratios[8] = {8, 6, 5, 4, 0, 0, 0, 0};     // upsampling_ratios; the Seanet walks them REVERSED (STE.swift:420)
+  int use_causal_conv = 1, use_conv_shortcut = 0;
+  int valid_quantizers = 16;                                   // encoder_valid_num_quantizers (Config.swift:586); STE.swift:957
+  int downsample_stride() const {                              // STE.swift:1005-1006
+    int s = 1;
+    for (int i = 0; i < n_ratios; ++i) s *= ratios[i];
+    return (int)(((float)sampling_rate / (float)s) / frame_rate);
+  }
+};
+struct EncoderCheckpoint {
+  EncoderConfig cfg;
+  TensorMap tensors;
+  int64_t num_parameters = 0;
+};
+// Throws q3::Error(Q3TTS_EFORMAT) when config.json has no encoder_config (the "lite" checkpoints) or a tensor is missing / misshapen.
+void load_encoder_checkpoint(const std::string& dir, EncoderCheckpoint* out);
+
 // The decoder's expected tensor inventory after sanitize: key -> MLX-layout shape.
 std::map<std::string, std::vector<int64_t>> expected_decoder_tensors(const q3tts_config& cfg);
 

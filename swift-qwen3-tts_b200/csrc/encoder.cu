@@ -1,0 +1,382 @@
+// Speech-tokenizer ENCODER (audio -> codes), SURVEY 8(f) row N3: host engine.  Reference: Qwen3TTSSpeechTokenizerEncoder.encode,
+// Sources/Qwen3TTS/Models/SpeechTokenizerEncoder.swift:1031-1056 ("STE.swift") and the modules it drives (cited per stage below).
+// Everything is float32 and channels-last [B, rows, C]; see encoder.hpp for the data layout.
+#include "encoder.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#define ENC_CUDA_OK(x)                                                                                          \
+  do {                                                                                                          \
+    cudaError_t e_ = (x);                                                                                       \
+    if (e_ != cudaSuccess) throw Error(Q3TTS_ECUDA, std::string(#x) + ": " + cudaGetErrorString(e_));           \
+  } while (0)
+
+namespace q3 {
+namespace {
+
+float* upload(EncoderModel& m, const std::vector<float>& v) {
+  float* d = nullptr;
+  ENC_CUDA_OK(cudaMalloc(&d, std::max<size_t>(v.size(), 1) * sizeof(float)));
+  m.allocs.push_back(d);
+  ENC_CUDA_OK(cudaMemcpyAsync(d, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice, m.stream));
+  ENC_CUDA_OK(cudaStreamSynchronize(m.stream));
+  return d;
+}
+
+const HostTensor& T(const EncoderCheckpoint& ck, const std::string& k) {
+  auto it = ck.tensors.find(k);
+  if (it == ck.tensors.end()) throw Error(Q3TTS_EFORMAT, "missing encoder tensor " + k);
+  return it->second;
+}
+
+// MLX conv weight [Cout, K, Cin] -> multi-tap GEMM weights [taps][N][Cin'].
+//  stride 1: taps = K, W[j][n][c] = w[n][j][c]                                   (cross-correlation, STE.swift:262-284)
+//  stride s, K = 2s (STE.swift:369-379, 688-698): the input is viewed as [frames, s*Cin]; left padding K - s = s is exactly one
+//  row of that view, so y[t] = W0 . row(t-1) + W1 . row(t) with W0[n][j*Cin + c] = w[n][j][c], W1[n][j*Cin + c] = w[n][s + j][c].
+EncGemm pack_conv(EncoderModel& m, const HostTensor& w, const HostTensor* bias, int stride) {
+  const int N = (int)w.shape[0], K = (int)w.shape[1], Cin = (int)w.shape[2];
+  EncGemm g;
+  g.N = N;
+  std::vector<float> packed;
+  if (stride == 1) {
+    g.taps = K; g.Cin = Cin;
+    packed.resize((size_t)K * N * Cin);
+    for (int n = 0; n < N; ++n)
+      for (int j = 0; j < K; ++j)
+        for (int c = 0; c < Cin; ++c) packed[((size_t)j * N + n) * Cin + c] = w.data[((size_t)n * K + j) * Cin + c];
+  } else {
+    if (K != 2 * stride) throw Error(Q3TTS_EFORMAT, "encoder: a strided conv must have kernel = 2 * stride");
+    g.taps = 2; g.Cin = stride * Cin;
+    packed.resize((size_t)2 * N * g.Cin);
+    for (int n = 0; n < N; ++n)
+      for (int j = 0; j < K; ++j)
+        for (int c = 0; c < Cin; ++c)
+          packed[((size_t)(j / stride) * N + n) * g.Cin + (size_t)(j % stride) * Cin + c] = w.data[((size_t)n * K + j) * Cin + c];
+  }
+  if (g.Cin % 4) throw Error(Q3TTS_EFORMAT, "encoder: channel counts must be multiples of 4");
+  g.w = upload(m, packed);
+  g.bias = bias ? upload(m, bias->data) : nullptr;
+  return g;
+}
+
+EncGemm pack_linear(EncoderModel& m, const std::vector<const HostTensor*>& rows) {   // y = x W^T, W [out, in]; several matrices stacked
+  EncGemm g;
+  g.taps = 1; g.Cin = (int)rows[0]->shape[1];
+  std::vector<float> packed;
+  for (auto* r : rows) {
+    if ((int)r->shape[1] != g.Cin) throw Error(Q3TTS_EFORMAT, "encoder: stacked linears differ in width");
+    packed.insert(packed.end(), r->data.begin(), r->data.end());
+    g.N += (int)r->shape[0];
+  }
+  if (g.Cin % 4) throw Error(Q3TTS_EFORMAT, "encoder: channel counts must be multiples of 4");
+  g.w = upload(m, packed);
+  return g;
+}
+
+void run_gemm(EncoderModel& m, const EncGemm& w, const BatchGeom& g, const float* A, int lda, int64_t a_bstride, const ConvGemmParams& epi) {
+  ConvGemmParams p = epi;
+  p.A = A; p.lda = lda; p.a_bstride = a_bstride;
+  p.W = w.w; p.rows_per_frame = 1; p.N = w.N; p.Cin = w.Cin; p.taps = w.taps; p.dil = 1;
+  if (!p.bias) p.bias = w.bias;
+  launch_conv_gemm_simt(p, g, DT_F32, DT_F32, m.stream);
+  ++m.launches;
+}
+
+}  // namespace
+
+EncoderModel* encoder_create(const std::string& dir, const q3tts_options& opts) {
+  EncoderCheckpoint ck;
+  load_encoder_checkpoint(dir, &ck);
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) throw Error(Q3TTS_ECUDA, "no CUDA device (this library has no CPU path)");
+  if (opts.device < 0 || opts.device >= ndev) throw Error(Q3TTS_EINVAL, "device index out of range");
+  ENC_CUDA_OK(cudaSetDevice(opts.device));
+  std::unique_ptr<EncoderModel> mp(new EncoderModel());
+  EncoderModel& m = *mp;
+  m.cfg = ck.cfg;
+  m.device = opts.device;
+  m.num_parameters = ck.num_parameters;
+  ENC_CUDA_OK(cudaStreamCreateWithFlags(&m.stream, cudaStreamNonBlocking));
+  const EncoderConfig& c = m.cfg;
+  {  // init conv: [nf, k, 1] -> [k][nf]
+    const HostTensor& w = T(ck, "encoder.encoder.init_conv1d.conv.conv.weight");
+    std::vector<float> pk((size_t)c.kernel_size * c.num_filters);
+    for (int n = 0; n < c.num_filters; ++n)
+      for (int j = 0; j < c.kernel_size; ++j) pk[(size_t)j * c.num_filters + n] = w.data[(size_t)n * c.kernel_size + j];
+    m.init_w = upload(m, pk);
+    m.init_b = upload(m, T(ck, "encoder.encoder.init_conv1d.conv.conv.bias").data);
+  }
+  int mult = 1;
+  for (int li = 0; li < c.n_ratios; ++li) {
+    EncStage st;
+    st.ratio = c.ratios[c.n_ratios - 1 - li];                                                 // ratios.reversed(), STE.swift:420
+    st.dim = mult * c.num_filters;
+    const std::string p = "encoder.encoder.layers." + std::to_string(li);
+    st.res3 = pack_conv(m, T(ck, p + ".residuals.0.block.0.conv.conv.weight"), &T(ck, p + ".residuals.0.block.0.conv.conv.bias"), 1);
+    st.res1 = pack_conv(m, T(ck, p + ".residuals.0.block.1.conv.conv.weight"), &T(ck, p + ".residuals.0.block.1.conv.conv.bias"), 1);
+    st.down = pack_conv(m, T(ck, p + ".downsample.conv.conv.weight"), &T(ck, p + ".downsample.conv.conv.bias"), st.ratio);
+    m.stages.push_back(st);
+    mult *= 2;
+  }
+  m.final_conv = pack_conv(m, T(ck, "encoder.encoder.final_conv1d.conv.conv.weight"), &T(ck, "encoder.encoder.final_conv1d.conv.conv.bias"), 1);
+  for (int i = 0; i < c.num_hidden_layers; ++i) {
+    const std::string p = "encoder.encoder_transformer.transformer.layers." + std::to_string(i);
+    EncLayer L;
+    L.n1w = upload(m, T(ck, p + ".norm1.weight").data); L.n1b = upload(m, T(ck, p + ".norm1.bias").data);
+    L.n2w = upload(m, T(ck, p + ".norm2.weight").data); L.n2b = upload(m, T(ck, p + ".norm2.bias").data);
+    L.qkv = pack_linear(m, {&T(ck, p + ".self_attn.q_proj.weight"), &T(ck, p + ".self_attn.k_proj.weight"), &T(ck, p + ".self_attn.v_proj.weight")});
+    L.o = pack_linear(m, {&T(ck, p + ".self_attn.o_proj.weight")});
+    L.fc1 = pack_linear(m, {&T(ck, p + ".gating.linear1.weight")});
+    L.fc2 = pack_linear(m, {&T(ck, p + ".gating.linear2.weight")});
+    L.ls1 = upload(m, T(ck, p + ".layer_scale_1.scale").data);
+    L.ls2 = upload(m, T(ck, p + ".layer_scale_2.scale").data);
+    m.layers.push_back(L);
+  }
+  {  // MLX RoPE(dimensions: head_dim, traditional: false, base: rope_theta), STE.swift:494: inv_freq[i] = base^(-i / (hd/2))
+    const int hd = c.hidden_size / c.num_attention_heads, half = hd / 2;
+    std::vector<float> f((size_t)half);
+    for (int i = 0; i < half; ++i) f[(size_t)i] = std::exp(-(float)i * (std::log(c.rope_theta) / (float)half));
+    m.inv_freq = upload(m, f);
+  }
+  m.downsample = pack_conv(m, T(ck, "encoder.downsample.conv.conv.conv.weight"), nullptr, c.downsample_stride());
+  for (int part = 0; part < 2; ++part) {
+    const std::string q = std::string("encoder.quantizer.") + (part == 0 ? "rvq_first" : "rvq_rest");
+    const HostTensor& pw = T(ck, q + ".input_proj.weight");                                   // [cb, 1, H]
+    HostTensor lin;
+    lin.shape = {pw.shape[0], pw.shape[2]};
+    lin.data = pw.data;
+    m.proj[part] = pack_linear(m, {&lin});
+    const int n = part == 0 ? 1 : c.valid_quantizers - 1;
+    for (int i = 0; i < n; ++i) {
+      const std::string b = q + ".vq.layers." + std::to_string(i) + ".codebook";
+      const HostTensor& sum = T(ck, b + ".embeddingSum");
+      const HostTensor& usage = T(ck, b + ".clusterUsage");
+      const int K = c.codebook_size, D = c.codebook_dim;
+      std::vector<float> E((size_t)K * D), nc2((size_t)K);
+      for (int r = 0; r < K; ++r) {                                                           // STE.swift:738-743
+        const float den = std::max(usage.data[(size_t)r], 1e-5f);
+        float s2 = 0.f;
+        for (int d = 0; d < D; ++d) {
+          const float e = sum.data[(size_t)r * D + d] / den;
+          E[(size_t)r * D + d] = e;
+          s2 += e * e;
+        }
+        nc2[(size_t)r] = -(s2 / 2.0f);
+      }
+      EncBook bk;
+      bk.part = part;
+      bk.score.taps = 1; bk.score.Cin = D; bk.score.N = K;
+      bk.score.w = upload(m, E);
+      bk.score.bias = upload(m, nc2);
+      m.books.push_back(bk);
+    }
+  }
+  return mp.release();
+}
+
+void encoder_destroy(EncoderModel* m) {
+  if (!m) return;
+  cudaSetDevice(m->device);
+  if (m->stream) cudaStreamSynchronize(m->stream);
+  for (void* p : m->allocs) cudaFree(p);
+  if (m->arena) cudaFree(m->arena);
+  if (m->stream) cudaStreamDestroy(m->stream);
+  delete m;
+}
+
+int64_t encoder_frames(const EncoderConfig& c, int64_t samples) {
+  int64_t L = samples;
+  for (int li = 0; li < c.n_ratios; ++li) {
+    const int r = c.ratios[c.n_ratios - 1 - li];
+    L = (L + r - 1) / r;                       // getExtraPaddingForConv1d pads the input to ceil(L / stride) frames, STE.swift:115-119
+  }
+  const int ds = c.downsample_stride();
+  return (L + ds - 1) / ds;
+}
+
+void encoder_encode(EncoderModel& m, const float* audio, int B, int64_t samples, int32_t* codes_out) {
+  std::lock_guard<std::mutex> lock(m.mu);
+  const EncoderConfig& c = m.cfg;
+  if (B < 1 || samples < 1 || !audio || !codes_out) throw Error(Q3TTS_EINVAL, "encode: bad arguments");
+  if (samples > (int64_t)1 << 30) throw Error(Q3TTS_EINVAL, "encode: audio too long");
+  ENC_CUDA_OK(cudaSetDevice(m.device));
+  cudaStream_t s = m.stream;
+  const int nst = c.n_ratios, ds = c.downsample_stride(), H = c.hidden_size, I = c.intermediate_size;
+  const int nh = c.num_attention_heads, nkv = c.num_key_value_heads, hd = H / nh, QW = (nh + 2 * nkv) * hd;
+  const int K = c.codebook_size, CB = c.codebook_dim, NQ = c.valid_quantizers;
+  // rows per utterance at every level: L valid, P allocated (the next strided conv views [P / r, r * C]; rows L..P-1 stay zero,
+  // which is the reference's right-hand "extra padding")
+  std::vector<int64_t> L((size_t)nst + 2), P((size_t)nst + 1);
+  L[0] = samples;
+  for (int li = 0; li < nst; ++li) {
+    const int r = m.stages[(size_t)li].ratio;
+    L[(size_t)li + 1] = (L[(size_t)li] + r - 1) / r;
+    P[(size_t)li] = L[(size_t)li + 1] * r;
+  }
+  const int64_t Tq = (L[(size_t)nst] + ds - 1) / ds;
+  L[(size_t)nst + 1] = Tq;
+  P[(size_t)nst] = Tq * ds;
+  if (P[0] * (int64_t)m.stages[0].dim > (int64_t)1 << 40) throw Error(Q3TTS_EINVAL, "encode: batch too large");
+
+  // ---- arena plan (bytes, 256-aligned) ----
+  size_t off = 0;
+  auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+  const size_t o_len = take(sizeof(int) * (size_t)B * (size_t)(nst + 2));
+  const size_t o_audio = take(sizeof(float) * (size_t)B * (size_t)samples);
+  std::vector<size_t> oX((size_t)nst + 1), oA((size_t)nst + 1), oH((size_t)nst);
+  for (int li = 0; li <= nst; ++li) {
+    const int dim = li < nst ? m.stages[(size_t)li].dim : 2 * m.stages[(size_t)nst - 1].dim;
+    oX[(size_t)li] = take(sizeof(float) * (size_t)B * (size_t)P[(size_t)li] * (size_t)dim);
+    oA[(size_t)li] = take(sizeof(float) * (size_t)B * (size_t)P[(size_t)li] * (size_t)dim);
+    if (li < nst) oH[(size_t)li] = take(sizeof(float) * (size_t)B * (size_t)P[(size_t)li] * (size_t)(dim / c.compress));
+  }
+  const size_t rowsT = (size_t)B * (size_t)P[(size_t)nst];
+  const size_t o_hs = take(sizeof(float) * rowsT * (size_t)H), o_nb = take(sizeof(float) * rowsT * (size_t)H);
+  const size_t o_qkv = take(sizeof(float) * rowsT * (size_t)QW), o_ao = take(sizeof(float) * rowsT * (size_t)H);
+  const size_t o_ff = take(sizeof(float) * rowsT * (size_t)I);
+  const size_t o_tap = take(m.taps_enabled ? sizeof(float) * rowsT * (size_t)H : 0);
+  const size_t rowsQ = (size_t)B * (size_t)Tq;
+  const size_t o_d = take(sizeof(float) * rowsQ * (size_t)H);
+  const size_t o_r0 = take(sizeof(float) * rowsQ * (size_t)CB), o_r1 = take(sizeof(float) * rowsQ * (size_t)CB);
+  const size_t o_sc = take(sizeof(float) * rowsQ * (size_t)K);
+  const size_t o_codes = take(sizeof(int32_t) * rowsQ * (size_t)NQ);
+  if (off > m.arena_cap) {
+    ENC_CUDA_OK(cudaStreamSynchronize(s));
+    if (m.arena) cudaFree(m.arena);
+    m.arena = nullptr; m.arena_cap = 0;
+    size_t free_b = 0, total_b = 0;
+    ENC_CUDA_OK(cudaMemGetInfo(&free_b, &total_b));
+    if (off > free_b) throw Error(Q3TTS_ENOMEM, "encode: the batch needs " + std::to_string(off >> 20) + " MiB of device memory; encode it in smaller batches");
+    if (cudaMalloc(&m.arena, off) != cudaSuccess) { cudaGetLastError(); throw Error(Q3TTS_ENOMEM, "encode: device allocation failed"); }
+    m.arena_cap = off;
+  }
+  char* base = (char*)m.arena;
+  auto F = [&](size_t o) { return (float*)(base + o); };
+  // zero everything the strided views may read past a level's valid rows (and the stale rows of a previous, longer call)
+  ENC_CUDA_OK(cudaMemsetAsync(base + o_audio, 0, off - o_audio, s));
+  m.launches = 0;
+
+  // ---- lengths + audio to the device ----
+  std::vector<int> hlen((size_t)B * (size_t)(nst + 2));
+  for (int lv = 0; lv < nst + 2; ++lv)
+    for (int b = 0; b < B; ++b) hlen[(size_t)lv * (size_t)B + (size_t)b] = (int)L[(size_t)lv];
+  int* d_len = (int*)(base + o_len);
+  ENC_CUDA_OK(cudaMemcpyAsync(d_len, hlen.data(), hlen.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+  ENC_CUDA_OK(cudaMemcpyAsync(F(o_audio), audio, sizeof(float) * (size_t)B * (size_t)samples, cudaMemcpyHostToDevice, s));
+  auto geom = [&](int64_t slot_rows, int level) {
+    BatchGeom g{};
+    g.B = B; g.Tmax = (int)slot_rows; g.len_frames = d_len + (size_t)level * (size_t)B; g.valid_frames = (long long)B * L[(size_t)level]; g.row_begin = nullptr;
+    return g;
+  };
+
+  // ---- Seanet (STE.swift:436-443) ----
+  launch_enc_init_conv(F(o_audio), samples, m.init_w, m.init_b, c.kernel_size, c.num_filters, F(oX[0]), F(oA[0]),
+                       P[0] * (int64_t)c.num_filters, geom(P[0], 0), s);
+  ++m.launches;
+  m.tap_index.clear();
+  for (int li = 0; li < nst; ++li) {
+    const EncStage& st = m.stages[(size_t)li];
+    const int dim = st.dim, hid = dim / c.compress;
+    const int64_t Pl = P[(size_t)li];
+    const BatchGeom g = geom(Pl, li);
+    {  // block.0: conv k3 on elu(x) -> elu(.) (STE.swift:337-340)
+      ConvGemmParams e{};
+      e.out_a = F(oH[(size_t)li]); e.lda_out = hid; e.ao_bstride = Pl * hid; e.a_elu = 1;
+      run_gemm(m, st.res3, g, F(oA[(size_t)li]), dim, Pl * dim, e);
+    }
+    {  // block.1: conv k1, + x (true skip, STE.swift:345-348); the stage's downsample reads elu(x') (STE.swift:389)
+      ConvGemmParams e{};
+      e.res = F(oX[(size_t)li]); e.ldres = dim; e.res_bstride = Pl * dim;
+      e.out_y = F(oX[(size_t)li]); e.ldy = dim; e.y_bstride = Pl * dim;
+      e.out_a = F(oA[(size_t)li]); e.lda_out = dim; e.ao_bstride = Pl * dim; e.a_elu = 1;
+      run_gemm(m, st.res1, g, F(oH[(size_t)li]), hid, Pl * hid, e);
+    }
+    {  // downsample: k = 2r, stride r, as a 2-tap GEMM over [frames, r * dim]
+      const int64_t Pn = P[(size_t)li + 1];
+      ConvGemmParams e{};
+      e.out_y = F(oX[(size_t)li + 1]); e.ldy = 2 * dim; e.y_bstride = Pn * 2 * dim;
+      e.out_a = F(oA[(size_t)li + 1]); e.lda_out = 2 * dim; e.ao_bstride = Pn * 2 * dim; e.a_elu = 1;
+      run_gemm(m, st.down, geom(L[(size_t)li + 1], li + 1), F(oA[(size_t)li]), st.ratio * dim, Pl * dim, e);
+      if (li == nst - 1) m.tap_index["layer" + std::to_string(li)] = EncTap{oX[(size_t)li + 1], Pn, L[(size_t)li + 1], 2 * dim};   // (earlier stages' outputs are updated in place by the next residual block)
+      m.tap_index["res" + std::to_string(li)] = EncTap{oX[(size_t)li], Pl, L[(size_t)li], dim};          // x + block(x), the stage's stream
+      m.tap_index["hid" + std::to_string(li)] = EncTap{oH[(size_t)li], Pl, L[(size_t)li], hid};          // elu(conv3(elu(x)))
+    }
+  }
+  const int64_t PT = P[(size_t)nst], LT = L[(size_t)nst];
+  const BatchGeom gT = geom(PT, nst);
+  {  // final conv on elu(x) (STE.swift:441-442) -> the transformer's stream
+    const int dimL = 2 * m.stages[(size_t)nst - 1].dim;
+    ConvGemmParams e{};
+    e.out_y = F(o_hs); e.ldy = H; e.y_bstride = PT * H;
+    run_gemm(m, m.final_conv, gT, F(oA[(size_t)nst]), dimL, PT * dimL, e);
+  }
+  if (m.taps_enabled) {
+    ENC_CUDA_OK(cudaMemcpyAsync(F(o_tap), F(o_hs), sizeof(float) * rowsT * (size_t)H, cudaMemcpyDeviceToDevice, s));
+    m.tap_index["seanet"] = EncTap{o_tap, PT, LT, H};
+  }
+
+  // ---- transformer (STE.swift:571-590; full causal mask STE.swift:1038-1042; no input / output projection at 512 == d_model) ----
+  const float scale = 1.0f / std::sqrt((float)hd);
+  for (const EncLayer& Ly : m.layers) {
+    launch_layernorm(F(o_hs), Ly.n1w, Ly.n1b, 1e-5f, F(o_nb), gT, H, s); ++m.launches;
+    { ConvGemmParams e{}; e.out_y = F(o_qkv); e.ldy = QW; e.y_bstride = PT * QW; run_gemm(m, Ly.qkv, gT, F(o_nb), H, PT * H, e); }
+    launch_rope(F(o_qkv), QW, nh + nkv, hd, m.inv_freq, gT, s); ++m.launches;
+    launch_attention(F(o_qkv), DT_F32, F(o_ao), DT_F32, gT, nh, nkv, hd, scale, (int)PT + 1, s); ++m.launches;
+    {
+      ConvGemmParams e{};
+      e.res = F(o_hs); e.ldres = H; e.res_bstride = PT * H; e.scale = Ly.ls1;
+      e.out_y = F(o_hs); e.ldy = H; e.y_bstride = PT * H;
+      run_gemm(m, Ly.o, gT, F(o_ao), H, PT * H, e);
+    }
+    launch_layernorm(F(o_hs), Ly.n2w, Ly.n2b, 1e-5f, F(o_nb), gT, H, s); ++m.launches;
+    { ConvGemmParams e{}; e.act = ACT_GELU_TANH; e.out_y = F(o_ff); e.ldy = I; e.y_bstride = PT * I; run_gemm(m, Ly.fc1, gT, F(o_nb), H, PT * H, e); }
+    {
+      ConvGemmParams e{};
+      e.res = F(o_hs); e.ldres = H; e.res_bstride = PT * H; e.scale = Ly.ls2;
+      e.out_y = F(o_hs); e.ldy = H; e.y_bstride = PT * H;
+      run_gemm(m, Ly.fc2, gT, F(o_ff), I, PT * I, e);
+    }
+  }
+  m.tap_index["transformer"] = EncTap{o_hs, PT, LT, H};
+
+  // ---- downsample to the code rate (STE.swift:684-705), then the split residual quantizer (STE.swift:816-829, 934-941) ----
+  const BatchGeom gQ = geom(Tq, nst + 1);
+  { ConvGemmParams e{}; e.out_y = F(o_d); e.ldy = H; e.y_bstride = Tq * H; run_gemm(m, m.downsample, gQ, F(o_hs), ds * H, PT * H, e); }
+  m.tap_index["downsample"] = EncTap{o_d, Tq, Tq, H};
+  const size_t o_res[2] = {o_r0, o_r1};
+  for (int part = 0; part < 2; ++part) {
+    ConvGemmParams e{};
+    e.out_y = F(o_res[part]); e.ldy = CB; e.y_bstride = Tq * CB;
+    run_gemm(m, m.proj[part], gQ, F(o_d), H, Tq * H, e);
+  }
+  int32_t* d_codes = (int32_t*)(base + o_codes);
+  for (size_t q = 0; q < m.books.size(); ++q) {
+    const EncBook& bk = m.books[q];
+    { ConvGemmParams e{}; e.out_y = F(o_sc); e.ldy = K; e.y_bstride = Tq * K; run_gemm(m, bk.score, gQ, F(o_res[bk.part]), CB, Tq * CB, e); }
+    launch_vq_select(F(o_sc), K, bk.score.w, CB, F(o_res[bk.part]), d_codes + (int64_t)q * Tq, (int64_t)NQ * Tq, gQ, s);
+    ++m.launches;
+  }
+  ENC_CUDA_OK(cudaMemcpyAsync(codes_out, d_codes, sizeof(int32_t) * rowsQ * (size_t)NQ, cudaMemcpyDeviceToHost, s));
+  ENC_CUDA_OK(cudaStreamSynchronize(s));
+  ENC_CUDA_OK(cudaGetLastError());
+  m.last_B = B;
+}
+
+void encoder_tap(EncoderModel& m, const std::string& name, float* out, int64_t cap, int64_t dims[3]) {
+  std::lock_guard<std::mutex> lock(m.mu);
+  auto it = m.tap_index.find(name);
+  if (it == m.tap_index.end() || !m.arena || m.last_B < 1) throw Error(Q3TTS_EINVAL, "encoder tap '" + name + "' is not available (enable taps, then encode)");
+  const EncTap& t = it->second;
+  dims[0] = m.last_B; dims[1] = t.valid_rows; dims[2] = t.C;
+  if (!out) return;
+  if (cap < dims[0] * dims[1] * dims[2]) throw Error(Q3TTS_EINVAL, "encoder tap: output buffer too small");
+  ENC_CUDA_OK(cudaSetDevice(m.device));
+  ENC_CUDA_OK(cudaMemcpy2DAsync(out, sizeof(float) * (size_t)t.valid_rows * (size_t)t.C, (const char*)m.arena + t.offset,
+                                sizeof(float) * (size_t)t.slot_rows * (size_t)t.C, sizeof(float) * (size_t)t.valid_rows * (size_t)t.C,
+                                (size_t)m.last_B, cudaMemcpyDeviceToHost, m.stream));
+  ENC_CUDA_OK(cudaStreamSynchronize(m.stream));
+}
+
+}  // namespace q3

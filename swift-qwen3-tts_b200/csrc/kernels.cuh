@@ -10,7 +10,7 @@
 
 namespace q3 {
 
-enum ActKind : int { ACT_NONE = 0, ACT_GELU = 1, ACT_SWIGLU = 2 };
+enum ActKind : int { ACT_NONE = 0, ACT_GELU = 1, ACT_SWIGLU = 2, ACT_GELU_TANH = 3 };   // GELU_TANH: the encoder's geluApprox (STE.swift:1080-1082), CUDA-core engine only
 enum DType : int { DT_F32 = 0, DT_F16 = 1, DT_BF16 = 2 };
 
 // Batch geometry shared by every kernel of one launch chain (one micro-batch).
@@ -53,6 +53,7 @@ struct ConvGemmParams {
   const float* snake_ea;                          // [N] exp(alpha) or null: out_a = v + snake_ib*sin^2(v*ea)
   const float* snake_ib;                          // [N] 1/(exp(beta)+1e-9)
   void* out_tap;  int ldt; int64_t tap_bstride;   // optional fp32 copy of v (pre-snake) for stage taps
+  int a_elu;                                      // CUDA-core engine only: out_a = elu(v) (the encoder's pre-activation, STE.swift:1075-1077)
 };
 
 // ---- CUDA-core GEMM: the fp32 parity engine, and the 16-bit fallback for shapes tcgen05 skips ----
@@ -83,6 +84,20 @@ void launch_dwconv_ln(const float* x, const float* w7 /*[7][C]*/, const float* w
 // Attention over one utterance's frames.  qkv: [B*Tmax, (nh+2*nkv)*hd] (q | k | v), out [B*Tmax, nh*hd].
 void launch_attention(const void* qkv, int qkv_dtype, void* out, int out_dtype, const BatchGeom& g, int nh,
                       int nkv, int hd, float scale, int causal_window /*0 = full*/, cudaStream_t s);
+
+// ---- speech-tokenizer ENCODER (row N3), fp32, kernels_enc.cu --------------------------------------------------------------
+// First conv of the Seanet encoder: 1 -> C channels, k taps, causal (STE.swift:405-415): y = x' (stream), a = elu(x') (operand).
+void launch_enc_init_conv(const float* audio, int64_t audio_bstride, const float* w /*[k][C]*/, const float* bias, int k, int C,
+                          float* out_y, float* out_a, int64_t out_bstride, const BatchGeom& g, cudaStream_t s);
+// LayerNorm over C (biased variance, eps inside the sqrt, affine), one warp per valid row of [B, Tmax, C]
+void launch_layernorm(const float* x, const float* w, const float* b, float eps, float* out, const BatchGeom& g, int C, cudaStream_t s);
+// MLX RoPE(dimensions = hd, traditional = false): pairs (i, i + hd/2) of the first `heads` heads of every valid row of
+// qkv [B, Tmax, ld], angle = t * inv_freq[i] (inv_freq [hd/2], host-computed), position t = row index in the utterance
+void launch_rope(float* qkv, int ld, int heads, int hd, const float* inv_freq, const BatchGeom& g, cudaStream_t s);
+// One layer of EncoderResidualVectorQuantization.encode (STE.swift:816-829) after the GEMM score = x E^T - c2:
+// idx = first argmax of score[row, :K]; codes[b*code_bstride + t] = idx; resid[row, :D] -= E[idx, :D]
+void launch_vq_select(const float* score, int K, const float* E, int D, float* resid, int32_t* codes, int64_t code_bstride,
+                      const BatchGeom& g, cudaStream_t s);
 
 // Tensor-core (mma.sync) flash-style attention for 16-bit operands, head_dim 64 (kernels_attn.cu).
 bool attention_mma_supported(int dtype, int hd);

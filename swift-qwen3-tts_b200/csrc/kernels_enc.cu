@@ -1,0 +1,131 @@
+// Row kernels of the speech-tokenizer ENCODER (reference: Sources/Qwen3TTS/Models/SpeechTokenizerEncoder.swift,
+// "STE.swift").  fp32 throughout: the reference evaluates the nearest-codebook search in float32 on purpose (STE.swift:750-757), and
+// a code is an argmin -- there is no "close enough".  The convolutions / linears run on the CUDA-core multi-tap GEMM of
+// kernels_f32.cu (a strided conv with k = 2s is a 2-tap GEMM on the input viewed as [frames, s * Cin]); what is here is the rest.
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include "kernels.cuh"
+
+namespace q3 {
+namespace {
+
+__device__ __forceinline__ float elu1(float v) { return v > 0.f ? v : expf(v) - 1.0f; }
+
+// y[b, t, c] = bias[c] + sum_j w[j][c] * x[b, t - (k-1) + j]   (zeros before the utterance); one thread per (t, c), c fastest
+__global__ void __launch_bounds__(256)
+enc_init_conv_kernel(const float* __restrict__ audio, int64_t audio_bstride, const float* __restrict__ w, const float* __restrict__ bias, int k,
+                     int C, float* __restrict__ out_y, float* __restrict__ out_a, int64_t out_bstride, BatchGeom g) {
+  const int b = blockIdx.y;
+  const int len = g.len_frames[b];
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t t = i / C;
+  const int c = (int)(i - t * C);
+  if (t >= len) return;
+  const float* x = audio + (int64_t)b * audio_bstride;
+  float acc = bias[c];
+  for (int j = 0; j < k; ++j) {
+    const int64_t src = t - (k - 1) + j;
+    if (src >= 0) acc = fmaf(w[j * C + c], x[src], acc);
+  }
+  const int64_t o = (int64_t)b * out_bstride + t * C + c;
+  out_y[o] = acc;
+  out_a[o] = elu1(acc);
+}
+
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bs, float eps, float* __restrict__ out, BatchGeom g,
+                 int C) {
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= (int64_t)g.B * g.Tmax) return;
+  const int b = (int)(row / g.Tmax), t = (int)(row % g.Tmax);
+  if (t >= g.len_frames[b]) return;
+  const float* xr = x + row * C;
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s += xr[c];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / (float)C;
+  float v = 0.f;
+  for (int c = lane; c < C; c += 32) { const float d = xr[c] - mean; v = fmaf(d, d, v); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const float r = rsqrtf(v / (float)C + eps);
+  for (int c = lane; c < C; c += 32) out[row * C + c] = (xr[c] - mean) * r * w[c] + bs[c];
+}
+
+// one thread per (row, head, i < hd/2)
+__global__ void __launch_bounds__(256)
+rope_kernel(float* __restrict__ qkv, int ld, int heads, int hd, const float* __restrict__ inv_freq, BatchGeom g) {
+  const int half = hd >> 1;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int per_row = heads * half;
+  const int64_t row = i / per_row;
+  if (row >= (int64_t)g.B * g.Tmax) return;
+  const int b = (int)(row / g.Tmax), t = (int)(row % g.Tmax);
+  if (t >= g.len_frames[b]) return;
+  const int r = (int)(i - row * per_row), h = r / half, j = r - h * half;
+  float* p = qkv + row * ld + h * hd;
+  float sn, cs;
+  sincosf((float)t * inv_freq[j], &sn, &cs);
+  const float x1 = p[j], x2 = p[j + half];
+  p[j] = x1 * cs - x2 * sn;
+  p[j + half] = x1 * sn + x2 * cs;
+}
+
+// one warp per valid row: first index of the maximum (== the reference's argMin of c2 - x.E^T: IEEE negation is exact), then the
+// residual update in float32 (STE.swift:824-826)
+__global__ void __launch_bounds__(256)
+vq_select_kernel(const float* __restrict__ score, int K, const float* __restrict__ E, int D, float* __restrict__ resid, int32_t* __restrict__ codes,
+                 int64_t code_bstride, BatchGeom g) {
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= (int64_t)g.B * g.Tmax) return;
+  const int b = (int)(row / g.Tmax), t = (int)(row % g.Tmax);
+  if (t >= g.len_frames[b]) return;
+  const float* sr = score + row * K;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int c = lane; c < K; c += 32) {
+    const float v = sr[c];
+    if (v > best) { best = v; bi = c; }          // ascending c per lane: keeps the lane's first maximum
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+  }
+  if (bi == 0x7fffffff) bi = 0;                  // a row of NaNs: argMin would also return an index, keep the decode defined
+  if (lane == 0) codes[(int64_t)b * code_bstride + t] = bi;
+  const float* e = E + (int64_t)bi * D;
+  float* rr = resid + row * D;
+  for (int c = lane; c < D; c += 32) rr[c] = rr[c] - e[c];
+}
+}  // namespace
+
+void launch_enc_init_conv(const float* audio, int64_t audio_bstride, const float* w, const float* bias, int k, int C, float* out_y,
+                          float* out_a, int64_t out_bstride, const BatchGeom& g, cudaStream_t s) {
+  const int64_t n = (int64_t)g.Tmax * C;
+  dim3 grid((unsigned)((n + 255) / 256), (unsigned)g.B);
+  enc_init_conv_kernel<<<grid, 256, 0, s>>>(audio, audio_bstride, w, bias, k, C, out_y, out_a, out_bstride, g);
+}
+
+void launch_layernorm(const float* x, const float* w, const float* b, float eps, float* out, const BatchGeom& g, int C, cudaStream_t s) {
+  const int64_t rows = (int64_t)g.B * g.Tmax;
+  layernorm_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, s>>>(x, w, b, eps, out, g, C);
+}
+
+void launch_rope(float* qkv, int ld, int heads, int hd, const float* inv_freq, const BatchGeom& g, cudaStream_t s) {
+  const int64_t n = (int64_t)g.B * g.Tmax * heads * (hd / 2);
+  rope_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(qkv, ld, heads, hd, inv_freq, g);
+}
+
+void launch_vq_select(const float* score, int K, const float* E, int D, float* resid, int32_t* codes, int64_t code_bstride,
+                      const BatchGeom& g, cudaStream_t s) {
+  const int64_t rows = (int64_t)g.B * g.Tmax;
+  vq_select_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, s>>>(score, K, E, D, resid, codes, code_bstride, g);
+}
+
+}  // namespace q3

@@ -164,6 +164,7 @@ conv_gemm_simt_kernel(ConvGemmParams p, BatchGeom g, int tiles_per_utt) {
       float v = acc[i][j];
       if (p.bias) v += p.bias[n];
       if (p.act == ACT_GELU) v = gelu_exact(v);
+      else if (p.act == ACT_GELU_TANH) v = v * 0.5f * (1.0f + tanhf(0.7978845608f * (v + 0.044715f * (v * v * v))));
       if (p.res) {
         const float r = ldf((const TS*)p.res, (int64_t)b * p.res_bstride + (int64_t)t * p.ldres + n);
         v = r + (p.scale ? p.scale[n] * v : v);
@@ -171,7 +172,7 @@ conv_gemm_simt_kernel(ConvGemmParams p, BatchGeom g, int tiles_per_utt) {
       if (p.out_y) stf((TS*)p.out_y, (int64_t)b * p.y_bstride + (int64_t)t * p.ldy + n, v);
       if (p.out_tap) ((float*)p.out_tap)[(int64_t)b * p.tap_bstride + (int64_t)t * p.ldt + n] = v;
       if (p.out_a) {
-        const float a = p.snake_ea ? snake_f(v, p.snake_ea[n], p.snake_ib[n]) : v;
+        const float a = p.snake_ea ? snake_f(v, p.snake_ea[n], p.snake_ib[n]) : (p.a_elu ? (v > 0.f ? v : expf(v) - 1.0f) : v);
         stf((TA*)p.out_a, (int64_t)b * p.ao_bstride + (int64_t)t * p.lda_out + n, a);
       }
     }

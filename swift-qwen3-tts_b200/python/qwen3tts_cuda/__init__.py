@@ -145,6 +145,13 @@ def lib() -> C.CDLL:
         "q3tts_pool_decode_varlen_int16": (C.c_int, [vp, vp, vp, i32, vp, vp]),
         "q3tts_pool_decode": (C.c_int, [vp, vp, i32, i32, i32, vp, vp]),
         "q3tts_pool_last_stats": (C.c_int, [vp, vp, vp, i32]),
+        "q3tts_encoder_load": (C.c_int, [cp, C.POINTER(Options), C.POINTER(vp)]),
+        "q3tts_encoder_free": (None, [vp]),
+        "q3tts_encoder_info": (C.c_int, [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i64)]),
+        "q3tts_encode_frames": (i64, [vp, i64]),
+        "q3tts_encode": (C.c_int, [vp, vp, i32, i64, vp]),
+        "q3tts_encoder_set_taps": (C.c_int, [vp, i32]),
+        "q3tts_encoder_tap": (C.c_int, [vp, cp, vp, i64, C.POINTER(i64 * 3)]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(L, name)
@@ -247,6 +254,60 @@ class CodecEmbedder:
     def close(self) -> None:
         if self._h:
             lib().q3tts_codec_embedder_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Qwen3TTSSpeechTokenizerEncoder:
+    """Speech-tokenizer encoder, audio -> codes (SpeechTokenizerEncoder.swift:955-1056): same name and `encode` shapes as the
+    reference -- audio [B, 1, samples] float -> codes [B, 16, T] int32 at 12.5 frames per second."""
+
+    def __init__(self, speech_tokenizer_dir: str, device: int = 0):
+        opts = Options()
+        lib().q3tts_options_default(C.byref(opts))
+        opts.device = device
+        h = C.c_void_p()
+        _check(lib().q3tts_encoder_load(speech_tokenizer_dir.encode(), C.byref(opts), C.byref(h)))
+        self._h = h
+        nq, cb, hop, sr, npar = C.c_int32(0), C.c_int32(0), C.c_int32(0), C.c_int32(0), C.c_int64(0)
+        _check(lib().q3tts_encoder_info(self._h, C.byref(nq), C.byref(cb), C.byref(hop), C.byref(sr), C.byref(npar)))
+        self.valid_num_quantizers, self.codebook_size, self.hop = int(nq.value), int(cb.value), int(hop.value)
+        self.sampling_rate, self.num_parameters = int(sr.value), int(npar.value)
+
+    def frames(self, samples: int) -> int:
+        return int(lib().q3tts_encode_frames(self._h, samples))
+
+    def encode(self, audio: np.ndarray) -> np.ndarray:
+        a = np.ascontiguousarray(audio, dtype=np.float32)
+        if a.ndim == 3 and a.shape[1] == 1:
+            a = a[:, 0, :]
+        if a.ndim != 2:
+            raise AudioDecodingFailed(1, f"audio must be [B, 1, samples] or [B, samples], got {audio.shape}")
+        a = np.ascontiguousarray(a)
+        B, S = a.shape
+        codes = np.empty((B, self.valid_num_quantizers, self.frames(S)), dtype=np.int32)
+        _check(lib().q3tts_encode(self._h, a.ctypes.data, B, S, codes.ctypes.data))
+        return codes
+
+    def set_taps(self, on: bool) -> None:
+        _check(lib().q3tts_encoder_set_taps(self._h, 1 if on else 0))
+
+    def stage_tap(self, name: str) -> np.ndarray:
+        """Stage output of the last encode as [B, C, rows] (the reference's NCL layout)."""
+        dims = (C.c_int64 * 3)()
+        _check(lib().q3tts_encoder_tap(self._h, name.encode(), None, 0, C.byref(dims)))
+        out = np.empty((dims[0], dims[1], dims[2]), dtype=np.float32)
+        _check(lib().q3tts_encoder_tap(self._h, name.encode(), out.ctypes.data, out.size, C.byref(dims)))
+        return np.ascontiguousarray(np.transpose(out, (0, 2, 1)))
+
+    def close(self) -> None:
+        if self._h:
+            lib().q3tts_encoder_free(self._h)
             self._h = None
 
     def __del__(self):

@@ -128,8 +128,8 @@ class EncoderConfig:
     @classmethod
     def tiny(cls) -> "EncoderConfig":
         """Same topology, small widths, for CPU tests (total stride 2*2*3*2 * 2 = 48 samples per code frame)."""
-        return cls(codebook_dim=16, codebook_size=32, head_dim=8, hidden_size=32, intermediate_size=64, num_attention_heads=4,
-                   num_key_value_heads=4, num_filters=4, num_hidden_layers=2, num_quantizers=20, upsampling_ratios=[2, 3, 2, 2],
+        return cls(codebook_dim=16, codebook_size=32, head_dim=32, hidden_size=64, intermediate_size=128, num_attention_heads=2,
+                   num_key_value_heads=2, num_filters=8, num_hidden_layers=2, num_quantizers=20, upsampling_ratios=[2, 3, 2, 2],
                    sampling_rate=24000, frame_rate=500.0)
 
 
