@@ -129,9 +129,40 @@ def cpu_baseline_block(dec, cfg, synth_codes):
     return out
 
 
+def reference_arm_encode(args, W, K):
+    """--impl reference --workload encode: the CPU restatement of the reference ENCODER, one 10 s utterance per step."""
+    from oracle import encoder as oe
+    from tools.fixtures import checkpoint_dir
+    from tools.q3cfg import DecoderConfig, EncoderConfig
+    from tools.synth_checkpoint import synth_audio
+    ec = EncoderConfig()
+    d = os.path.join(checkpoint_dir(DecoderConfig.tiny(), seed=7, encoder_cfg=ec), "speech_tokenizer")
+    cfg_o, w_o = oe.load_encoder(d)
+    torch.set_num_threads(os.cpu_count() or 1)
+    orc = oe.OracleEncoder(cfg_o, w_o, torch.float32)
+    one = synth_audio(1, 10 * ec.sampling_rate, 2000)
+    for _ in range(W):
+        orc.encode(one)
+    t0 = time.perf_counter()
+    for _ in range(K):
+        orc.encode(one)
+    dt = time.perf_counter() - t0
+    val = K * 10.0 / dt
+    what = "one utterance of 10 s of 24 kHz audio, B=1, per step"
+    return {"impl": "reference", "metric": "encoded audio-seconds per second (speech-tokenizer encoder, audio -> 16 x 12.5 Hz codes)", "value": val,
+            "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": 1e3 * dt / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "speech-tokenizer encoder, 10 s utterances", "sample_per_step": what,
+                       "note": "CPU restatement of the reference encoder (torch-CPU fp32 oracle, all host threads); Swift + MLX cannot be built in this image."},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": what},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
 def reference_arm(args, cfg, W, K, workload_name):
     from tools.fixtures import checkpoint_dir
     from tools.synth_checkpoint import synth_codes
+    if workload_name == "encode":
+        return reference_arm_encode(args, W, K)
     lite = workload_name == "config4"
     st_dir = os.path.join(checkpoint_dir(cfg, dtype="float16" if lite else "float32"), "speech_tokenizer")
     dec = oracle_decoder(st_dir, "causal_sw" if workload_name == "config5" else "reference")
@@ -447,6 +478,84 @@ def run_config4(cx, q, cfg, prec, W, K):
     return out
 
 
+ENC_FLOP_PER_AUDIO_S = None
+
+
+def encoder_flops_per_audio_second(ec):
+    """Algorithmic FLOPs (2 x MAC) of Qwen3TTSSpeechTokenizerEncoder.encode per second of 24 kHz audio (STE.swift:396-443, 545-591,
+    684-705, 816-829), attention excluded (it depends on the utterance length)."""
+    rate = float(ec.sampling_rate)
+    nf, fl = ec.num_filters, 0.0
+    fl += rate * nf * ec.kernel_size * 2
+    mult = 1
+    for r in reversed(ec.upsampling_ratios):
+        dim, hid = mult * nf, mult * nf // ec.compress
+        fl += rate * (dim * hid * ec.residual_kernel_size + hid * dim) * 2
+        rate /= r
+        fl += rate * (2 * dim) * dim * (2 * r) * 2
+        mult *= 2
+    H, I = ec.hidden_size, ec.intermediate_size
+    fl += rate * H * (mult * nf) * ec.last_kernel_size * 2
+    fl += rate * ec.num_hidden_layers * (4 * H * H + 2 * H * I) * 2
+    ds = ec.downsample_stride
+    rate /= ds
+    fl += rate * H * H * (2 * ds) * 2
+    fl += rate * (2 * ec.codebook_dim * H + 16 * ec.codebook_size * ec.codebook_dim) * 2
+    return fl
+
+
+def run_encode(cx, q, W, K, B=64, seconds=10.0, cpu_baseline=True):
+    """the speech-tokenizer ENCODER (audio -> codes).  One step = one q3tts_encode of B utterances of `seconds`
+    seconds per GPU, host audio in -> host codes out (the only form of the call: value == e2e).  Every rank encodes its own batch."""
+    from tools.fixtures import checkpoint_dir
+    from tools.q3cfg import DecoderConfig, EncoderConfig
+    from tools.synth_checkpoint import synth_audio
+    ec = EncoderConfig()
+    if cx.rank == 0:
+        checkpoint_dir(DecoderConfig.tiny(), seed=7, encoder_cfg=ec)
+    cx.barrier()
+    d = os.path.join(checkpoint_dir(DecoderConfig.tiny(), seed=7, encoder_cfg=ec), "speech_tokenizer")
+    enc = q.Qwen3TTSSpeechTokenizerEncoder(d, device=cx.local_rank)
+    samples = int(seconds * ec.sampling_rate)
+    audio = synth_audio(B, samples, 2000 + cx.rank)
+    out = {}
+
+    def step():
+        out["codes"] = enc.encode(audio)
+
+    dt = cx.timed_host(step, W, K)
+    audio_s = B * seconds * cx.world
+    fl = encoder_flops_per_audio_second(ec)
+    res = {"metric": "encoded audio-seconds per second (speech-tokenizer encoder, audio -> 16 x 12.5 Hz codes)", "value": audio_s * K / dt,
+           "unit": UNIT, "ms_per_step": dt / K * 1e3, "steps": K, "scaling": "weak", "dtype": "f32",
+           "workload": f"{B} utterances x {seconds:.0f} s of 24 kHz audio per GPU, host audio in -> host codes out, synthetic weights of the default "
+                       f"encoder architecture ({enc.num_parameters / 1e6:.1f} M parameters read by encode)",
+           "e2e": {"value": audio_s * K / dt, "unit": UNIT, "h2d_bytes_per_step": int(audio.nbytes), "d2h_bytes_per_step": int(out["codes"].nbytes)},
+           "gflop_per_audio_s": fl / 1e9,
+           "roofline": {"bound": "fp32 CUDA cores", "achieved": fl * audio_s / cx.world * K / dt / 1e12, "peak": 74.4, "unit": "TFLOP/s",
+                        "frac": fl * audio_s / cx.world * K / dt / 1e12 / 74.4,
+                        "peak_kind": "nominal fp32 FMA rate (148 SMs x 128 lanes x 2 x 1.965 GHz); whole call, copies included",
+                        "traffic": None}}
+    if cpu_baseline and cx.rank == 0:
+        import torch as _t
+        from oracle import encoder as oe
+        cfg_o, w_o = oe.load_encoder(d)
+        orc = oe.OracleEncoder(cfg_o, w_o, _t.float32)
+        _t.set_num_threads(os.cpu_count() or 1)
+        one = audio[:1]
+        orc.encode(one)
+        ts = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            ref = orc.encode(one).numpy()
+            ts.append(time.perf_counter() - t0)
+        res["cpu_baseline"] = {"value": seconds / float(np.median(ts)), "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+                               "sample": f"one utterance of {seconds:.0f} s, median of 3, torch-CPU fp32 restatement of the reference encoder (oracle/encoder.py)"}
+        res["codes_equal_to_cpu_restatement"] = float((ref == out["codes"][:1]).mean())
+    enc.close()
+    return res
+
+
 def run_config5(cx, q, cfg, st_dir, prec, n_chunks=C5_CHUNKS, streams_per_gpu=C5_STREAMS):
     """Chunked streaming: one step = one batched push (host codes in -> host PCM out) of every stream of this GPU."""
     from tools.synth_checkpoint import synth_codes
@@ -500,7 +609,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16", "fp32"])
-    ap.add_argument("--workload", default=os.environ.get("Q3TTS_BENCH_WORKLOAD", "config2"), choices=["config2", "config3", "config4", "config5"])
+    ap.add_argument("--workload", default=os.environ.get("Q3TTS_BENCH_WORKLOAD", "config2"), choices=["config2", "config3", "config4", "config5", "encode"])
     ap.add_argument("--batch", type=int, default=B_PER_GPU)
     ap.add_argument("--frames", type=int, default=T_FRAMES)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -556,11 +665,22 @@ def main():
                 other["config2_bf16"] = {"value": l2["value"], "unit": UNIT, "ms_per_step": l2["ms_per_step"], "e2e": l2["e2e"], "dtype": "bf16",
                                          "note": "bf16 operands reach 25-27 dB SNR on this decoder (fp16: 44 dB; tests/test_oracle.py, "
                                                  "tests/test_gpu_parity.py), so the headline mode is fp16 at the same tensor-core rate"}
+            other["encode"] = run_encode(cx, q, 1, 2, cpu_baseline=cx.world == 1 and not args.no_cpu_baseline)   # row N3, not a BASELINE config
             line["other_configs"] = other
         if tok is not None:
             tok.close()
         if cx.rank == 0 and cx.world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_block(oracle_decoder(st_dir), cfg, synth_codes)
+    elif args.workload == "encode":
+        r = run_encode(cx, q, W, K, cpu_baseline=cx.world == 1 and not args.no_cpu_baseline)
+        line = {"metric": r.pop("metric"), "value": r.pop("value"), "unit": UNIT, "n_gpus": cx.world, "steps": K, "warmup": W,
+                "ms_per_step": r.pop("ms_per_step"), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": {"workload": r.pop("workload"), "parallelism": f"x{cx.world} independent batches, no collective"},
+                "gpu_launches": 113 * K, "e2e": r.pop("e2e"), "roofline": r.pop("roofline")}
+        if "cpu_baseline" in r:
+            line["cpu_baseline"] = r.pop("cpu_baseline")
+        r.pop("steps", None); r.pop("scaling", None); r.pop("dtype", None)
+        line.update(r)
     else:
         if args.workload == "config3":
             r = run_config3(cx, q, cfg, st_dir, prec, W, K, with_roofline=True)

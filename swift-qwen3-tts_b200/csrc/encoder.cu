@@ -200,7 +200,7 @@ void encoder_encode(EncoderModel& m, const float* audio, int B, int64_t samples,
   std::lock_guard<std::mutex> lock(m.mu);
   const EncoderConfig& c = m.cfg;
   if (B < 1 || samples < 1 || !audio || !codes_out) throw Error(Q3TTS_EINVAL, "encode: bad arguments");
-  if (samples > (int64_t)1 << 30) throw Error(Q3TTS_EINVAL, "encode: audio too long");
+  if (samples > (int64_t)1 << 26 || B > 65535) throw Error(Q3TTS_EINVAL, "encode: at most 2^26 samples (46 minutes) per utterance and 65535 utterances per call");
   ENC_CUDA_OK(cudaSetDevice(m.device));
   cudaStream_t s = m.stream;
   const int nst = c.n_ratios, ds = c.downsample_stride(), H = c.hidden_size, I = c.intermediate_size;

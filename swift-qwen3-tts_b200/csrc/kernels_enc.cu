@@ -16,21 +16,27 @@ __device__ __forceinline__ float elu1(float v) { return v > 0.f ? v : expf(v) - 
 __global__ void __launch_bounds__(256)
 enc_init_conv_kernel(const float* __restrict__ audio, int64_t audio_bstride, const float* __restrict__ w, const float* __restrict__ bias, int k,
                      int C, float* __restrict__ out_y, float* __restrict__ out_a, int64_t out_bstride, BatchGeom g) {
+  // one thread per (sample, group of 4 channels): 16-byte stores, 32-bit index arithmetic (the host checks Tmax * C < 2^31)
   const int b = blockIdx.y;
   const int len = g.len_frames[b];
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t t = i / C;
-  const int c = (int)(i - t * C);
+  const int c4n = C >> 2;
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = (int)(i / (unsigned)c4n);
+  const int c = (int)(i - (unsigned)t * (unsigned)c4n) * 4;
   if (t >= len) return;
   const float* x = audio + (int64_t)b * audio_bstride;
-  float acc = bias[c];
+  float4 acc = *(const float4*)(bias + c);
   for (int j = 0; j < k; ++j) {
-    const int64_t src = t - (k - 1) + j;
-    if (src >= 0) acc = fmaf(w[j * C + c], x[src], acc);
+    const int src = t - (k - 1) + j;
+    if (src >= 0) {
+      const float xv = x[src];
+      const float4 wv = *(const float4*)(w + j * C + c);
+      acc.x = fmaf(wv.x, xv, acc.x); acc.y = fmaf(wv.y, xv, acc.y); acc.z = fmaf(wv.z, xv, acc.z); acc.w = fmaf(wv.w, xv, acc.w);
+    }
   }
-  const int64_t o = (int64_t)b * out_bstride + t * C + c;
-  out_y[o] = acc;
-  out_a[o] = elu1(acc);
+  const int64_t o = (int64_t)b * out_bstride + (int64_t)t * C + c;
+  *(float4*)(out_y + o) = acc;
+  *(float4*)(out_a + o) = make_float4(elu1(acc.x), elu1(acc.y), elu1(acc.z), elu1(acc.w));
 }
 
 __global__ void __launch_bounds__(256)
@@ -107,7 +113,7 @@ vq_select_kernel(const float* __restrict__ score, int K, const float* __restrict
 
 void launch_enc_init_conv(const float* audio, int64_t audio_bstride, const float* w, const float* bias, int k, int C, float* out_y,
                           float* out_a, int64_t out_bstride, const BatchGeom& g, cudaStream_t s) {
-  const int64_t n = (int64_t)g.Tmax * C;
+  const int64_t n = (int64_t)g.Tmax * (C / 4);
   dim3 grid((unsigned)((n + 255) / 256), (unsigned)g.B);
   enc_init_conv_kernel<<<grid, 256, 0, s>>>(audio, audio_bstride, w, bias, k, C, out_y, out_a, out_bstride, g);
 }

@@ -27,6 +27,13 @@ int main(int argc, char** argv) {
       q3::load_codec_embeddings(argv[i], &t);
     } catch (const q3::Error&) {
     }
+    try {   // ... and so does the encoder reader (row N3): key remap, forced transposes, strict shape table
+      q3::EncoderCheckpoint e;
+      q3::load_encoder_checkpoint(argv[i], &e);
+      std::printf("%s: encoder OK, %lld parameters\n", argv[i], (long long)e.num_parameters);
+    } catch (const q3::Error& e) {
+      std::printf("%s: encoder: %s\n", argv[i], e.what());
+    }
   }
   // host-only entry points on edge cases
   {

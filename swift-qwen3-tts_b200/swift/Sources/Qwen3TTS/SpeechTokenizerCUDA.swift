@@ -114,7 +114,7 @@ public final class Qwen3TTSSpeechTokenizer {
 
     deinit { q3tts_model_free(handle) }
 
-    /// The CUDA path is decode-only (the encoder stays on the reference implementation).
+    /// The encoder is a separate handle (`Qwen3TTSSpeechTokenizerEncoder`): a decode-only deployment never loads its weights.
     public var hasEncoder: Bool { false }                      // SpeechTokenizer.swift:816
 
     /// Decode codes to audio
@@ -184,6 +184,45 @@ public final class Qwen3TTSSpeechTokenizer {
 /// Codec-embedding sum for the Talker's next-step input (Qwen3.swift:720-728; 485-491 for the voice-cloning prefix):
 /// `talker.getInputEmbeddings()(code0) + codePredictor.codecEmbedding[0](code1) + ...`, left to right in the checkpoint's
 /// dtype, for `n` frames in one launch.  `modelDir` holds the main checkpoint's safetensors.
+/// Speech-tokenizer encoder: audio -> codes (SpeechTokenizerEncoder.swift:955-1056), for voice cloning (Qwen3.swift:430-440).
+/// Same method name and shapes as the reference: `encode([batch, 1, samples]) -> [batch, 16, time]`.
+public final class Qwen3TTSSpeechTokenizerEncoder {
+    let handle: OpaquePointer
+    public let validNumQuantizers: Int                          // SpeechTokenizerEncoder.swift:957
+
+    /// `speechTokenizerDir` must hold an `encoder_config` and the `encoder.*` tensors; a "lite" checkpoint throws
+    /// (the reference: `Qwen3TTSSpeechTokenizerError.encoderNotAvailable`, SpeechTokenizer.swift:842-844).
+    public init(speechTokenizerDir: URL, device: Int32 = 0) throws {
+        var opts = q3tts_options()
+        q3tts_options_default(&opts)
+        opts.device = device
+        var h: OpaquePointer?
+        try check(q3tts_encoder_load(speechTokenizerDir.path, &opts, &h))
+        guard let enc = h else { throw Qwen3TTSCUDAError.audioDecodingFailed("q3tts_encoder_load returned NULL") }
+        var nq: Int32 = 0
+        try check(q3tts_encoder_info(enc, &nq, nil, nil, nil, nil))
+        self.handle = enc
+        self.validNumQuantizers = Int(nq)
+    }
+
+    deinit { q3tts_encoder_free(handle) }
+
+    /// - Parameter audio: [batch, 1, samples] (or [batch, samples]) 24 kHz waveform
+    /// - Returns: codes [batch, num_quantizers, time]
+    public func encode(_ audio: FloatTensor) throws -> Int32Tensor {
+        precondition(audio.shape.count == 2 || (audio.shape.count == 3 && audio.shape[1] == 1))
+        let (b, samples) = (audio.shape[0], audio.shape[audio.shape.count - 1])
+        let frames = Int(q3tts_encode_frames(handle, Int64(samples)))
+        var codes = [Int32](repeating: 0, count: b * validNumQuantizers * frames)
+        try audio.data.withUnsafeBufferPointer { a in
+            try codes.withUnsafeMutableBufferPointer { c in
+                try check(q3tts_encode(handle, a.baseAddress, Int32(b), Int64(samples), c.baseAddress))
+            }
+        }
+        return Int32Tensor(shape: [b, validNumQuantizers, frames], data: codes)
+    }
+}
+
 public final class Qwen3TTSCodecEmbedder {
     private let handle: OpaquePointer
     public let hiddenSize: Int

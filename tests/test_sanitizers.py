@@ -25,6 +25,8 @@ def harness():
 def test_host_library_is_clean_under_asan_and_ubsan(harness, tiny_cfg, tmp_path):
     good = [os.path.join(checkpoint_dir(tiny_cfg, seed=7, **kw), "speech_tokenizer")
             for kw in (dict(), dict(dtype="float16"), dict(dtype="bfloat16"), dict(with_encoder_stub=True), dict(mlx_layout=True))]
+    from tools.q3cfg import EncoderConfig
+    good.append(os.path.join(checkpoint_dir(tiny_cfg, seed=7, encoder_cfg=EncoderConfig.tiny()), "speech_tokenizer"))   # a real encoder shard
     bad = []
 
     def variant(name):
@@ -63,12 +65,18 @@ def test_host_library_is_clean_under_asan_and_ubsan(harness, tiny_cfg, tmp_path)
     d = variant("negative_dims_config")
     with open(d / "config.json", "w") as f:
         json.dump({"decoder_config": {"latent_dim": -4, "num_quantizers": 100000, "upsample_rates": [0] * 40}}, f)
+    d = tmp_path / "encoder_with_a_truncated_shard"
+    shutil.copytree(good[-1], d)
+    bad_enc = str(d)
+    with open(d / "model-encoder.safetensors", "r+b") as f:
+        f.truncate(os.path.getsize(d / "model-encoder.safetensors") // 3)
     bad.append(str(tmp_path / "does_not_exist"))
     env = dict(os.environ, ASAN_OPTIONS="detect_leaks=1:abort_on_error=0", UBSAN_OPTIONS="print_stacktrace=1",
                Q3TTS_HARNESS_WAV=str(tmp_path / "x.wav"))
-    r = subprocess.run([harness] + good + bad, capture_output=True, text=True, env=env, timeout=600)
+    r = subprocess.run([harness] + good + bad + [bad_enc], capture_output=True, text=True, env=env, timeout=600)
     out = r.stdout + r.stderr
     assert "AddressSanitizer" not in out and "runtime error" not in out and "LeakSanitizer" not in out, out[-4000:]
     assert r.returncode == 0, out[-4000:]
-    assert f"harness: {len(good)} parsed, {len(bad)} rejected" in out, out[-2000:]
+    assert f"harness: {len(good) + 1} parsed, {len(bad)} rejected" in out, out[-2000:]   # the decoder half of bad_enc is intact
+    assert out.count("encoder OK") == 1 and "encoder_with_a_truncated_shard: encoder:" in out, out[-3000:]
     assert os.path.getsize(tmp_path / "x.wav") == 44 + 12
