@@ -134,3 +134,46 @@ def test_pcm_post_processing(tmp_path):
     assert raw[:4] == b"RIFF" and raw[8:16] == b"WAVEfmt " and len(raw) == 44 + 2 * len(pcm)
     assert struct.unpack("<I", raw[24:28])[0] == 24000 and struct.unpack("<H", raw[34:36])[0] == 16
     assert np.frombuffer(raw[44:], dtype="<i2").tolist() == i16.tolist()
+
+
+# ---- row N3: the encoder's checkpoint reader runs before any CUDA call, so its verdicts are visible without a GPU ----
+def _encoder_status(st_dir):
+    """(status, message) of q3tts_encoder_load on this machine: 4 (ECUDA, "no CUDA device") means the checkpoint was accepted."""
+    try:
+        q.Qwen3TTSSpeechTokenizerEncoder(st_dir).close()
+        return 0, ""
+    except q.AudioDecodingFailed as e:
+        return e.status, str(e)
+
+
+def test_encoder_checkpoint_is_read_strictly(tmp_path, tiny_cfg):
+    from safetensors.torch import load_file, save_file
+    from tools.q3cfg import EncoderConfig
+    good = os.path.join(checkpoint_dir(tiny_cfg, seed=7, encoder_cfg=EncoderConfig.tiny()), "speech_tokenizer")
+    st, msg = _encoder_status(good)
+    assert st in (0, 4), msg                                     # accepted (then: no GPU here, or a working encoder)
+    # a decode-only ("lite") checkpoint has no encoder: the reference throws encoderNotAvailable (SpeechTokenizer.swift:842-844)
+    st, msg = _encoder_status(os.path.join(checkpoint_dir(tiny_cfg, seed=7), "speech_tokenizer"))
+    assert st == 3 and "encoder_config" in msg
+    # a missing / misshapen tensor is an error, not a silently random layer (the reference's update(verify: []) accepts it)
+    for victim, mutate in (("encoder.encoder.layers.4.block.3.conv.bias", None),
+                           ("encoder.quantizer.acoustic_residual_vector_quantizer.layers.14.codebook.embed_sum", None),
+                           ("encoder.downsample.conv.weight", lambda t: t[:, :, :2].contiguous())):
+        d = tmp_path / ("enc_" + victim.split(".")[-3] + "_" + victim.split(".")[-1])
+        shutil.copytree(good, d)
+        t = load_file(str(d / "model-encoder.safetensors"))
+        if mutate is None:
+            del t[victim]
+        else:
+            t[victim] = mutate(t[victim])
+        save_file(t, str(d / "model-encoder.safetensors"))
+        st, msg = _encoder_status(str(d))
+        assert st == 3 and "encoder" in msg, (victim, st, msg)
+    # tensors past encoder_valid_num_quantizers are never read: dropping one is fine
+    d = tmp_path / "enc_deep_codebook_dropped"
+    shutil.copytree(good, d)
+    t = load_file(str(d / "model-encoder.safetensors"))
+    del t["encoder.quantizer.acoustic_residual_vector_quantizer.layers.17.codebook.embed_sum"]
+    save_file(t, str(d / "model-encoder.safetensors"))
+    st, msg = _encoder_status(str(d))
+    assert st in (0, 4), msg
