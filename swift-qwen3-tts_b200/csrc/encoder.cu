@@ -91,12 +91,17 @@ EncoderModel* encoder_create(const std::string& dir, const q3tts_options& opts) 
   load_encoder_checkpoint(dir, &ck);
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) throw Error(Q3TTS_ECUDA, "no CUDA device (this library has no CPU path)");
-  if (opts.device < 0 || opts.device >= ndev) throw Error(Q3TTS_EINVAL, "device index out of range");
-  ENC_CUDA_OK(cudaSetDevice(opts.device));
+  int device = opts.device;
+  if (device < 0) ENC_CUDA_OK(cudaGetDevice(&device));                      // -1 = the calling thread's current device, as q3tts_model_load
+  if (device >= ndev) throw Error(Q3TTS_EINVAL, "device index out of range");
+  if (opts.precision != Q3TTS_PREC_FP32 && opts.precision != Q3TTS_PREC_FP16)
+    throw Error(Q3TTS_EINVAL, "encoder precision: Q3TTS_PREC_FP32 (CUDA cores) or Q3TTS_PREC_FP16 (tensor cores, split fp16 operands)");
+  ENC_CUDA_OK(cudaSetDevice(device));
   std::unique_ptr<EncoderModel> mp(new EncoderModel());
   EncoderModel& m = *mp;
   m.cfg = ck.cfg;
-  m.device = opts.device;
+  m.device = device;
+  m.tc = opts.precision == Q3TTS_PREC_FP16;
   m.num_parameters = ck.num_parameters;
   ENC_CUDA_OK(cudaStreamCreateWithFlags(&m.stream, cudaStreamNonBlocking));
   const EncoderConfig& c = m.cfg;
@@ -173,6 +178,23 @@ EncoderModel* encoder_create(const std::string& dir, const q3tts_options& opts) 
       m.books.push_back(bk);
     }
   }
+  if (m.tc) {
+    int maxN = std::max(std::max(c.codebook_size, c.intermediate_size), (c.num_attention_heads + 2 * c.num_key_value_heads) * (c.hidden_size / c.num_attention_heads));
+    for (auto& st : m.stages) maxN = std::max(maxN, 2 * st.dim);
+    m.zeros = upload(m, std::vector<float>((size_t)maxN, 0.f));
+    m.inv_split = upload(m, std::vector<float>((size_t)maxN, 1.0f / kSplitScale));
+    auto split_w = [&](EncGemm& g) {
+      const int64_t n = (int64_t)g.taps * g.N * g.Cin;
+      ENC_CUDA_OK(cudaMalloc(&g.w_hi, (size_t)n * 2)); m.allocs.push_back(g.w_hi);
+      ENC_CUDA_OK(cudaMalloc(&g.w_lo, (size_t)n * 2)); m.allocs.push_back(g.w_lo);
+      launch_split_flat(g.w, g.w_hi, g.w_lo, n, m.stream);
+    };
+    for (auto& st : m.stages) { split_w(st.res3); split_w(st.res1); split_w(st.down); }
+    split_w(m.final_conv); split_w(m.downsample); split_w(m.proj[0]); split_w(m.proj[1]);
+    for (auto& L : m.layers) { split_w(L.qkv); split_w(L.o); split_w(L.fc1); split_w(L.fc2); }
+    for (auto& b : m.books) split_w(b.score);
+    ENC_CUDA_OK(cudaStreamSynchronize(m.stream));
+  }
   return mp.release();
 }
 
@@ -196,8 +218,219 @@ int64_t encoder_frames(const EncoderConfig& c, int64_t samples) {
   return (L + ds - 1) / ds;
 }
 
+namespace {
+// The strided convs read whole strides: rows between a level's valid length and its padded length must be zero (the reference's
+// "extra padding").  No kernel ever writes such a row, so the workspace is cleared once per (batch, length, taps) shape -- not per
+// call: a memset of the 20-35 GB a 64 x 10 s batch touches would cost 7-12 ms -- and again whenever the shape (hence the plan) changes.
+void zero_if_new_shape(EncoderModel& m, char* from, size_t bytes, int B, int64_t samples, cudaStream_t s) {
+  if (m.zeroed_B == B && m.zeroed_samples == samples && m.zeroed_taps == m.taps_enabled) return;
+  ENC_CUDA_OK(cudaMemsetAsync(from, 0, bytes, s));
+  m.zeroed_B = B; m.zeroed_samples = samples; m.zeroed_taps = m.taps_enabled;
+}
+
+// ---- tensor-core engine -------------------------------------------------------------------------------------------------
+// Same graph, but a GEMM is three tcgen05 products of split fp16 operands accumulated in float32 (kernels.cuh: kSplitScale),
+//   Y = b + A_hi.W_hi;  Y += (A_hi.W_lo) / 2048;  Y += (A_lo.W_hi) / 2048
+// through the decoder's multi-tap GEMM (kernels_tc2.cu, fp32 stream output, residual + per-column scale epilogue), and everything
+// element-wise around it (residual, layer scale, elu / GELU, the split of the next operand) is ONE pass of enc_split_kernel.
+// A GEMM the tensor-core kernel does not take (Cin < 64: the first stage's 1x1 conv, the tiny test architecture) runs on the
+// CUDA-core engine from a float32 operand.
+struct Opnd { float* f32 = nullptr; __half* hi = nullptr; __half* lo = nullptr; };
+
+bool tc_takes(const EncoderModel& m, const EncGemm& w) {
+  ConvGemmParams p{};
+  p.N = w.N; p.Cin = w.Cin; p.lda = w.Cin; p.taps = w.taps; p.dil = 1;
+  return m.tc && w.w_hi && tc2_supported(p, DT_F16);
+}
+
+void gemm_y(EncoderModel& m, const EncGemm& w, const BatchGeom& g, const Opnd& a, int lda, int64_t a_bstride, float* Y, int ldy, int64_t y_bstride) {
+  if (!tc_takes(m, w)) {
+    if (!a.f32) throw Error(Q3TTS_EINVAL, "internal: CUDA-core GEMM without a float32 operand");
+    ConvGemmParams e{};
+    e.out_y = Y; e.ldy = ldy; e.y_bstride = y_bstride;
+    run_gemm(m, w, g, a.f32, lda, a_bstride, e);
+    return;
+  }
+  if (!a.hi || !a.lo) throw Error(Q3TTS_EINVAL, "internal: tensor-core GEMM without split operands");
+  ConvGemmParams p{};
+  p.lda = lda; p.a_bstride = a_bstride; p.rows_per_frame = 1; p.N = w.N; p.Cin = w.Cin; p.taps = w.taps; p.dil = 1;
+  p.out_y = Y; p.ldy = ldy; p.y_bstride = y_bstride;
+  for (int pass = 0; pass < 3; ++pass) {
+    p.A = pass < 2 ? (const void*)a.hi : (const void*)a.lo;
+    p.W = pass == 1 ? (const void*)w.w_lo : (const void*)w.w_hi;
+    p.bias = (pass == 0 && w.bias) ? w.bias : m.zeros;
+    if (pass > 0) { p.res = Y; p.ldres = ldy; p.res_bstride = y_bstride; p.scale = m.inv_split; }
+    cudaError_t err = launch_conv_gemm_tc2(p, g, DT_F16, DT_F32, m.stream);
+    if (err != cudaSuccess) throw Error(Q3TTS_ECUDA, std::string("encoder tcgen05 GEMM launch: ") + cudaGetErrorString(err));
+    ++m.launches;
+  }
+}
+
+void encode_tc(EncoderModel& m, const float* audio, int B, int64_t samples, int32_t* codes_out) {
+  const EncoderConfig& c = m.cfg;
+  ENC_CUDA_OK(cudaSetDevice(m.device));
+  cudaStream_t s = m.stream;
+  const int nst = c.n_ratios, ds = c.downsample_stride(), H = c.hidden_size, I = c.intermediate_size;
+  const int nh = c.num_attention_heads, nkv = c.num_key_value_heads, hd = H / nh, QW = (nh + 2 * nkv) * hd;
+  const int K = c.codebook_size, CB = c.codebook_dim, NQ = c.valid_quantizers;
+  std::vector<int64_t> L((size_t)nst + 2), P((size_t)nst + 1);
+  L[0] = samples;
+  for (int li = 0; li < nst; ++li) {
+    const int r = m.stages[(size_t)li].ratio;
+    L[(size_t)li + 1] = (L[(size_t)li] + r - 1) / r;
+    P[(size_t)li] = L[(size_t)li + 1] * r;
+  }
+  const int64_t Tq = (L[(size_t)nst] + ds - 1) / ds;
+  L[(size_t)nst + 1] = Tq;
+  P[(size_t)nst] = Tq * ds;
+
+  size_t off = 0;
+  auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+  const size_t o_len = take(sizeof(int) * (size_t)B * (size_t)(nst + 2));
+  const size_t o_audio = take(sizeof(float) * (size_t)B * (size_t)samples);
+  // per level: X (stream), Y (GEMM output / float32 operand), operand halves; per stage also the hidden activation in the three forms
+  std::vector<size_t> oX((size_t)nst + 1), oY((size_t)nst + 1), oAh((size_t)nst + 1), oAl((size_t)nst + 1), oHY((size_t)nst), oHh((size_t)nst), oHl((size_t)nst);
+  for (int li = 0; li <= nst; ++li) {
+    const size_t dim = (size_t)(li < nst ? m.stages[(size_t)li].dim : 2 * m.stages[(size_t)nst - 1].dim), n = (size_t)B * (size_t)P[(size_t)li];
+    oX[(size_t)li] = take(4 * n * dim); oY[(size_t)li] = take(4 * n * dim); oAh[(size_t)li] = take(2 * n * dim); oAl[(size_t)li] = take(2 * n * dim);
+    if (li < nst) { const size_t hid = dim / (size_t)c.compress; oHY[(size_t)li] = take(4 * n * hid); oHh[(size_t)li] = take(2 * n * hid); oHl[(size_t)li] = take(2 * n * hid); }
+  }
+  const size_t rowsT = (size_t)B * (size_t)P[(size_t)nst], WT = (size_t)std::max(std::max(H, I), QW);
+  const size_t o_hs = take(4 * rowsT * (size_t)H), o_nb = take(4 * rowsT * (size_t)H), o_qkv = take(4 * rowsT * (size_t)QW), o_ao = take(4 * rowsT * (size_t)H);
+  const size_t o_yt = take(4 * rowsT * WT), o_th = take(2 * rowsT * WT), o_tl = take(2 * rowsT * WT);
+  const size_t o_dsh = take(2 * rowsT * (size_t)H), o_dsl = take(2 * rowsT * (size_t)H);   // the strided downsample's operand: its padding rows must stay zero
+  const size_t o_tap = take(m.taps_enabled ? 4 * rowsT * (size_t)H : 0);
+  const size_t rowsQ = (size_t)B * (size_t)Tq;
+  const size_t o_d = take(4 * rowsQ * (size_t)H), o_r0 = take(4 * rowsQ * (size_t)CB), o_r1 = take(4 * rowsQ * (size_t)CB), o_sc = take(4 * rowsQ * (size_t)K);
+  const size_t o_qh = take(2 * rowsQ * (size_t)std::max(H, CB)), o_ql = take(2 * rowsQ * (size_t)std::max(H, CB));
+  const size_t o_codes = take(sizeof(int32_t) * rowsQ * (size_t)NQ);
+  if (off > m.arena_cap) {
+    ENC_CUDA_OK(cudaStreamSynchronize(s));
+    if (m.arena) cudaFree(m.arena);
+    m.arena = nullptr; m.arena_cap = 0; m.zeroed_B = -1;
+    size_t free_b = 0, total_b = 0;
+    ENC_CUDA_OK(cudaMemGetInfo(&free_b, &total_b));
+    if (off > free_b) throw Error(Q3TTS_ENOMEM, "encode: the batch needs " + std::to_string(off >> 20) + " MiB of device memory; encode it in smaller batches");
+    if (cudaMalloc(&m.arena, off) != cudaSuccess) { cudaGetLastError(); throw Error(Q3TTS_ENOMEM, "encode: device allocation failed"); }
+    m.arena_cap = off;
+  }
+  char* base = (char*)m.arena;
+  auto F = [&](size_t o) { return (float*)(base + o); };
+  auto Hp = [&](size_t o) { return (__half*)(base + o); };
+  zero_if_new_shape(m, base + o_audio, off - o_audio, B, samples, s);
+  m.launches = 0;
+  std::vector<int> hlen((size_t)B * (size_t)(nst + 2));
+  for (int lv = 0; lv < nst + 2; ++lv)
+    for (int b = 0; b < B; ++b) hlen[(size_t)lv * (size_t)B + (size_t)b] = (int)L[(size_t)lv];
+  int* d_len = (int*)(base + o_len);
+  ENC_CUDA_OK(cudaMemcpyAsync(d_len, hlen.data(), hlen.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+  ENC_CUDA_OK(cudaMemcpyAsync(F(o_audio), audio, sizeof(float) * (size_t)B * (size_t)samples, cudaMemcpyHostToDevice, s));
+  auto geom = [&](int64_t slot_rows, int level) {
+    BatchGeom g{};
+    g.B = B; g.Tmax = (int)slot_rows; g.len_frames = d_len + (size_t)level * (size_t)B; g.valid_frames = (long long)B * L[(size_t)level]; g.row_begin = nullptr;
+    return g;
+  };
+  // split pass: v = y (+ res, scaled); x_out = v; the operand act(v) in the form the consuming GEMM takes
+  auto split = [&](const BatchGeom& g, int C, const float* y, const float* res, const float* scale, int act, float* x_out, const EncGemm* consumer,
+                   float* a32, __half* hi, __half* lo, bool tap_a32 = false) {
+    const bool tcg = consumer && tc_takes(m, *consumer);
+    const bool want32 = (consumer && !tcg) || (tap_a32 && m.taps_enabled);     // (a stage tap reads the float32 form)
+    launch_enc_split(y, res, scale, act, x_out, want32 ? a32 : nullptr, tcg ? hi : nullptr, tcg ? lo : nullptr, C, g, s);
+    ++m.launches;
+  };
+  m.tap_index.clear();
+
+  // ---- Seanet ----
+  {  // init conv on the CUDA cores (1 input channel); its elu output lands in Y[0], then the split for stage 0's first conv
+    const int nf = c.num_filters;
+    launch_enc_init_conv(F(o_audio), samples, m.init_w, m.init_b, c.kernel_size, nf, F(oX[0]), F(oY[0]), P[0] * (int64_t)nf, geom(P[0], 0), s);
+    ++m.launches;
+    if (tc_takes(m, m.stages[0].res3)) split(geom(P[0], 0), nf, F(oY[0]), nullptr, nullptr, 0, nullptr, &m.stages[0].res3, nullptr, Hp(oAh[0]), Hp(oAl[0]));
+  }
+  for (int li = 0; li < nst; ++li) {
+    const EncStage& st = m.stages[(size_t)li];
+    const int dim = st.dim, hid = dim / c.compress;
+    const int64_t Pl = P[(size_t)li], Pn = P[(size_t)li + 1];
+    const BatchGeom g = geom(Pl, li);
+    const Opnd a{F(oY[(size_t)li]), Hp(oAh[(size_t)li]), Hp(oAl[(size_t)li])};
+    const Opnd h{F(oHY[(size_t)li]), Hp(oHh[(size_t)li]), Hp(oHl[(size_t)li])};
+    gemm_y(m, st.res3, g, a, dim, Pl * dim, F(oHY[(size_t)li]), hid, Pl * hid);
+    split(g, hid, F(oHY[(size_t)li]), nullptr, nullptr, 1, nullptr, &st.res1, F(oHY[(size_t)li]), h.hi, h.lo, true);
+    m.tap_index["hid" + std::to_string(li)] = EncTap{oHY[(size_t)li], Pl, L[(size_t)li], hid};
+    gemm_y(m, st.res1, g, h, hid, Pl * hid, F(oY[(size_t)li]), dim, Pl * dim);
+    split(g, dim, F(oY[(size_t)li]), F(oX[(size_t)li]), nullptr, 1, F(oX[(size_t)li]), &st.down, F(oY[(size_t)li]), a.hi, a.lo);
+    m.tap_index["res" + std::to_string(li)] = EncTap{oX[(size_t)li], Pl, L[(size_t)li], dim};
+    const BatchGeom gd = geom(L[(size_t)li + 1], li + 1);
+    gemm_y(m, st.down, gd, a, st.ratio * dim, Pl * dim, F(oX[(size_t)li + 1]), 2 * dim, Pn * 2 * dim);
+    const EncGemm* next = li + 1 < nst ? &m.stages[(size_t)li + 1].res3 : &m.final_conv;
+    split(geom(Pn, li + 1), 2 * dim, F(oX[(size_t)li + 1]), nullptr, nullptr, 1, nullptr, next, F(oY[(size_t)li + 1]), Hp(oAh[(size_t)li + 1]), Hp(oAl[(size_t)li + 1]));
+    if (li == nst - 1) m.tap_index["layer" + std::to_string(li)] = EncTap{oX[(size_t)li + 1], Pn, L[(size_t)li + 1], 2 * dim};
+  }
+  const int64_t PT = P[(size_t)nst], LT = L[(size_t)nst];
+  const BatchGeom gT = geom(PT, nst);
+  {
+    const int dimL = 2 * m.stages[(size_t)nst - 1].dim;
+    gemm_y(m, m.final_conv, gT, Opnd{F(oY[(size_t)nst]), Hp(oAh[(size_t)nst]), Hp(oAl[(size_t)nst])}, dimL, PT * dimL, F(o_hs), H, PT * H);
+  }
+  if (m.taps_enabled) {
+    ENC_CUDA_OK(cudaMemcpyAsync(F(o_tap), F(o_hs), 4 * rowsT * (size_t)H, cudaMemcpyDeviceToDevice, s));
+    m.tap_index["seanet"] = EncTap{o_tap, PT, LT, H};
+  }
+
+  // ---- transformer ----
+  const float scale = 1.0f / std::sqrt((float)hd);
+  const Opnd tmp{F(o_yt), Hp(o_th), Hp(o_tl)};                    // operand scratch of the layer in flight
+  for (const EncLayer& Ly : m.layers) {
+    launch_layernorm(F(o_hs), Ly.n1w, Ly.n1b, 1e-5f, F(o_nb), gT, H, s); ++m.launches;
+    if (tc_takes(m, Ly.qkv)) split(gT, H, F(o_nb), nullptr, nullptr, 0, nullptr, &Ly.qkv, nullptr, tmp.hi, tmp.lo);
+    gemm_y(m, Ly.qkv, gT, Opnd{F(o_nb), tmp.hi, tmp.lo}, H, PT * H, F(o_qkv), QW, PT * QW);
+    launch_rope(F(o_qkv), QW, nh + nkv, hd, m.inv_freq, gT, s); ++m.launches;
+    launch_attention(F(o_qkv), DT_F32, F(o_ao), DT_F32, gT, nh, nkv, hd, scale, (int)PT + 1, s); ++m.launches;
+    if (tc_takes(m, Ly.o)) split(gT, H, F(o_ao), nullptr, nullptr, 0, nullptr, &Ly.o, nullptr, tmp.hi, tmp.lo);
+    gemm_y(m, Ly.o, gT, Opnd{F(o_ao), tmp.hi, tmp.lo}, H, PT * H, F(o_yt), H, PT * H);
+    split(gT, H, F(o_yt), F(o_hs), Ly.ls1, 0, F(o_hs), nullptr, nullptr, nullptr, nullptr);          // h += ls1 * attn
+    launch_layernorm(F(o_hs), Ly.n2w, Ly.n2b, 1e-5f, F(o_nb), gT, H, s); ++m.launches;
+    if (tc_takes(m, Ly.fc1)) split(gT, H, F(o_nb), nullptr, nullptr, 0, nullptr, &Ly.fc1, nullptr, tmp.hi, tmp.lo);
+    gemm_y(m, Ly.fc1, gT, Opnd{F(o_nb), tmp.hi, tmp.lo}, H, PT * H, F(o_yt), I, PT * I);
+    split(gT, I, F(o_yt), nullptr, nullptr, 2, nullptr, &Ly.fc2, F(o_yt), tmp.hi, tmp.lo);            // tanh-GELU, in place / split
+    gemm_y(m, Ly.fc2, gT, tmp, I, PT * I, F(o_nb), H, PT * H);
+    split(gT, H, F(o_nb), F(o_hs), Ly.ls2, 0, F(o_hs), nullptr, nullptr, nullptr, nullptr);          // h += ls2 * mlp
+  }
+  m.tap_index["transformer"] = EncTap{o_hs, PT, LT, H};
+
+  // ---- downsample + quantizer ----
+  const BatchGeom gQ = geom(Tq, nst + 1);
+  if (tc_takes(m, m.downsample)) split(gT, H, F(o_hs), nullptr, nullptr, 0, nullptr, &m.downsample, nullptr, Hp(o_dsh), Hp(o_dsl));
+  gemm_y(m, m.downsample, gQ, Opnd{F(o_hs), Hp(o_dsh), Hp(o_dsl)}, ds * H, PT * H, F(o_d), H, Tq * H);
+  m.tap_index["downsample"] = EncTap{o_d, Tq, Tq, H};
+  const Opnd qop{nullptr, Hp(o_qh), Hp(o_ql)};
+  const size_t o_res[2] = {o_r0, o_r1};
+  if (tc_takes(m, m.proj[0])) split(gQ, H, F(o_d), nullptr, nullptr, 0, nullptr, &m.proj[0], nullptr, qop.hi, qop.lo);
+  for (int part = 0; part < 2; ++part) gemm_y(m, m.proj[part], gQ, Opnd{F(o_d), qop.hi, qop.lo}, H, Tq * H, F(o_res[part]), CB, Tq * CB);
+  int32_t* d_codes = (int32_t*)(base + o_codes);
+  for (size_t q = 0; q < m.books.size(); ++q) {
+    const EncBook& bk = m.books[q];
+    float* R = F(o_res[bk.part]);
+    if (tc_takes(m, bk.score)) split(gQ, CB, R, nullptr, nullptr, 0, nullptr, &bk.score, nullptr, qop.hi, qop.lo);
+    gemm_y(m, bk.score, gQ, Opnd{R, qop.hi, qop.lo}, CB, Tq * CB, F(o_sc), K, Tq * K);
+    launch_vq_select(F(o_sc), K, bk.score.w, CB, R, d_codes + (int64_t)q * Tq, (int64_t)NQ * Tq, gQ, s);
+    ++m.launches;
+  }
+  ENC_CUDA_OK(cudaMemcpyAsync(codes_out, d_codes, sizeof(int32_t) * rowsQ * (size_t)NQ, cudaMemcpyDeviceToHost, s));
+  ENC_CUDA_OK(cudaStreamSynchronize(s));
+  ENC_CUDA_OK(cudaGetLastError());
+  m.last_B = B;
+}
+}  // namespace
+
 void encoder_encode(EncoderModel& m, const float* audio, int B, int64_t samples, int32_t* codes_out) {
   std::lock_guard<std::mutex> lock(m.mu);
+  if (m.tc) {
+    if (B < 1 || samples < 1 || !audio || !codes_out) throw Error(Q3TTS_EINVAL, "encode: bad arguments");
+    if (samples > (int64_t)1 << 26 || B > 65535) throw Error(Q3TTS_EINVAL, "encode: at most 2^26 samples (46 minutes) per utterance and 65535 utterances per call");
+    encode_tc(m, audio, B, samples, codes_out);
+    return;
+  }
   const EncoderConfig& c = m.cfg;
   if (B < 1 || samples < 1 || !audio || !codes_out) throw Error(Q3TTS_EINVAL, "encode: bad arguments");
   if (samples > (int64_t)1 << 26 || B > 65535) throw Error(Q3TTS_EINVAL, "encode: at most 2^26 samples (46 minutes) per utterance and 65535 utterances per call");
@@ -245,7 +478,7 @@ void encoder_encode(EncoderModel& m, const float* audio, int B, int64_t samples,
   if (off > m.arena_cap) {
     ENC_CUDA_OK(cudaStreamSynchronize(s));
     if (m.arena) cudaFree(m.arena);
-    m.arena = nullptr; m.arena_cap = 0;
+    m.arena = nullptr; m.arena_cap = 0; m.zeroed_B = -1;
     size_t free_b = 0, total_b = 0;
     ENC_CUDA_OK(cudaMemGetInfo(&free_b, &total_b));
     if (off > free_b) throw Error(Q3TTS_ENOMEM, "encode: the batch needs " + std::to_string(off >> 20) + " MiB of device memory; encode it in smaller batches");
@@ -254,8 +487,7 @@ void encoder_encode(EncoderModel& m, const float* audio, int B, int64_t samples,
   }
   char* base = (char*)m.arena;
   auto F = [&](size_t o) { return (float*)(base + o); };
-  // zero everything the strided views may read past a level's valid rows (and the stale rows of a previous, longer call)
-  ENC_CUDA_OK(cudaMemsetAsync(base + o_audio, 0, off - o_audio, s));
+  zero_if_new_shape(m, base + o_audio, off - o_audio, B, samples, s);
   m.launches = 0;
 
   // ---- lengths + audio to the device ----

@@ -18,7 +18,10 @@
 
 namespace q3 {
 
-struct EncGemm { float* w = nullptr; float* bias = nullptr; int taps = 1, Cin = 0, N = 0; };   // [taps][N][Cin] fp32
+struct EncGemm {                     // [taps][N][Cin] fp32; tensor-core engine: the same weights as split fp16 pairs (kernels.cuh)
+  float* w = nullptr; float* bias = nullptr; int taps = 1, Cin = 0, N = 0;
+  __half *w_hi = nullptr, *w_lo = nullptr;
+};
 struct EncStage { EncGemm res3, res1, down; int dim = 0, ratio = 1; };                        // STE.swift:353-391
 struct EncLayer { float *n1w, *n1b, *n2w, *n2b, *ls1, *ls2; EncGemm qkv, o, fc1, fc2; };       // STE.swift:545-591
 struct EncBook { int part = 0; EncGemm score; };                                               // score.w = E [K][D], score.bias = -|E|^2 / 2
@@ -32,12 +35,15 @@ struct EncoderModel {
   std::vector<void*> allocs;
   std::mutex mu;                       // calls on one handle are serialised
   float *init_w = nullptr, *init_b = nullptr, *inv_freq = nullptr;
+  bool tc = false;                     // tensor-core engine (opts.precision == Q3TTS_PREC_FP16): GEMMs as three tcgen05 products of split fp16 operands
+  float *zeros = nullptr, *inv_split = nullptr;   // [max N]: zero bias, 1 / kSplitScale
   std::vector<EncStage> stages;
   EncGemm final_conv, downsample, proj[2];
   std::vector<EncLayer> layers;
   std::vector<EncBook> books;
   void* arena = nullptr;               // grow-only workspace
   size_t arena_cap = 0;
+  int zeroed_B = -1; int64_t zeroed_samples = -1; bool zeroed_taps = false;   // the shape the workspace was last cleared for
   bool taps_enabled = false;
   std::map<std::string, EncTap> tap_index;   // stage outputs of the last encode (inside the arena)
   int last_B = 0;

@@ -99,6 +99,17 @@ void launch_rope(float* qkv, int ld, int heads, int hd, const float* inv_freq, c
 void launch_vq_select(const float* score, int K, const float* E, int D, float* resid, int32_t* codes, int64_t code_bstride,
                       const BatchGeom& g, cudaStream_t s);
 
+// Split-precision operands for the tensor-core path of the encoder: a float32 value a is carried as two fp16 numbers,
+// hi = fp16(a) and lo = fp16((a - hi) * 2048) (the factor keeps lo out of fp16's subnormal range), so that
+// a.w ~= hi_a.hi_w + (hi_a.lo_w + lo_a.hi_w) / 2048 with ~22 mantissa bits per operand and fp32 accumulation.
+//  v = y (+ res, scaled per column if `scale`);  out_x = v;  a = act(v) (0 none, 1 elu, 2 tanh-GELU);  out_a32 = a;  (out_hi, out_lo) = split(a).
+// All tensors are [B, Tmax, C] with the same strides; only rows < len are touched.  Any output may be null.
+constexpr float kSplitScale = 2048.0f;
+void launch_enc_split(const float* y, const float* res, const float* scale, int act, float* out_x, float* out_a32, __half* out_hi,
+                      __half* out_lo, int C, const BatchGeom& g, cudaStream_t s);
+// the same split for a flat weight array
+void launch_split_flat(const float* src, __half* hi, __half* lo, int64_t n, cudaStream_t s);
+
 // Tensor-core (mma.sync) flash-style attention for 16-bit operands, head_dim 64 (kernels_attn.cu).
 bool attention_mma_supported(int dtype, int hd);
 void launch_attention_mma(const void* qkv, int dtype, void* out, const BatchGeom& g, int nh, int nkv, float scale,

@@ -2,6 +2,7 @@
 // "STE.swift").  fp32 throughout: the reference evaluates the nearest-codebook search in float32 on purpose (STE.swift:750-757), and
 // a code is an argmin -- there is no "close enough".  The convolutions / linears run on the CUDA-core multi-tap GEMM of
 // kernels_f32.cu (a strided conv with k = 2s is a 2-tap GEMM on the input viewed as [frames, s * Cin]); what is here is the rest.
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math.h>
 
@@ -109,7 +110,66 @@ vq_select_kernel(const float* __restrict__ score, int K, const float* __restrict
   float* rr = resid + row * D;
   for (int c = lane; c < D; c += 32) rr[c] = rr[c] - e[c];
 }
+__device__ __forceinline__ void split1(float a, __half& hi, __half& lo) {
+  hi = __float2half_rn(a);
+  lo = __float2half_rn((a - __half2float(hi)) * kSplitScale);
+}
+
+// one thread per (row, 4 channels)
+__global__ void __launch_bounds__(256)
+enc_split_kernel(const float* __restrict__ y, const float* __restrict__ res, const float* __restrict__ scale, int act, float* __restrict__ out_x,
+                 float* __restrict__ out_a32, __half* __restrict__ out_hi, __half* __restrict__ out_lo, int C, BatchGeom g) {
+  const int c4n = C >> 2;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t row = i / c4n;
+  if (row >= (int64_t)g.B * g.Tmax) return;
+  const int b = (int)(row / g.Tmax), t = (int)(row % g.Tmax);
+  if (t >= g.len_frames[b]) return;
+  const int c = (int)(i - row * c4n) * 4;
+  const int64_t o = row * C + c;
+  float4 v = *(const float4*)(y + o);
+  if (res) {
+    const float4 r = *(const float4*)(res + o);
+    if (scale) {
+      const float4 sc = *(const float4*)(scale + c);
+      v.x = r.x + sc.x * v.x; v.y = r.y + sc.y * v.y; v.z = r.z + sc.z * v.z; v.w = r.w + sc.w * v.w;
+    } else {
+      v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+    }
+  }
+  if (out_x) *(float4*)(out_x + o) = v;
+  float a[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (act == 1) a[k] = elu1(a[k]);
+    else if (act == 2) a[k] = a[k] * 0.5f * (1.0f + tanhf(0.7978845608f * (a[k] + 0.044715f * (a[k] * a[k] * a[k]))));
+  }
+  if (out_a32) *(float4*)(out_a32 + o) = make_float4(a[0], a[1], a[2], a[3]);
+  if (out_hi) {
+    __half h[4], l[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) split1(a[k], h[k], l[k]);
+    *(uint2*)(out_hi + o) = *(const uint2*)h;
+    *(uint2*)(out_lo + o) = *(const uint2*)l;
+  }
+}
+
+__global__ void __launch_bounds__(256) split_flat_kernel(const float* __restrict__ src, __half* __restrict__ hi, __half* __restrict__ lo, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  split1(src[i], hi[i], lo[i]);
+}
 }  // namespace
+
+void launch_enc_split(const float* y, const float* res, const float* scale, int act, float* out_x, float* out_a32, __half* out_hi,
+                      __half* out_lo, int C, const BatchGeom& g, cudaStream_t s) {
+  const int64_t n = (int64_t)g.B * g.Tmax * (C / 4);
+  enc_split_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(y, res, scale, act, out_x, out_a32, out_hi, out_lo, C, g);
+}
+
+void launch_split_flat(const float* src, __half* hi, __half* lo, int64_t n, cudaStream_t s) {
+  split_flat_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(src, hi, lo, n);
+}
 
 void launch_enc_init_conv(const float* audio, int64_t audio_bstride, const float* w, const float* bias, int k, int C, float* out_y,
                           float* out_a, int64_t out_bstride, const BatchGeom& g, cudaStream_t s) {

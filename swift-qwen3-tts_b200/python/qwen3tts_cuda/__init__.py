@@ -267,10 +267,13 @@ class Qwen3TTSSpeechTokenizerEncoder:
     """Speech-tokenizer encoder, audio -> codes (SpeechTokenizerEncoder.swift:955-1056): same name and `encode` shapes as the
     reference -- audio [B, 1, samples] float -> codes [B, 16, T] int32 at 12.5 frames per second."""
 
-    def __init__(self, speech_tokenizer_dir: str, device: int = 0):
+    def __init__(self, speech_tokenizer_dir: str, device: int = 0, precision: int = PREC_FP16):
+        """precision: PREC_FP16 = tensor-core engine (every GEMM as three tcgen05 products of split fp16 operands, float32-equivalent),
+        PREC_FP32 = CUDA-core float32 engine."""
         opts = Options()
         lib().q3tts_options_default(C.byref(opts))
         opts.device = device
+        opts.precision = precision
         h = C.c_void_p()
         _check(lib().q3tts_encoder_load(speech_tokenizer_dir.encode(), C.byref(opts), C.byref(h)))
         self._h = h

@@ -19,20 +19,24 @@ pytestmark = pytest.mark.gpu
 STAGES = ("hid0", "res0", "hid1", "res1", "hid2", "res2", "hid3", "res3", "layer3", "seanet", "transformer", "downsample")
 
 
-@pytest.fixture(scope="module")
-def tiny_pair():
+ENGINES = [pytest.param(q.PREC_FP16, id="tensor_cores"), pytest.param(q.PREC_FP32, id="cuda_cores")]
+
+
+@pytest.fixture(scope="module", params=ENGINES)
+def tiny_pair(request):
+    # the tiny architecture's narrow layers fall back to the CUDA-core GEMM inside the tensor-core engine: both routes in one graph
     d = os.path.join(checkpoint_dir(DecoderConfig.tiny(), seed=7, encoder_cfg=EncoderConfig.tiny()), "speech_tokenizer")
     cfg, w = oe.load_encoder(d)
-    enc = q.Qwen3TTSSpeechTokenizerEncoder(d)
+    enc = q.Qwen3TTSSpeechTokenizerEncoder(d, precision=request.param)
     yield d, cfg, oe.OracleEncoder(cfg, w, torch.float64), enc
     enc.close()
 
 
-@pytest.fixture(scope="module")
-def full_pair():
+@pytest.fixture(scope="module", params=ENGINES)
+def full_pair(request):
     d = os.path.join(checkpoint_dir(DecoderConfig.tiny(), seed=7, encoder_cfg=EncoderConfig()), "speech_tokenizer")
     cfg, w = oe.load_encoder(d)
-    enc = q.Qwen3TTSSpeechTokenizerEncoder(d)
+    enc = q.Qwen3TTSSpeechTokenizerEncoder(d, precision=request.param)
     yield d, cfg, oe.OracleEncoder(cfg, w, torch.float64), enc
     enc.close()
 
@@ -102,6 +106,8 @@ def test_encoder_errors(tiny_pair):
     with pytest.raises(q.AudioDecodingFailed) as ei:
         q.Qwen3TTSSpeechTokenizerEncoder(lite)                         # no encoder_config: Qwen3.swift:433
     assert "encoder" in str(ei.value)
+    with pytest.raises(q.AudioDecodingFailed):
+        q.Qwen3TTSSpeechTokenizerEncoder(d, precision=q.PREC_BF16)     # bf16 pairs carry too few mantissa bits for an argmin
 
 
 def test_codes_feed_the_decoder(tiny_pair):

@@ -15,7 +15,7 @@ ec = EncoderConfig() if (len(sys.argv) > 3 and sys.argv[3] == "full") else Encod
 d = os.path.join(checkpoint_dir(DecoderConfig.tiny(), seed=7, encoder_cfg=ec), "speech_tokenizer")
 cfg, w = oe.load_encoder(d)
 orc = oe.OracleEncoder(cfg, w, torch.float64)
-enc = q.Qwen3TTSSpeechTokenizerEncoder(d)
+enc = q.Qwen3TTSSpeechTokenizerEncoder(d, precision=q.PREC_FP32 if os.environ.get("Q3TTS_ENC_FP32") == "1" else q.PREC_FP16)
 a = synth_audio(B, samples, 100 + samples)
 taps, margins = {}, []
 want = orc.encode(a, taps, margins).numpy()

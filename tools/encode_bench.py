@@ -14,7 +14,7 @@ def main():
     secs = float(sys.argv[2]) if len(sys.argv) > 2 else 10.0
     iters = int(sys.argv[3]) if len(sys.argv) > 3 else 5
     d = os.path.join(checkpoint_dir(DecoderConfig.tiny(), seed=7, encoder_cfg=EncoderConfig()), "speech_tokenizer")
-    enc = q.Qwen3TTSSpeechTokenizerEncoder(d)
+    enc = q.Qwen3TTSSpeechTokenizerEncoder(d, precision=q.PREC_FP32 if os.environ.get("Q3TTS_ENC_FP32") == "1" else q.PREC_FP16)
     a = synth_audio(B, int(secs * 24000), 1)
     for _ in range(2):
         codes = enc.encode(a)
