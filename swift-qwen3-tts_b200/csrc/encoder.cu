@@ -40,6 +40,7 @@ EncGemm pack_conv(EncoderModel& m, const HostTensor& w, const HostTensor* bias, 
   EncGemm g;
   g.N = N;
   std::vector<float> packed;
+  g.inner = Cin;
   if (stride == 1) {
     g.taps = K; g.Cin = Cin;
     packed.resize((size_t)K * N * Cin);
@@ -63,7 +64,7 @@ EncGemm pack_conv(EncoderModel& m, const HostTensor& w, const HostTensor* bias, 
 
 EncGemm pack_linear(EncoderModel& m, const std::vector<const HostTensor*>& rows) {   // y = x W^T, W [out, in]; several matrices stacked
   EncGemm g;
-  g.taps = 1; g.Cin = (int)rows[0]->shape[1];
+  g.taps = 1; g.Cin = (int)rows[0]->shape[1]; g.inner = g.Cin;
   std::vector<float> packed;
   for (auto* r : rows) {
     if ((int)r->shape[1] != g.Cin) throw Error(Q3TTS_EFORMAT, "encoder: stacked linears differ in width");
@@ -172,7 +173,7 @@ EncoderModel* encoder_create(const std::string& dir, const q3tts_options& opts) 
       }
       EncBook bk;
       bk.part = part;
-      bk.score.taps = 1; bk.score.Cin = D; bk.score.N = K;
+      bk.score.taps = 1; bk.score.Cin = D; bk.score.N = K; bk.score.inner = D;
       bk.score.w = upload(m, E);
       bk.score.bias = upload(m, nc2);
       m.books.push_back(bk);
@@ -182,12 +183,26 @@ EncoderModel* encoder_create(const std::string& dir, const q3tts_options& opts) 
     int maxN = std::max(std::max(c.codebook_size, c.intermediate_size), (c.num_attention_heads + 2 * c.num_key_value_heads) * (c.hidden_size / c.num_attention_heads));
     for (auto& st : m.stages) maxN = std::max(maxN, 2 * st.dim);
     m.zeros = upload(m, std::vector<float>((size_t)maxN, 0.f));
-    m.inv_split = upload(m, std::vector<float>((size_t)maxN, 1.0f / kSplitScale));
+    int* d_flag = nullptr;
+    ENC_CUDA_OK(cudaMalloc(&d_flag, sizeof(int))); m.allocs.push_back(d_flag);
     auto split_w = [&](EncGemm& g) {
-      const int64_t n = (int64_t)g.taps * g.N * g.Cin;
-      ENC_CUDA_OK(cudaMalloc(&g.w_hi, (size_t)n * 2)); m.allocs.push_back(g.w_hi);
-      ENC_CUDA_OK(cudaMalloc(&g.w_lo, (size_t)n * 2)); m.allocs.push_back(g.w_lo);
-      launch_split_flat(g.w, g.w_hi, g.w_lo, n, m.stream);
+      const int64_t rows = (int64_t)g.taps * g.N;
+      ENC_CUDA_OK(cudaMalloc(&g.w3, (size_t)rows * 3 * (size_t)g.Cin * 2)); m.allocs.push_back(g.w3);
+      ENC_CUDA_OK(cudaMemsetAsync(d_flag, 0, sizeof(int), m.stream));
+      launch_expand_w3(g.w, g.w3, rows, g.Cin, g.Cin, d_flag, m.stream);
+      int flag = 0;
+      ENC_CUDA_OK(cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, m.stream));
+      ENC_CUDA_OK(cudaStreamSynchronize(m.stream));
+      if (flag) { g.w3 = nullptr; return; }            // a weight too large for the scaled fp16 form: this GEMM stays on the CUDA cores
+      if (g.bias) {
+        std::vector<float> hb((size_t)g.N);
+        ENC_CUDA_OK(cudaMemcpyAsync(hb.data(), g.bias, sizeof(float) * (size_t)g.N, cudaMemcpyDeviceToHost, m.stream));
+        ENC_CUDA_OK(cudaStreamSynchronize(m.stream));
+        for (auto& v : hb) v *= kSplitScale;
+        g.bias_s = upload(m, hb);
+      } else {
+        g.bias_s = m.zeros;
+      }
     };
     for (auto& st : m.stages) { split_w(st.res3); split_w(st.res1); split_w(st.down); }
     split_w(m.final_conv); split_w(m.downsample); split_w(m.proj[0]); split_w(m.proj[1]);
@@ -235,35 +250,34 @@ void zero_if_new_shape(EncoderModel& m, char* from, size_t bytes, int B, int64_t
 // element-wise around it (residual, layer scale, elu / GELU, the split of the next operand) is ONE pass of enc_split_kernel.
 // A GEMM the tensor-core kernel does not take (Cin < 64: the first stage's 1x1 conv, the tiny test architecture) runs on the
 // CUDA-core engine from a float32 operand.
-struct Opnd { float* f32 = nullptr; __half* hi = nullptr; __half* lo = nullptr; };
+struct Opnd { float* f32 = nullptr; __half* h3 = nullptr; };   // float32 form [rows][C] and / or split form [rows][3 C]
 
 bool tc_takes(const EncoderModel& m, const EncGemm& w) {
   ConvGemmParams p{};
-  p.N = w.N; p.Cin = w.Cin; p.lda = w.Cin; p.taps = w.taps; p.dil = 1;
-  return m.tc && w.w_hi && tc2_supported(p, DT_F16);
+  p.N = w.N; p.Cin = 3 * w.Cin; p.lda = 3 * w.Cin; p.taps = w.taps; p.dil = 1;
+  return m.tc && w.w3 && tc2_supported(p, DT_F16);
 }
 
-void gemm_y(EncoderModel& m, const EncGemm& w, const BatchGeom& g, const Opnd& a, int lda, int64_t a_bstride, float* Y, int ldy, int64_t y_bstride) {
+// Y = (bias + conv(a)) x out_scale; returns out_scale (kSplitScale from the tensor-core GEMM, 1 from the CUDA-core fallback).
+// lda / a_bstride are in elements of the float32 form; the split form has three times as many halves per row.
+float gemm_y(EncoderModel& m, const EncGemm& w, const BatchGeom& g, const Opnd& a, int lda, int64_t a_bstride, float* Y, int ldy, int64_t y_bstride) {
   if (!tc_takes(m, w)) {
     if (!a.f32) throw Error(Q3TTS_EINVAL, "internal: CUDA-core GEMM without a float32 operand");
     ConvGemmParams e{};
     e.out_y = Y; e.ldy = ldy; e.y_bstride = y_bstride;
     run_gemm(m, w, g, a.f32, lda, a_bstride, e);
-    return;
+    return 1.0f;
   }
-  if (!a.hi || !a.lo) throw Error(Q3TTS_EINVAL, "internal: tensor-core GEMM without split operands");
+  if (!a.h3) throw Error(Q3TTS_EINVAL, "internal: tensor-core GEMM without a split operand");
   ConvGemmParams p{};
-  p.lda = lda; p.a_bstride = a_bstride; p.rows_per_frame = 1; p.N = w.N; p.Cin = w.Cin; p.taps = w.taps; p.dil = 1;
+  p.A = a.h3; p.lda = 3 * lda; p.a_bstride = 3 * a_bstride; p.W = w.w3;
+  p.rows_per_frame = 1; p.N = w.N; p.Cin = 3 * w.Cin; p.taps = w.taps; p.dil = 1;
+  p.bias = w.bias_s;
   p.out_y = Y; p.ldy = ldy; p.y_bstride = y_bstride;
-  for (int pass = 0; pass < 3; ++pass) {
-    p.A = pass < 2 ? (const void*)a.hi : (const void*)a.lo;
-    p.W = pass == 1 ? (const void*)w.w_lo : (const void*)w.w_hi;
-    p.bias = (pass == 0 && w.bias) ? w.bias : m.zeros;
-    if (pass > 0) { p.res = Y; p.ldres = ldy; p.res_bstride = y_bstride; p.scale = m.inv_split; }
-    cudaError_t err = launch_conv_gemm_tc2(p, g, DT_F16, DT_F32, m.stream);
-    if (err != cudaSuccess) throw Error(Q3TTS_ECUDA, std::string("encoder tcgen05 GEMM launch: ") + cudaGetErrorString(err));
-    ++m.launches;
-  }
+  cudaError_t err = launch_conv_gemm_tc2(p, g, DT_F16, DT_F32, m.stream);
+  if (err != cudaSuccess) throw Error(Q3TTS_ECUDA, std::string("encoder tcgen05 GEMM launch: ") + cudaGetErrorString(err));
+  ++m.launches;
+  return kSplitScale;
 }
 
 void encode_tc(EncoderModel& m, const float* audio, int B, int64_t samples, int32_t* codes_out) {
@@ -288,21 +302,23 @@ void encode_tc(EncoderModel& m, const float* audio, int B, int64_t samples, int3
   auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
   const size_t o_len = take(sizeof(int) * (size_t)B * (size_t)(nst + 2));
   const size_t o_audio = take(sizeof(float) * (size_t)B * (size_t)samples);
-  // per level: X (stream), Y (GEMM output / float32 operand), operand halves; per stage also the hidden activation in the three forms
-  std::vector<size_t> oX((size_t)nst + 1), oY((size_t)nst + 1), oAh((size_t)nst + 1), oAl((size_t)nst + 1), oHY((size_t)nst), oHh((size_t)nst), oHl((size_t)nst);
+  // per level: X (stream), Y (GEMM output / float32 operand), A3 (split operand, 3 C halves per row); per stage the hidden activation likewise
+  // (the strided conv's operand D3 has its own buffer: its rows are grouped by the stride, and the padding rows of the last group must
+  //  never have been written in another layout)
+  std::vector<size_t> oX((size_t)nst + 1), oY((size_t)nst + 1), oA3((size_t)nst + 1), oD3((size_t)nst), oHY((size_t)nst), oH3((size_t)nst);
   for (int li = 0; li <= nst; ++li) {
     const size_t dim = (size_t)(li < nst ? m.stages[(size_t)li].dim : 2 * m.stages[(size_t)nst - 1].dim), n = (size_t)B * (size_t)P[(size_t)li];
-    oX[(size_t)li] = take(4 * n * dim); oY[(size_t)li] = take(4 * n * dim); oAh[(size_t)li] = take(2 * n * dim); oAl[(size_t)li] = take(2 * n * dim);
-    if (li < nst) { const size_t hid = dim / (size_t)c.compress; oHY[(size_t)li] = take(4 * n * hid); oHh[(size_t)li] = take(2 * n * hid); oHl[(size_t)li] = take(2 * n * hid); }
+    oX[(size_t)li] = take(4 * n * dim); oY[(size_t)li] = take(4 * n * dim); oA3[(size_t)li] = take(6 * n * dim);
+    if (li < nst) { const size_t hid = dim / (size_t)c.compress; oHY[(size_t)li] = take(4 * n * hid); oH3[(size_t)li] = take(6 * n * hid); oD3[(size_t)li] = take(6 * n * dim); }
   }
   const size_t rowsT = (size_t)B * (size_t)P[(size_t)nst], WT = (size_t)std::max(std::max(H, I), QW);
   const size_t o_hs = take(4 * rowsT * (size_t)H), o_nb = take(4 * rowsT * (size_t)H), o_qkv = take(4 * rowsT * (size_t)QW), o_ao = take(4 * rowsT * (size_t)H);
-  const size_t o_yt = take(4 * rowsT * WT), o_th = take(2 * rowsT * WT), o_tl = take(2 * rowsT * WT);
-  const size_t o_dsh = take(2 * rowsT * (size_t)H), o_dsl = take(2 * rowsT * (size_t)H);   // the strided downsample's operand: its padding rows must stay zero
+  const size_t o_yt = take(4 * rowsT * WT), o_t3 = take(6 * rowsT * WT);
+  const size_t o_ds3 = take(6 * rowsT * (size_t)H);               // the strided downsample's operand: its padding rows must stay zero
   const size_t o_tap = take(m.taps_enabled ? 4 * rowsT * (size_t)H : 0);
   const size_t rowsQ = (size_t)B * (size_t)Tq;
   const size_t o_d = take(4 * rowsQ * (size_t)H), o_r0 = take(4 * rowsQ * (size_t)CB), o_r1 = take(4 * rowsQ * (size_t)CB), o_sc = take(4 * rowsQ * (size_t)K);
-  const size_t o_qh = take(2 * rowsQ * (size_t)std::max(H, CB)), o_ql = take(2 * rowsQ * (size_t)std::max(H, CB));
+  const size_t o_q3 = take(6 * rowsQ * (size_t)std::max(H, CB));
   const size_t o_codes = take(sizeof(int32_t) * rowsQ * (size_t)NQ);
   if (off > m.arena_cap) {
     ENC_CUDA_OK(cudaStreamSynchronize(s));
@@ -330,47 +346,49 @@ void encode_tc(EncoderModel& m, const float* audio, int B, int64_t samples, int3
     g.B = B; g.Tmax = (int)slot_rows; g.len_frames = d_len + (size_t)level * (size_t)B; g.valid_frames = (long long)B * L[(size_t)level]; g.row_begin = nullptr;
     return g;
   };
-  // split pass: v = y (+ res, scaled); x_out = v; the operand act(v) in the form the consuming GEMM takes
-  auto split = [&](const BatchGeom& g, int C, const float* y, const float* res, const float* scale, int act, float* x_out, const EncGemm* consumer,
-                   float* a32, __half* hi, __half* lo, bool tap_a32 = false) {
+  // element-wise pass: v = y / y_scale (+ res, scaled); x_out = v; the operand act(v) in the form the consuming GEMM takes
+  auto split = [&](const BatchGeom& g, int C, const float* y, float y_scale, const float* res, const float* scale, int act, float* x_out,
+                   const EncGemm* consumer, float* a32, __half* h3, bool tap_a32 = false) {
     const bool tcg = consumer && tc_takes(m, *consumer);
     const bool want32 = (consumer && !tcg) || (tap_a32 && m.taps_enabled);     // (a stage tap reads the float32 form)
-    launch_enc_split(y, res, scale, act, x_out, want32 ? a32 : nullptr, tcg ? hi : nullptr, tcg ? lo : nullptr, C, g, s);
+    const int grp = consumer ? consumer->Cin / C : 1;                          // the consumer's stride: its Cin is stride x C
+    launch_enc_split(y, 1.0f / y_scale, res, scale, act, x_out, want32 ? a32 : nullptr, tcg ? h3 : nullptr, grp, C, g, s);
     ++m.launches;
   };
   m.tap_index.clear();
 
   // ---- Seanet ----
-  {  // init conv on the CUDA cores (1 input channel); its elu output lands in Y[0], then the split for stage 0's first conv
+  {  // init conv on the CUDA cores (1 input channel); its elu output lands in Y[0], split for stage 0's first conv if that runs on tensor cores
     const int nf = c.num_filters;
     launch_enc_init_conv(F(o_audio), samples, m.init_w, m.init_b, c.kernel_size, nf, F(oX[0]), F(oY[0]), P[0] * (int64_t)nf, geom(P[0], 0), s);
     ++m.launches;
-    if (tc_takes(m, m.stages[0].res3)) split(geom(P[0], 0), nf, F(oY[0]), nullptr, nullptr, 0, nullptr, &m.stages[0].res3, nullptr, Hp(oAh[0]), Hp(oAl[0]));
+    if (tc_takes(m, m.stages[0].res3)) split(geom(P[0], 0), nf, F(oY[0]), 1.0f, nullptr, nullptr, 0, nullptr, &m.stages[0].res3, nullptr, Hp(oA3[0]));
   }
   for (int li = 0; li < nst; ++li) {
     const EncStage& st = m.stages[(size_t)li];
     const int dim = st.dim, hid = dim / c.compress;
     const int64_t Pl = P[(size_t)li], Pn = P[(size_t)li + 1];
     const BatchGeom g = geom(Pl, li);
-    const Opnd a{F(oY[(size_t)li]), Hp(oAh[(size_t)li]), Hp(oAl[(size_t)li])};
-    const Opnd h{F(oHY[(size_t)li]), Hp(oHh[(size_t)li]), Hp(oHl[(size_t)li])};
-    gemm_y(m, st.res3, g, a, dim, Pl * dim, F(oHY[(size_t)li]), hid, Pl * hid);
-    split(g, hid, F(oHY[(size_t)li]), nullptr, nullptr, 1, nullptr, &st.res1, F(oHY[(size_t)li]), h.hi, h.lo, true);
+    const Opnd a{F(oY[(size_t)li]), Hp(oA3[(size_t)li])};
+    const Opnd h{F(oHY[(size_t)li]), Hp(oH3[(size_t)li])};
+    float sc = gemm_y(m, st.res3, g, a, dim, Pl * dim, F(oHY[(size_t)li]), hid, Pl * hid);
+    split(g, hid, F(oHY[(size_t)li]), sc, nullptr, nullptr, 1, nullptr, &st.res1, F(oHY[(size_t)li]), h.h3, true);
     m.tap_index["hid" + std::to_string(li)] = EncTap{oHY[(size_t)li], Pl, L[(size_t)li], hid};
-    gemm_y(m, st.res1, g, h, hid, Pl * hid, F(oY[(size_t)li]), dim, Pl * dim);
-    split(g, dim, F(oY[(size_t)li]), F(oX[(size_t)li]), nullptr, 1, F(oX[(size_t)li]), &st.down, F(oY[(size_t)li]), a.hi, a.lo);
+    sc = gemm_y(m, st.res1, g, h, hid, Pl * hid, F(oY[(size_t)li]), dim, Pl * dim);
+    const Opnd d{F(oY[(size_t)li]), Hp(oD3[(size_t)li])};
+    split(g, dim, F(oY[(size_t)li]), sc, F(oX[(size_t)li]), nullptr, 1, F(oX[(size_t)li]), &st.down, d.f32, d.h3);
     m.tap_index["res" + std::to_string(li)] = EncTap{oX[(size_t)li], Pl, L[(size_t)li], dim};
-    const BatchGeom gd = geom(L[(size_t)li + 1], li + 1);
-    gemm_y(m, st.down, gd, a, st.ratio * dim, Pl * dim, F(oX[(size_t)li + 1]), 2 * dim, Pn * 2 * dim);
+    sc = gemm_y(m, st.down, geom(L[(size_t)li + 1], li + 1), d, st.ratio * dim, Pl * dim, F(oX[(size_t)li + 1]), 2 * dim, Pn * 2 * dim);
     const EncGemm* next = li + 1 < nst ? &m.stages[(size_t)li + 1].res3 : &m.final_conv;
-    split(geom(Pn, li + 1), 2 * dim, F(oX[(size_t)li + 1]), nullptr, nullptr, 1, nullptr, next, F(oY[(size_t)li + 1]), Hp(oAh[(size_t)li + 1]), Hp(oAl[(size_t)li + 1]));
+    split(geom(Pn, li + 1), 2 * dim, F(oX[(size_t)li + 1]), sc, nullptr, nullptr, 1, F(oX[(size_t)li + 1]), next, F(oY[(size_t)li + 1]), Hp(oA3[(size_t)li + 1]));
     if (li == nst - 1) m.tap_index["layer" + std::to_string(li)] = EncTap{oX[(size_t)li + 1], Pn, L[(size_t)li + 1], 2 * dim};
   }
   const int64_t PT = P[(size_t)nst], LT = L[(size_t)nst];
   const BatchGeom gT = geom(PT, nst);
   {
     const int dimL = 2 * m.stages[(size_t)nst - 1].dim;
-    gemm_y(m, m.final_conv, gT, Opnd{F(oY[(size_t)nst]), Hp(oAh[(size_t)nst]), Hp(oAl[(size_t)nst])}, dimL, PT * dimL, F(o_hs), H, PT * H);
+    const float sc = gemm_y(m, m.final_conv, gT, Opnd{F(oY[(size_t)nst]), Hp(oA3[(size_t)nst])}, dimL, PT * dimL, F(o_hs), H, PT * H);
+    if (sc != 1.0f) split(gT, H, F(o_hs), sc, nullptr, nullptr, 0, F(o_hs), nullptr, nullptr, nullptr);
   }
   if (m.taps_enabled) {
     ENC_CUDA_OK(cudaMemcpyAsync(F(o_tap), F(o_hs), 4 * rowsT * (size_t)H, cudaMemcpyDeviceToDevice, s));
@@ -379,40 +397,46 @@ void encode_tc(EncoderModel& m, const float* audio, int B, int64_t samples, int3
 
   // ---- transformer ----
   const float scale = 1.0f / std::sqrt((float)hd);
-  const Opnd tmp{F(o_yt), Hp(o_th), Hp(o_tl)};                    // operand scratch of the layer in flight
+  const Opnd tmp{F(o_yt), Hp(o_t3)};                              // operand scratch of the layer in flight
   for (const EncLayer& Ly : m.layers) {
     launch_layernorm(F(o_hs), Ly.n1w, Ly.n1b, 1e-5f, F(o_nb), gT, H, s); ++m.launches;
-    if (tc_takes(m, Ly.qkv)) split(gT, H, F(o_nb), nullptr, nullptr, 0, nullptr, &Ly.qkv, nullptr, tmp.hi, tmp.lo);
-    gemm_y(m, Ly.qkv, gT, Opnd{F(o_nb), tmp.hi, tmp.lo}, H, PT * H, F(o_qkv), QW, PT * QW);
+    if (tc_takes(m, Ly.qkv)) split(gT, H, F(o_nb), 1.0f, nullptr, nullptr, 0, nullptr, &Ly.qkv, nullptr, tmp.h3);
+    const float sq = gemm_y(m, Ly.qkv, gT, Opnd{F(o_nb), tmp.h3}, H, PT * H, F(o_qkv), QW, PT * QW);
+    // q, k, v all carry the factor sq: RoPE is linear, the scores carry sq^2 (folded into the softmax scale), the output carries sq
     launch_rope(F(o_qkv), QW, nh + nkv, hd, m.inv_freq, gT, s); ++m.launches;
-    launch_attention(F(o_qkv), DT_F32, F(o_ao), DT_F32, gT, nh, nkv, hd, scale, (int)PT + 1, s); ++m.launches;
-    if (tc_takes(m, Ly.o)) split(gT, H, F(o_ao), nullptr, nullptr, 0, nullptr, &Ly.o, nullptr, tmp.hi, tmp.lo);
-    gemm_y(m, Ly.o, gT, Opnd{F(o_ao), tmp.hi, tmp.lo}, H, PT * H, F(o_yt), H, PT * H);
-    split(gT, H, F(o_yt), F(o_hs), Ly.ls1, 0, F(o_hs), nullptr, nullptr, nullptr, nullptr);          // h += ls1 * attn
+    launch_attention(F(o_qkv), DT_F32, F(o_ao), DT_F32, gT, nh, nkv, hd, scale / (sq * sq), (int)PT + 1, s); ++m.launches;
+    split(gT, H, F(o_ao), sq, nullptr, nullptr, 0, nullptr, &Ly.o, F(o_ao), tmp.h3);
+    float sc = gemm_y(m, Ly.o, gT, Opnd{F(o_ao), tmp.h3}, H, PT * H, F(o_yt), H, PT * H);
+    split(gT, H, F(o_yt), sc, F(o_hs), Ly.ls1, 0, F(o_hs), nullptr, nullptr, nullptr);               // h += ls1 * attn
     launch_layernorm(F(o_hs), Ly.n2w, Ly.n2b, 1e-5f, F(o_nb), gT, H, s); ++m.launches;
-    if (tc_takes(m, Ly.fc1)) split(gT, H, F(o_nb), nullptr, nullptr, 0, nullptr, &Ly.fc1, nullptr, tmp.hi, tmp.lo);
-    gemm_y(m, Ly.fc1, gT, Opnd{F(o_nb), tmp.hi, tmp.lo}, H, PT * H, F(o_yt), I, PT * I);
-    split(gT, I, F(o_yt), nullptr, nullptr, 2, nullptr, &Ly.fc2, F(o_yt), tmp.hi, tmp.lo);            // tanh-GELU, in place / split
-    gemm_y(m, Ly.fc2, gT, tmp, I, PT * I, F(o_nb), H, PT * H);
-    split(gT, H, F(o_nb), F(o_hs), Ly.ls2, 0, F(o_hs), nullptr, nullptr, nullptr, nullptr);          // h += ls2 * mlp
+    if (tc_takes(m, Ly.fc1)) split(gT, H, F(o_nb), 1.0f, nullptr, nullptr, 0, nullptr, &Ly.fc1, nullptr, tmp.h3);
+    sc = gemm_y(m, Ly.fc1, gT, Opnd{F(o_nb), tmp.h3}, H, PT * H, F(o_yt), I, PT * I);
+    split(gT, I, F(o_yt), sc, nullptr, nullptr, 2, nullptr, &Ly.fc2, F(o_yt), tmp.h3);               // tanh-GELU, in place / split
+    sc = gemm_y(m, Ly.fc2, gT, tmp, I, PT * I, F(o_nb), H, PT * H);
+    split(gT, H, F(o_nb), sc, F(o_hs), Ly.ls2, 0, F(o_hs), nullptr, nullptr, nullptr);               // h += ls2 * mlp
   }
   m.tap_index["transformer"] = EncTap{o_hs, PT, LT, H};
 
   // ---- downsample + quantizer ----
   const BatchGeom gQ = geom(Tq, nst + 1);
-  if (tc_takes(m, m.downsample)) split(gT, H, F(o_hs), nullptr, nullptr, 0, nullptr, &m.downsample, nullptr, Hp(o_dsh), Hp(o_dsl));
-  gemm_y(m, m.downsample, gQ, Opnd{F(o_hs), Hp(o_dsh), Hp(o_dsl)}, ds * H, PT * H, F(o_d), H, Tq * H);
+  if (tc_takes(m, m.downsample)) split(gT, H, F(o_hs), 1.0f, nullptr, nullptr, 0, nullptr, &m.downsample, nullptr, Hp(o_ds3));
+  {
+    const float sc = gemm_y(m, m.downsample, gQ, Opnd{F(o_hs), Hp(o_ds3)}, ds * H, PT * H, F(o_d), H, Tq * H);
+    // true scale in place (the stage tap and the CUDA-core fallback read D), and the split operand of the two input projections
+    split(gQ, H, F(o_d), sc, nullptr, nullptr, 0, F(o_d), &m.proj[0], F(o_d), Hp(o_q3));
+  }
   m.tap_index["downsample"] = EncTap{o_d, Tq, Tq, H};
-  const Opnd qop{nullptr, Hp(o_qh), Hp(o_ql)};
   const size_t o_res[2] = {o_r0, o_r1};
-  if (tc_takes(m, m.proj[0])) split(gQ, H, F(o_d), nullptr, nullptr, 0, nullptr, &m.proj[0], nullptr, qop.hi, qop.lo);
-  for (int part = 0; part < 2; ++part) gemm_y(m, m.proj[part], gQ, Opnd{F(o_d), qop.hi, qop.lo}, H, Tq * H, F(o_res[part]), CB, Tq * CB);
+  for (int part = 0; part < 2; ++part) {
+    const float sc = gemm_y(m, m.proj[part], gQ, Opnd{F(o_d), Hp(o_q3)}, H, Tq * H, F(o_res[part]), CB, Tq * CB);
+    if (sc != 1.0f) split(gQ, CB, F(o_res[part]), sc, nullptr, nullptr, 0, F(o_res[part]), nullptr, nullptr, nullptr);   // the residual is updated with unscaled code vectors
+  }
   int32_t* d_codes = (int32_t*)(base + o_codes);
   for (size_t q = 0; q < m.books.size(); ++q) {
     const EncBook& bk = m.books[q];
     float* R = F(o_res[bk.part]);
-    if (tc_takes(m, bk.score)) split(gQ, CB, R, nullptr, nullptr, 0, nullptr, &bk.score, nullptr, qop.hi, qop.lo);
-    gemm_y(m, bk.score, gQ, Opnd{R, qop.hi, qop.lo}, CB, Tq * CB, F(o_sc), K, Tq * K);
+    if (tc_takes(m, bk.score)) split(gQ, CB, R, 1.0f, nullptr, nullptr, 0, nullptr, &bk.score, nullptr, Hp(o_q3));
+    gemm_y(m, bk.score, gQ, Opnd{R, Hp(o_q3)}, CB, Tq * CB, F(o_sc), K, Tq * K);                     // the argmax does not see the common factor
     launch_vq_select(F(o_sc), K, bk.score.w, CB, R, d_codes + (int64_t)q * Tq, (int64_t)NQ * Tq, gQ, s);
     ++m.launches;
   }

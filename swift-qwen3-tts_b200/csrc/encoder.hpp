@@ -18,9 +18,10 @@
 
 namespace q3 {
 
-struct EncGemm {                     // [taps][N][Cin] fp32; tensor-core engine: the same weights as split fp16 pairs (kernels.cuh)
+struct EncGemm {                     // [taps][N][Cin] fp32; tensor-core engine: the same weights as [taps][N][3 Cin] fp16 triples (kernels.cuh)
   float* w = nullptr; float* bias = nullptr; int taps = 1, Cin = 0, N = 0;
-  __half *w_hi = nullptr, *w_lo = nullptr;
+  int inner = 0;                     // channels of one operand row (a strided conv's Cin is stride x inner)
+  __half* w3 = nullptr; float* bias_s = nullptr;   // bias x kSplitScale (zeros when there is none)
 };
 struct EncStage { EncGemm res3, res1, down; int dim = 0, ratio = 1; };                        // STE.swift:353-391
 struct EncLayer { float *n1w, *n1b, *n2w, *n2b, *ls1, *ls2; EncGemm qkv, o, fc1, fc2; };       // STE.swift:545-591
@@ -36,7 +37,7 @@ struct EncoderModel {
   std::mutex mu;                       // calls on one handle are serialised
   float *init_w = nullptr, *init_b = nullptr, *inv_freq = nullptr;
   bool tc = false;                     // tensor-core engine (opts.precision == Q3TTS_PREC_FP16): GEMMs as three tcgen05 products of split fp16 operands
-  float *zeros = nullptr, *inv_split = nullptr;   // [max N]: zero bias, 1 / kSplitScale
+  float* zeros = nullptr;              // [max N] zero bias
   std::vector<EncStage> stages;
   EncGemm final_conv, downsample, proj[2];
   std::vector<EncLayer> layers;

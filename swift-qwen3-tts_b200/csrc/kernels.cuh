@@ -99,16 +99,23 @@ void launch_rope(float* qkv, int ld, int heads, int hd, const float* inv_freq, c
 void launch_vq_select(const float* score, int K, const float* E, int D, float* resid, int32_t* codes, int64_t code_bstride,
                       const BatchGeom& g, cudaStream_t s);
 
-// Split-precision operands for the tensor-core path of the encoder: a float32 value a is carried as two fp16 numbers,
-// hi = fp16(a) and lo = fp16((a - hi) * 2048) (the factor keeps lo out of fp16's subnormal range), so that
-// a.w ~= hi_a.hi_w + (hi_a.lo_w + lo_a.hi_w) / 2048 with ~22 mantissa bits per operand and fp32 accumulation.
-//  v = y (+ res, scaled per column if `scale`);  out_x = v;  a = act(v) (0 none, 1 elu, 2 tanh-GELU);  out_a32 = a;  (out_hi, out_lo) = split(a).
-// All tensors are [B, Tmax, C] with the same strides; only rows < len are touched.  Any output may be null.
+// Split-precision operands for the tensor-core engine of the encoder.  A float32 value a is carried as two fp16 numbers,
+// hi = fp16(a) and lo' = fp16((a - hi) * 2048) (the factor keeps lo' out of fp16's subnormal range).  One GEMM with K' = 3 K,
+//   A' = [a_lo' | a_hi | a_hi],   W' = [w_hi | w_lo' | 2048 w_hi]   =>   A'.W' = 2048 (a_lo w_hi + a_hi w_lo + a_hi w_hi)
+// accumulates in float32 inside tensor memory: ~22 mantissa bits per operand, every scaling an exact power of two.  The small terms
+// come FIRST in K: the tensor core truncates at every accumulation step, relative to the accumulator's magnitude, so they must be
+// summed while the accumulator is still small (measured: 3x the error otherwise).  The output (and the bias) carry the factor
+// 2048, which the next element-wise pass removes (`y_scale`).
+//  v = y * y_scale (+ res, scaled per column if `scale`);  out_x = v;  a = act(v) (0 none, 1 elu, 2 tanh-GELU);  out_a32 = a;
+//  out_h3: rows in groups of `grp` (the consuming conv's stride; Tmax % grp == 0): [lo' of the group's rows | hi | hi], so that the
+//  conv's view [Tmax / grp, 3 grp C] of the same memory keeps the three parts contiguous.
+// All tensors are [B, Tmax, C] (out_h3: [B, Tmax, 3 C]); only rows < len are touched.  Any output may be null.
 constexpr float kSplitScale = 2048.0f;
-void launch_enc_split(const float* y, const float* res, const float* scale, int act, float* out_x, float* out_a32, __half* out_hi,
-                      __half* out_lo, int C, const BatchGeom& g, cudaStream_t s);
-// the same split for a flat weight array
-void launch_split_flat(const float* src, __half* hi, __half* lo, int64_t n, cudaStream_t s);
+void launch_enc_split(const float* y, float y_scale, const float* res, const float* scale, int act, float* out_x, float* out_a32,
+                      __half* out_h3, int grp, int C, const BatchGeom& g, cudaStream_t s);
+// weights [rows][Cin] float32 -> [rows][3 Cin] fp16 in blocks of `inner` channels ([hi | lo' | 2048 hi] per block; inner = Cin here)
+// *overflow (device int) is set when some |w| x 2048 does not fit fp16: such a GEMM must stay on the CUDA cores
+void launch_expand_w3(const float* w, __half* out, int64_t rows, int Cin, int inner, int* overflow, cudaStream_t s);
 
 // Tensor-core (mma.sync) flash-style attention for 16-bit operands, head_dim 64 (kernels_attn.cu).
 bool attention_mma_supported(int dtype, int hd);

@@ -117,8 +117,8 @@ __device__ __forceinline__ void split1(float a, __half& hi, __half& lo) {
 
 // one thread per (row, 4 channels)
 __global__ void __launch_bounds__(256)
-enc_split_kernel(const float* __restrict__ y, const float* __restrict__ res, const float* __restrict__ scale, int act, float* __restrict__ out_x,
-                 float* __restrict__ out_a32, __half* __restrict__ out_hi, __half* __restrict__ out_lo, int C, BatchGeom g) {
+enc_split_kernel(const float* __restrict__ y, float y_scale, const float* __restrict__ res, const float* __restrict__ scale, int act,
+                 float* __restrict__ out_x, float* __restrict__ out_a32, __half* __restrict__ out_h3, int grp, int C, BatchGeom g) {
   const int c4n = C >> 2;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t row = i / c4n;
@@ -128,6 +128,7 @@ enc_split_kernel(const float* __restrict__ y, const float* __restrict__ res, con
   const int c = (int)(i - row * c4n) * 4;
   const int64_t o = row * C + c;
   float4 v = *(const float4*)(y + o);
+  v.x *= y_scale; v.y *= y_scale; v.z *= y_scale; v.w *= y_scale;
   if (res) {
     const float4 r = *(const float4*)(res + o);
     if (scale) {
@@ -145,30 +146,45 @@ enc_split_kernel(const float* __restrict__ y, const float* __restrict__ res, con
     else if (act == 2) a[k] = a[k] * 0.5f * (1.0f + tanhf(0.7978845608f * (a[k] + 0.044715f * (a[k] * a[k] * a[k]))));
   }
   if (out_a32) *(float4*)(out_a32 + o) = make_float4(a[0], a[1], a[2], a[3]);
-  if (out_hi) {
+  if (out_h3) {
     __half h[4], l[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) split1(a[k], h[k], l[k]);
-    *(uint2*)(out_hi + o) = *(const uint2*)h;
-    *(uint2*)(out_lo + o) = *(const uint2*)l;
+    // rows are grouped `grp` at a time (the stride of the consuming conv): [lo' of the group | hi of the group | hi of the group]
+    const int64_t grow = (int64_t)b * g.Tmax + (t / grp) * grp;          // first row of this row's group (Tmax is a multiple of grp)
+    __half* d = out_h3 + grow * 3 * C + (int64_t)(t % grp) * C + c;
+    const int64_t part = (int64_t)grp * C;
+    *(uint2*)d = *(const uint2*)l;
+    *(uint2*)(d + part) = *(const uint2*)h;
+    *(uint2*)(d + 2 * part) = *(const uint2*)h;
   }
 }
 
-__global__ void __launch_bounds__(256) split_flat_kernel(const float* __restrict__ src, __half* __restrict__ hi, __half* __restrict__ lo, int64_t n) {
+__global__ void __launch_bounds__(256)
+expand_w3_kernel(const float* __restrict__ w, __half* __restrict__ out, int64_t rows, int Cin, int inner, int* __restrict__ overflow) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  split1(src[i], hi[i], lo[i]);
+  if (i >= rows * Cin) return;
+  if (!(fabsf(w[i]) * kSplitScale < 60000.0f)) atomicOr(overflow, 1);   // 2048 x hi would leave fp16's range (or w is not finite)
+  const int64_t r = i / Cin;
+  const int k = (int)(i - r * Cin), j = k / inner, c = k - j * inner;
+  __half hi, lo;
+  split1(w[i], hi, lo);
+  __half* d = out + r * 3 * Cin + (int64_t)j * 3 * inner + c;
+  d[0] = hi;                                                   // meets the operand's lo'
+  d[inner] = lo;                                               // meets hi
+  d[2 * inner] = __float2half_rn(__half2float(hi) * kSplitScale);   // meets hi; exact (a power of two, range checked above)
 }
 }  // namespace
 
-void launch_enc_split(const float* y, const float* res, const float* scale, int act, float* out_x, float* out_a32, __half* out_hi,
-                      __half* out_lo, int C, const BatchGeom& g, cudaStream_t s) {
+void launch_enc_split(const float* y, float y_scale, const float* res, const float* scale, int act, float* out_x, float* out_a32,
+                      __half* out_h3, int grp, int C, const BatchGeom& g, cudaStream_t s) {
   const int64_t n = (int64_t)g.B * g.Tmax * (C / 4);
-  enc_split_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(y, res, scale, act, out_x, out_a32, out_hi, out_lo, C, g);
+  enc_split_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(y, y_scale, res, scale, act, out_x, out_a32, out_h3, grp < 1 ? 1 : grp, C, g);
 }
 
-void launch_split_flat(const float* src, __half* hi, __half* lo, int64_t n, cudaStream_t s) {
-  split_flat_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(src, hi, lo, n);
+void launch_expand_w3(const float* w, __half* out, int64_t rows, int Cin, int inner, int* overflow, cudaStream_t s) {
+  const int64_t n = rows * Cin;
+  expand_w3_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(w, out, rows, Cin, inner, overflow);
 }
 
 void launch_enc_init_conv(const float* audio, int64_t audio_bstride, const float* w, const float* bias, int k, int C, float* out_y,
