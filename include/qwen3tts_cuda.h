@@ -164,7 +164,10 @@ int q3tts_codec_embed_sum_device(q3tts_codec_embedder* e, const int32_t* d_codes
  * vector quantizer (nearest codebook entry per layer, float32), first `valid_quantizers` (16) codebooks returned.
  * q3tts_encoder_load reads <dir>/config.json (`encoder_config`, Config.swift:419-560) and the `encoder.*` tensors of the
  * directory's .safetensors files with the reference's key remap (Qwen3.swift:1514-1748); a checkpoint without an
- * encoder (the "lite" variants) is Q3TTS_EFORMAT.  Only opts->device is used (the encoder computes in float32).
+ * encoder (the "lite" variants) is Q3TTS_EFORMAT.  opts->device selects the GPU; opts->precision selects the engine, both of
+ * float32 accuracy (a code is an argmin: lower precision would be a different tokenizer): Q3TTS_PREC_FP16 (the options' default)
+ * = tensor cores, every float32 operand carried as a pair of fp16 numbers and every GEMM as one tcgen05 product of three times
+ * the depth; Q3TTS_PREC_FP32 = CUDA cores.  Q3TTS_PREC_BF16 is rejected (two bf16 halves hold 16 mantissa bits).
  * audio: float32 [B, samples] (the reference's [B, 1, samples]); codes_out: int32 [B, valid_quantizers, T] with
  * T = q3tts_encode_frames(samples) = the ceil-division chain of the strides (12.5 frames per second).
  * Every utterance of a call has the same length (the reference API); encode different lengths in separate calls.     */
@@ -176,6 +179,8 @@ int q3tts_encoder_info(const q3tts_encoder* e, int32_t* valid_quantizers, int32_
                        int32_t* sampling_rate, int64_t* num_parameters);
 int64_t q3tts_encode_frames(const q3tts_encoder* e, int64_t samples);
 int q3tts_encode(q3tts_encoder* e, const float* audio, int32_t B, int64_t samples, int32_t* codes_out);
+/* kernels launched by the last q3tts_encode on this handle (benchmark bookkeeping) */
+int64_t q3tts_encoder_launch_count(const q3tts_encoder* e);
 /* debug / parity: keep stage outputs of the next encodes; q3tts_encoder_tap copies stage `name` as float32 [B, rows, C]
  * (channels last) and writes {B, rows, C} to dims; out == NULL only queries dims.  Names: "hid0".."hid3" / "res0".."res3" (the Seanet stages' hidden
  * activation and stream after the residual block), "layer3" (last strided conv), "seanet", "transformer", "downsample".                                                                   */

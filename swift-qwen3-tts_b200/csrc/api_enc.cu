@@ -57,6 +57,8 @@ int q3tts_encode(q3tts_encoder* e, const float* audio, int32_t B, int64_t sample
   });
 }
 
+int64_t q3tts_encoder_launch_count(const q3tts_encoder* e) { return (e && e->m) ? e->m->launches : -1; }
+
 int q3tts_encoder_set_taps(q3tts_encoder* e, int32_t enable) {
   if (!e || !e->m) return fail(Q3TTS_EINVAL, "q3tts_encoder_set_taps: null handle");
   std::lock_guard<std::mutex> lock(e->m->mu);

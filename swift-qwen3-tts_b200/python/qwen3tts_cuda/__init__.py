@@ -150,6 +150,7 @@ def lib() -> C.CDLL:
         "q3tts_encoder_info": (C.c_int, [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i64)]),
         "q3tts_encode_frames": (i64, [vp, i64]),
         "q3tts_encode": (C.c_int, [vp, vp, i32, i64, vp]),
+        "q3tts_encoder_launch_count": (i64, [vp]),
         "q3tts_encoder_set_taps": (C.c_int, [vp, i32]),
         "q3tts_encoder_tap": (C.c_int, [vp, cp, vp, i64, C.POINTER(i64 * 3)]),
     }
@@ -296,6 +297,9 @@ class Qwen3TTSSpeechTokenizerEncoder:
         codes = np.empty((B, self.valid_num_quantizers, self.frames(S)), dtype=np.int32)
         _check(lib().q3tts_encode(self._h, a.ctypes.data, B, S, codes.ctypes.data))
         return codes
+
+    def launch_count(self) -> int:
+        return int(lib().q3tts_encoder_launch_count(self._h))
 
     def set_taps(self, on: bool) -> None:
         _check(lib().q3tts_encoder_set_taps(self._h, 1 if on else 0))
