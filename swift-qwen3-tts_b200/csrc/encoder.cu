@@ -183,6 +183,15 @@ EncoderModel* encoder_create(const std::string& dir, const q3tts_options& opts) 
     int maxN = std::max(std::max(c.codebook_size, c.intermediate_size), (c.num_attention_heads + 2 * c.num_key_value_heads) * (c.hidden_size / c.num_attention_heads));
     for (auto& st : m.stages) maxN = std::max(maxN, 2 * st.dim);
     m.zeros = upload(m, std::vector<float>((size_t)maxN, 0.f));
+    m.inv_split = upload(m, std::vector<float>((size_t)maxN, 1.0f / kSplitScale));
+    for (size_t i = 0; i < m.layers.size(); ++i) {   // layer scale with the tensor-core GEMM's factor folded in: h += (ls / 2048) * (2048 y)
+      const std::string p = "encoder.encoder_transformer.transformer.layers." + std::to_string(i);
+      std::vector<float> a = T(ck, p + ".layer_scale_1.scale").data, b = T(ck, p + ".layer_scale_2.scale").data;
+      for (auto& v : a) v /= kSplitScale;
+      for (auto& v : b) v /= kSplitScale;
+      m.layers[i].ls1_s = upload(m, a);
+      m.layers[i].ls2_s = upload(m, b);
+    }
     int* d_flag = nullptr;
     ENC_CUDA_OK(cudaMalloc(&d_flag, sizeof(int))); m.allocs.push_back(d_flag);
     auto split_w = [&](EncGemm& g) {
@@ -260,11 +269,14 @@ bool tc_takes(const EncoderModel& m, const EncGemm& w) {
 
 // Y = (bias + conv(a)) x out_scale; returns out_scale (kSplitScale from the tensor-core GEMM, 1 from the CUDA-core fallback).
 // lda / a_bstride are in elements of the float32 form; the split form has three times as many halves per row.
-float gemm_y(EncoderModel& m, const EncGemm& w, const BatchGeom& g, const Opnd& a, int lda, int64_t a_bstride, float* Y, int ldy, int64_t y_bstride) {
+// With `res`: Y = res + s * (bias + conv(a)) at true scale (s = scale_f32 per column, or 1), res may be Y itself; returns 1.
+float gemm_y(EncoderModel& m, const EncGemm& w, const BatchGeom& g, const Opnd& a, int lda, int64_t a_bstride, float* Y, int ldy, int64_t y_bstride,
+             const float* res = nullptr, const float* scale_tc = nullptr, const float* scale_f32 = nullptr) {
   if (!tc_takes(m, w)) {
     if (!a.f32) throw Error(Q3TTS_EINVAL, "internal: CUDA-core GEMM without a float32 operand");
     ConvGemmParams e{};
     e.out_y = Y; e.ldy = ldy; e.y_bstride = y_bstride;
+    if (res) { e.res = res; e.ldres = ldy; e.res_bstride = y_bstride; e.scale = scale_f32; }
     run_gemm(m, w, g, a.f32, lda, a_bstride, e);
     return 1.0f;
   }
@@ -274,10 +286,11 @@ float gemm_y(EncoderModel& m, const EncGemm& w, const BatchGeom& g, const Opnd& 
   p.rows_per_frame = 1; p.N = w.N; p.Cin = 3 * w.Cin; p.taps = w.taps; p.dil = 1;
   p.bias = w.bias_s;
   p.out_y = Y; p.ldy = ldy; p.y_bstride = y_bstride;
+  if (res) { p.res = res; p.ldres = ldy; p.res_bstride = y_bstride; p.scale = scale_tc ? scale_tc : m.inv_split; }   // the epilogue removes the factor
   cudaError_t err = launch_conv_gemm_tc2(p, g, DT_F16, DT_F32, m.stream);
   if (err != cudaSuccess) throw Error(Q3TTS_ECUDA, std::string("encoder tcgen05 GEMM launch: ") + cudaGetErrorString(err));
   ++m.launches;
-  return kSplitScale;
+  return res ? 1.0f : kSplitScale;
 }
 
 void encode_tc(EncoderModel& m, const float* audio, int B, int64_t samples, int32_t* codes_out) {
@@ -360,9 +373,10 @@ void encode_tc(EncoderModel& m, const float* audio, int B, int64_t samples, int3
   // ---- Seanet ----
   {  // init conv on the CUDA cores (1 input channel); its elu output lands in Y[0], split for stage 0's first conv if that runs on tensor cores
     const int nf = c.num_filters;
-    launch_enc_init_conv(F(o_audio), samples, m.init_w, m.init_b, c.kernel_size, nf, F(oX[0]), F(oY[0]), P[0] * (int64_t)nf, geom(P[0], 0), s);
+    const bool tcg = tc_takes(m, m.stages[0].res3);
+    launch_enc_init_conv(F(o_audio), samples, m.init_w, m.init_b, c.kernel_size, nf, F(oX[0]), tcg ? nullptr : F(oY[0]), tcg ? Hp(oA3[0]) : nullptr,
+                         P[0] * (int64_t)nf, geom(P[0], 0), s);
     ++m.launches;
-    if (tc_takes(m, m.stages[0].res3)) split(geom(P[0], 0), nf, F(oY[0]), 1.0f, nullptr, nullptr, 0, nullptr, &m.stages[0].res3, nullptr, Hp(oA3[0]));
   }
   for (int li = 0; li < nst; ++li) {
     const EncStage& st = m.stages[(size_t)li];
@@ -374,9 +388,9 @@ void encode_tc(EncoderModel& m, const float* audio, int B, int64_t samples, int3
     float sc = gemm_y(m, st.res3, g, a, dim, Pl * dim, F(oHY[(size_t)li]), hid, Pl * hid);
     split(g, hid, F(oHY[(size_t)li]), sc, nullptr, nullptr, 1, nullptr, &st.res1, F(oHY[(size_t)li]), h.h3, true);
     m.tap_index["hid" + std::to_string(li)] = EncTap{oHY[(size_t)li], Pl, L[(size_t)li], hid};
-    sc = gemm_y(m, st.res1, g, h, hid, Pl * hid, F(oY[(size_t)li]), dim, Pl * dim);
+    gemm_y(m, st.res1, g, h, hid, Pl * hid, F(oX[(size_t)li]), dim, Pl * dim, F(oX[(size_t)li]));     // x += conv1(.) in the GEMM's epilogue
     const Opnd d{F(oY[(size_t)li]), Hp(oD3[(size_t)li])};
-    split(g, dim, F(oY[(size_t)li]), sc, F(oX[(size_t)li]), nullptr, 1, F(oX[(size_t)li]), &st.down, d.f32, d.h3);
+    split(g, dim, F(oX[(size_t)li]), 1.0f, nullptr, nullptr, 1, nullptr, &st.down, d.f32, d.h3);
     m.tap_index["res" + std::to_string(li)] = EncTap{oX[(size_t)li], Pl, L[(size_t)li], dim};
     sc = gemm_y(m, st.down, geom(L[(size_t)li + 1], li + 1), d, st.ratio * dim, Pl * dim, F(oX[(size_t)li + 1]), 2 * dim, Pn * 2 * dim);
     const EncGemm* next = li + 1 < nst ? &m.stages[(size_t)li + 1].res3 : &m.final_conv;
@@ -406,14 +420,12 @@ void encode_tc(EncoderModel& m, const float* audio, int B, int64_t samples, int3
     launch_rope(F(o_qkv), QW, nh + nkv, hd, m.inv_freq, gT, s); ++m.launches;
     launch_attention(F(o_qkv), DT_F32, F(o_ao), DT_F32, gT, nh, nkv, hd, scale / (sq * sq), (int)PT + 1, s); ++m.launches;
     split(gT, H, F(o_ao), sq, nullptr, nullptr, 0, nullptr, &Ly.o, F(o_ao), tmp.h3);
-    float sc = gemm_y(m, Ly.o, gT, Opnd{F(o_ao), tmp.h3}, H, PT * H, F(o_yt), H, PT * H);
-    split(gT, H, F(o_yt), sc, F(o_hs), Ly.ls1, 0, F(o_hs), nullptr, nullptr, nullptr);               // h += ls1 * attn
+    gemm_y(m, Ly.o, gT, Opnd{F(o_ao), tmp.h3}, H, PT * H, F(o_hs), H, PT * H, F(o_hs), Ly.ls1_s, Ly.ls1);   // h += ls1 * attn, in the epilogue
     launch_layernorm(F(o_hs), Ly.n2w, Ly.n2b, 1e-5f, F(o_nb), gT, H, s); ++m.launches;
     if (tc_takes(m, Ly.fc1)) split(gT, H, F(o_nb), 1.0f, nullptr, nullptr, 0, nullptr, &Ly.fc1, nullptr, tmp.h3);
-    sc = gemm_y(m, Ly.fc1, gT, Opnd{F(o_nb), tmp.h3}, H, PT * H, F(o_yt), I, PT * I);
+    const float sc = gemm_y(m, Ly.fc1, gT, Opnd{F(o_nb), tmp.h3}, H, PT * H, F(o_yt), I, PT * I);
     split(gT, I, F(o_yt), sc, nullptr, nullptr, 2, nullptr, &Ly.fc2, F(o_yt), tmp.h3);               // tanh-GELU, in place / split
-    sc = gemm_y(m, Ly.fc2, gT, tmp, I, PT * I, F(o_nb), H, PT * H);
-    split(gT, H, F(o_nb), sc, F(o_hs), Ly.ls2, 0, F(o_hs), nullptr, nullptr, nullptr);               // h += ls2 * mlp
+    gemm_y(m, Ly.fc2, gT, tmp, I, PT * I, F(o_hs), H, PT * H, F(o_hs), Ly.ls2_s, Ly.ls2);            // h += ls2 * mlp, in the epilogue
   }
   m.tap_index["transformer"] = EncTap{o_hs, PT, LT, H};
 
@@ -528,7 +540,7 @@ void encoder_encode(EncoderModel& m, const float* audio, int B, int64_t samples,
   };
 
   // ---- Seanet (STE.swift:436-443) ----
-  launch_enc_init_conv(F(o_audio), samples, m.init_w, m.init_b, c.kernel_size, c.num_filters, F(oX[0]), F(oA[0]),
+  launch_enc_init_conv(F(o_audio), samples, m.init_w, m.init_b, c.kernel_size, c.num_filters, F(oX[0]), F(oA[0]), nullptr,
                        P[0] * (int64_t)c.num_filters, geom(P[0], 0), s);
   ++m.launches;
   m.tap_index.clear();

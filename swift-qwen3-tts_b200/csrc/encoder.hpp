@@ -24,7 +24,7 @@ struct EncGemm {                     // [taps][N][Cin] fp32; tensor-core engine:
   __half* w3 = nullptr; float* bias_s = nullptr;   // bias x kSplitScale (zeros when there is none)
 };
 struct EncStage { EncGemm res3, res1, down; int dim = 0, ratio = 1; };                        // STE.swift:353-391
-struct EncLayer { float *n1w, *n1b, *n2w, *n2b, *ls1, *ls2; EncGemm qkv, o, fc1, fc2; };       // STE.swift:545-591
+struct EncLayer { float *n1w, *n1b, *n2w, *n2b, *ls1, *ls2; EncGemm qkv, o, fc1, fc2; float *ls1_s = nullptr, *ls2_s = nullptr; };   // STE.swift:545-591; *_s = layer scale / kSplitScale
 struct EncBook { int part = 0; EncGemm score; };                                               // score.w = E [K][D], score.bias = -|E|^2 / 2
 struct EncTap { size_t offset; int64_t slot_rows, valid_rows; int C; };
 
@@ -37,7 +37,7 @@ struct EncoderModel {
   std::mutex mu;                       // calls on one handle are serialised
   float *init_w = nullptr, *init_b = nullptr, *inv_freq = nullptr;
   bool tc = false;                     // tensor-core engine (opts.precision == Q3TTS_PREC_FP16): GEMMs as three tcgen05 products of split fp16 operands
-  float* zeros = nullptr;              // [max N] zero bias
+  float *zeros = nullptr, *inv_split = nullptr;   // [max N]: zero bias, 1 / kSplitScale
   std::vector<EncStage> stages;
   EncGemm final_conv, downsample, proj[2];
   std::vector<EncLayer> layers;

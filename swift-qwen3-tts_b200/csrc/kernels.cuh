@@ -87,8 +87,9 @@ void launch_attention(const void* qkv, int qkv_dtype, void* out, int out_dtype, 
 
 // ---- speech-tokenizer ENCODER (row N3), fp32, kernels_enc.cu --------------------------------------------------------------
 // First conv of the Seanet encoder: 1 -> C channels, k taps, causal (STE.swift:405-415): y = x' (stream), a = elu(x') (operand).
+// out_a (float32) and / or out_h3 (split form, [lo' | hi | hi] per row) may be null
 void launch_enc_init_conv(const float* audio, int64_t audio_bstride, const float* w /*[k][C]*/, const float* bias, int k, int C,
-                          float* out_y, float* out_a, int64_t out_bstride, const BatchGeom& g, cudaStream_t s);
+                          float* out_y, float* out_a, __half* out_h3, int64_t out_bstride, const BatchGeom& g, cudaStream_t s);
 // LayerNorm over C (biased variance, eps inside the sqrt, affine), one warp per valid row of [B, Tmax, C]
 void launch_layernorm(const float* x, const float* w, const float* b, float eps, float* out, const BatchGeom& g, int C, cudaStream_t s);
 // MLX RoPE(dimensions = hd, traditional = false): pairs (i, i + hd/2) of the first `heads` heads of every valid row of

@@ -12,11 +12,15 @@ namespace q3 {
 namespace {
 
 __device__ __forceinline__ float elu1(float v) { return v > 0.f ? v : expf(v) - 1.0f; }
+__device__ __forceinline__ void split1(float a, __half& hi, __half& lo) {
+  hi = __float2half_rn(a);
+  lo = __float2half_rn((a - __half2float(hi)) * kSplitScale);
+}
 
 // y[b, t, c] = bias[c] + sum_j w[j][c] * x[b, t - (k-1) + j]   (zeros before the utterance); one thread per (t, c), c fastest
 __global__ void __launch_bounds__(256)
 enc_init_conv_kernel(const float* __restrict__ audio, int64_t audio_bstride, const float* __restrict__ w, const float* __restrict__ bias, int k,
-                     int C, float* __restrict__ out_y, float* __restrict__ out_a, int64_t out_bstride, BatchGeom g) {
+                     int C, float* __restrict__ out_y, float* __restrict__ out_a, __half* __restrict__ out_h3, int64_t out_bstride, BatchGeom g) {
   // one thread per (sample, group of 4 channels): 16-byte stores, 32-bit index arithmetic (the host checks Tmax * C < 2^31)
   const int b = blockIdx.y;
   const int len = g.len_frames[b];
@@ -37,7 +41,17 @@ enc_init_conv_kernel(const float* __restrict__ audio, int64_t audio_bstride, con
   }
   const int64_t o = (int64_t)b * out_bstride + (int64_t)t * C + c;
   *(float4*)(out_y + o) = acc;
-  *(float4*)(out_a + o) = make_float4(elu1(acc.x), elu1(acc.y), elu1(acc.z), elu1(acc.w));
+  const float a[4] = {elu1(acc.x), elu1(acc.y), elu1(acc.z), elu1(acc.w)};
+  if (out_a) *(float4*)(out_a + o) = make_float4(a[0], a[1], a[2], a[3]);
+  if (out_h3) {   // the split form of the operand for a tensor-core consumer (kernels.cuh): [lo' | hi | hi] per row
+    __half h[4], l[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) split1(a[q], h[q], l[q]);
+    __half* d = out_h3 + 3 * ((int64_t)b * out_bstride + (int64_t)t * C) + c;
+    *(uint2*)d = *(const uint2*)l;
+    *(uint2*)(d + C) = *(const uint2*)h;
+    *(uint2*)(d + 2 * C) = *(const uint2*)h;
+  }
 }
 
 __global__ void __launch_bounds__(256)
@@ -109,10 +123,6 @@ vq_select_kernel(const float* __restrict__ score, int K, const float* __restrict
   const float* e = E + (int64_t)bi * D;
   float* rr = resid + row * D;
   for (int c = lane; c < D; c += 32) rr[c] = rr[c] - e[c];
-}
-__device__ __forceinline__ void split1(float a, __half& hi, __half& lo) {
-  hi = __float2half_rn(a);
-  lo = __float2half_rn((a - __half2float(hi)) * kSplitScale);
 }
 
 // one thread per (row, 4 channels)
@@ -188,10 +198,10 @@ void launch_expand_w3(const float* w, __half* out, int64_t rows, int Cin, int in
 }
 
 void launch_enc_init_conv(const float* audio, int64_t audio_bstride, const float* w, const float* bias, int k, int C, float* out_y,
-                          float* out_a, int64_t out_bstride, const BatchGeom& g, cudaStream_t s) {
+                          float* out_a, __half* out_h3, int64_t out_bstride, const BatchGeom& g, cudaStream_t s) {
   const int64_t n = (int64_t)g.Tmax * (C / 4);
   dim3 grid((unsigned)((n + 255) / 256), (unsigned)g.B);
-  enc_init_conv_kernel<<<grid, 256, 0, s>>>(audio, audio_bstride, w, bias, k, C, out_y, out_a, out_bstride, g);
+  enc_init_conv_kernel<<<grid, 256, 0, s>>>(audio, audio_bstride, w, bias, k, C, out_y, out_a, out_h3, out_bstride, g);
 }
 
 void launch_layernorm(const float* x, const float* w, const float* b, float eps, float* out, const BatchGeom& g, int C, cudaStream_t s) {
