@@ -14,7 +14,11 @@ int q3tts_encoder_load(const char* dir, const q3tts_options* opts, q3tts_encoder
   *out = nullptr;
   return guarded([&]() {
     q3tts_options o;
-    if (opts) o = *opts; else q3tts_options_default(&o);
+    q3tts_options_default(&o);
+    if (opts) {
+      if (opts->struct_size != sizeof(q3tts_options)) return fail(Q3TTS_EINVAL, "q3tts_options.struct_size mismatch");
+      o = *opts;
+    }
     std::unique_ptr<q3tts_encoder> h(new q3tts_encoder());
     h->m = q3::encoder_create(dir, o);
     *out = h.release();
