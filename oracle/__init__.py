@@ -24,4 +24,4 @@ definition-level implementation (``ops_def.py``) that shares no code with the
 fast torch path.
 """
 
-from .config import DecoderConfig, TokenizerConfig, GOLDEN_CODES_5x16  # noqa: F401
+from tools.q3cfg import DecoderConfig, EncoderConfig, TokenizerConfig, GOLDEN_CODES_5x16  # noqa: F401  (hyper-parameters live in tools/q3cfg.py so that bench.py can build a synthetic checkpoint without importing the oracle)

@@ -27,7 +27,7 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-from .config import DecoderConfig
+from tools.q3cfg import DecoderConfig
 
 STAGES = ("quantized", "pre_conv", "pre_transformer", "upsample0", "upsample1", "init_conv",
           "block0", "block1", "block2", "block3", "out_snake", "out_conv", "audio")

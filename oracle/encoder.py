@@ -29,7 +29,7 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-from .config import EncoderConfig
+from tools.q3cfg import EncoderConfig
 
 SEANET_MAPPING = {  # Qwen3.swift:1517-1528
     "encoder.encoder.layers.0.": "encoder.encoder.init_conv1d.",
@@ -112,7 +112,7 @@ def sanitize_encoder_weights(weights: Dict[str, np.ndarray]) -> Dict[str, np.nda
 def load_encoder(speech_tokenizer_dir: str):
     """config.json + weights -> (EncoderConfig, sanitized weight dict).  Raises when the checkpoint has no encoder."""
     import os
-    from .config import TokenizerConfig
+    from tools.q3cfg import TokenizerConfig
     from .weights import load_safetensors_dir
     tok = TokenizerConfig.from_json(os.path.join(speech_tokenizer_dir, "config.json"))
     if tok.encoder_config is None:

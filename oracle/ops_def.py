@@ -12,7 +12,7 @@ from typing import Dict
 
 import numpy as np
 
-from .config import DecoderConfig
+from tools.q3cfg import DecoderConfig
 
 _erf = np.vectorize(math.erf, otypes=[np.float64])
 

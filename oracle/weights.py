@@ -107,7 +107,7 @@ def load_safetensors_dir(speech_tokenizer_dir: str) -> Dict[str, np.ndarray]:
 
 def load_decoder(speech_tokenizer_dir: str):
     """config.json + weights -> (TokenizerConfig, sanitized MLX-layout weight dict)."""
-    from .config import TokenizerConfig
+    from tools.q3cfg import TokenizerConfig
     cfg = TokenizerConfig.from_json(os.path.join(speech_tokenizer_dir, "config.json"))
     if cfg.decoder_config is None:
         raise ValueError("Decoder config is required")  # SpeechTokenizer.swift:801-805
