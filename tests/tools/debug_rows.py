@@ -1,7 +1,7 @@
 """GPU debugging aid: where (rows / channels) does a stage differ from the oracle?"""
 import os, sys
 import numpy as np, torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "swift-qwen3-tts_b200", "python"))
 import qwen3tts_cuda as q
 from oracle import decoder as od, weights as ow

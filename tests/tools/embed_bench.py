@@ -1,9 +1,9 @@
 """SURVEY 8(f) N2 on the GPU: codec-embedding sum for n frames (full-size bf16 tables: 3072 x 2048 + 15 x 2048 x 2048).
 Device-resident timing with CUDA events through q3tts_codec_embed_sum_device, host-to-host timing through
 q3tts_codec_embed_sum, and the CPU oracle (torch, all host threads) on the same codes.
-usage: python tools/embed_bench.py [n_frames] [iters]"""
+usage: python tests/tools/embed_bench.py [n_frames] [iters]"""
 import ctypes as C, json, os, sys, tempfile, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "swift-qwen3-tts_b200", "python"))
 import numpy as np
 import torch

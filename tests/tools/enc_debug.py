@@ -1,6 +1,6 @@
-"""Stage-by-stage comparison of the CUDA encoder with the oracle (debugging aid).  usage: python tools/enc_debug.py [samples] [B] [tiny|full]"""
+"""Stage-by-stage comparison of the CUDA encoder with the oracle (debugging aid).  usage: python tests/tools/enc_debug.py [samples] [B] [tiny|full]"""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "swift-qwen3-tts_b200", "python"))
 import numpy as np, torch
 import qwen3tts_cuda as q
