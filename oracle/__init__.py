@@ -22,6 +22,12 @@ per-stage shape chain (Tests.swift:69-253), the initConv weight layout KAT
 Op semantics follow MLX's documented definitions, cross-checked by a second,
 definition-level implementation (``ops_def.py``) that shares no code with the
 fast torch path.
+
+``encoder.py`` is the same kind of restatement for the inverse path (SURVEY 8(f) row N3,
+``SpeechTokenizerEncoder.swift:955-1056``): Seanet encoder, RoPE transformer, downsample,
+split residual vector quantizer; also parity-unpinned at the MLX boundary (the reference
+has no test or golden vector for ``encode``), pinned against tap-by-tap definitions,
+the padding rule's known answers and the key-remap table in ``tests/test_oracle_encoder.py``.
 """
 
 from tools.q3cfg import DecoderConfig, EncoderConfig, TokenizerConfig, GOLDEN_CODES_5x16  # noqa: F401  (hyper-parameters live in tools/q3cfg.py so that bench.py can build a synthetic checkpoint without importing the oracle)
