@@ -114,3 +114,35 @@ def test_fp32_restatement_agrees_with_fp64_except_at_near_ties(tiny_enc):
     c32 = enc32.encode(a).numpy()
     bad = count_near_tie_frames(c64, c32, [m.numpy() for m in margins], tol=1e-4)
     assert bad <= 0.02 * c64.shape[0] * c64.shape[2]
+
+
+def test_split_fp16_operands_carry_float32_products():
+    # The tensor-core engine's arithmetic, emulated in NumPy: a = hi + lo'/2048 with fp16 hi, lo';
+    # [lo' | hi | hi] . [w_hi | w_lo' | 2048 w_hi] / 2048 must reproduce a . w to ~2^-21, and every scaling must be exact.
+    rng = np.random.default_rng(5)
+    K = 4096
+    a = (rng.normal(size=K) * rng.choice([1e-3, 0.05, 1.0, 30.0], size=K)).astype(np.float32)      # activations over several decades
+    w = (rng.uniform(-1, 1, size=K) * 0.05).astype(np.float32)                                      # conv weights ~ U(+-1/sqrt(fan_in))
+
+    def split(x):
+        hi = x.astype(np.float16)
+        lo = ((x - hi.astype(np.float32)) * np.float32(2048.0)).astype(np.float16)
+        return hi, lo
+
+    a_hi, a_lo = split(a)
+    w_hi, w_lo = split(w)
+    w_big = (w_hi.astype(np.float32) * np.float32(2048.0)).astype(np.float16)
+    assert np.array_equal(w_big.astype(np.float64), w_hi.astype(np.float64) * 2048.0)               # the power-of-two scaling is exact in fp16
+    assert np.isfinite(w_big).all() and np.abs(a_lo.astype(np.float32)).min() >= 0
+    acc = (a_lo.astype(np.float64) @ w_hi.astype(np.float64) + a_hi.astype(np.float64) @ w_lo.astype(np.float64)
+           + a_hi.astype(np.float64) @ w_big.astype(np.float64))
+    got = acc / 2048.0
+    exact = a.astype(np.float64) @ w.astype(np.float64)
+    scale = np.abs(a.astype(np.float64)) @ np.abs(w.astype(np.float64))
+    assert abs(got - exact) <= 2.0 ** -20 * scale                                                    # ~22 bits per operand; plain fp16 operands: 2^-10
+    plain = a_hi.astype(np.float64) @ w_hi.astype(np.float64)
+    assert abs(plain - exact) > 50 * abs(got - exact)
+    # per-element reconstruction: hi + lo'/2048 is within 2^-21 relative of the float32 value (lo' stays a NORMAL fp16 number)
+    rec = a_hi.astype(np.float64) + a_lo.astype(np.float64) / 2048.0
+    nz = np.abs(a) > 1e-4
+    assert (np.abs(rec - a)[nz] <= 2.0 ** -21 * np.abs(a)[nz]).all()
