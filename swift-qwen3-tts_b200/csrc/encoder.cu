@@ -40,7 +40,6 @@ EncGemm pack_conv(EncoderModel& m, const HostTensor& w, const HostTensor* bias, 
   EncGemm g;
   g.N = N;
   std::vector<float> packed;
-  g.inner = Cin;
   if (stride == 1) {
     g.taps = K; g.Cin = Cin;
     packed.resize((size_t)K * N * Cin);
@@ -64,7 +63,7 @@ EncGemm pack_conv(EncoderModel& m, const HostTensor& w, const HostTensor* bias, 
 
 EncGemm pack_linear(EncoderModel& m, const std::vector<const HostTensor*>& rows) {   // y = x W^T, W [out, in]; several matrices stacked
   EncGemm g;
-  g.taps = 1; g.Cin = (int)rows[0]->shape[1]; g.inner = g.Cin;
+  g.taps = 1; g.Cin = (int)rows[0]->shape[1];
   std::vector<float> packed;
   for (auto* r : rows) {
     if ((int)r->shape[1] != g.Cin) throw Error(Q3TTS_EFORMAT, "encoder: stacked linears differ in width");
@@ -173,7 +172,7 @@ EncoderModel* encoder_create(const std::string& dir, const q3tts_options& opts) 
       }
       EncBook bk;
       bk.part = part;
-      bk.score.taps = 1; bk.score.Cin = D; bk.score.N = K; bk.score.inner = D;
+      bk.score.taps = 1; bk.score.Cin = D; bk.score.N = K;
       bk.score.w = upload(m, E);
       bk.score.bias = upload(m, nc2);
       m.books.push_back(bk);

@@ -20,7 +20,6 @@ namespace q3 {
 
 struct EncGemm {                     // [taps][N][Cin] fp32; tensor-core engine: the same weights as [taps][N][3 Cin] fp16 triples (kernels.cuh)
   float* w = nullptr; float* bias = nullptr; int taps = 1, Cin = 0, N = 0;
-  int inner = 0;                     // channels of one operand row (a strided conv's Cin is stride x inner)
   __half* w3 = nullptr; float* bias_s = nullptr;   // bias x kSplitScale (zeros when there is none)
 };
 struct EncStage { EncGemm res3, res1, down; int dim = 0, ratio = 1; };                        // STE.swift:353-391
