@@ -146,3 +146,79 @@ def test_split_fp16_operands_carry_float32_products():
     rec = a_hi.astype(np.float64) + a_lo.astype(np.float64) / 2048.0
     nz = np.abs(a) > 1e-4
     assert (np.abs(rec - a)[nz] <= 2.0 ** -21 * np.abs(a)[nz]).all()
+
+
+def test_transformer_layer_matches_a_definition_level_restatement(tiny_enc):
+    # second opinion for the encoder transformer (STE.swift:473-591), written out with explicit loops in float64 and sharing no
+    # code with OracleEncoder.transformer: LayerNorm (biased variance), RoPE on pairs (i, i + d/2), causal softmax, layer scale,
+    # tanh-GELU MLP
+    import math
+    cfg, w, enc = tiny_enc
+    W = {k: np.asarray(v, dtype=np.float64) for k, v in w.items()}
+    rng = np.random.default_rng(3)
+    B, T, D = 1, 9, cfg.hidden_size
+    x = rng.normal(size=(B, D, T))                                    # NCL, like the reference
+    want = enc.transformer(torch.from_numpy(x)).numpy()
+    nh = cfg.num_attention_heads
+    hd = D // nh
+    half = hd // 2
+
+    def layer_norm(v, g, b):
+        mu = v.mean()
+        var = ((v - mu) ** 2).mean()
+        return (v - mu) / math.sqrt(var + 1e-5) * g + b
+
+    def rope(vec, pos):
+        out = vec.copy()
+        for i in range(half):
+            th = pos * cfg.rope_theta ** (-i / half)
+            c, s = math.cos(th), math.sin(th)
+            out[i] = vec[i] * c - vec[i + half] * s
+            out[i + half] = vec[i] * s + vec[i + half] * c
+        return out
+
+    h = x[0].T.copy()                                                 # [T, D]
+    for li in range(cfg.num_hidden_layers):
+        p = f"encoder.encoder_transformer.transformer.layers.{li}"
+        n1 = np.stack([layer_norm(h[t], W[f"{p}.norm1.weight"], W[f"{p}.norm1.bias"]) for t in range(T)])
+        q = n1 @ W[f"{p}.self_attn.q_proj.weight"].T
+        k = n1 @ W[f"{p}.self_attn.k_proj.weight"].T
+        v = n1 @ W[f"{p}.self_attn.v_proj.weight"].T
+        att = np.zeros((T, D))
+        for hh in range(nh):
+            sl = slice(hh * hd, (hh + 1) * hd)
+            qr = np.stack([rope(q[t, sl], t) for t in range(T)])
+            kr = np.stack([rope(k[t, sl], t) for t in range(T)])
+            for t in range(T):
+                sc = np.array([qr[t] @ kr[u] * hd ** -0.5 for u in range(t + 1)])      # causal: keys 0..t only
+                pr = np.exp(sc - sc.max())
+                pr /= pr.sum()
+                att[t, sl] = pr @ v[: t + 1, sl]
+        h = h + W[f"{p}.layer_scale_1.scale"] * (att @ W[f"{p}.self_attn.o_proj.weight"].T)
+        n2 = np.stack([layer_norm(h[t], W[f"{p}.norm2.weight"], W[f"{p}.norm2.bias"]) for t in range(T)])
+        m = n2 @ W[f"{p}.gating.linear1.weight"].T
+        m = m * 0.5 * (1.0 + np.tanh(0.7978845608 * (m + 0.044715 * m ** 3)))
+        h = h + W[f"{p}.layer_scale_2.scale"] * (m @ W[f"{p}.gating.linear2.weight"].T)
+    assert np.abs(h.T - want[0]).max() < 1e-10
+
+
+def test_quantizer_matches_a_brute_force_nearest_neighbour_search(tiny_enc):
+    # STE.swift:746-759: argmin(|E|^2/2 - x.E^T) is the nearest codebook entry in Euclidean distance; the residual chain by hand
+    cfg, w, enc = tiny_enc
+    rng = np.random.default_rng(9)
+    x = rng.normal(size=(1, cfg.hidden_size, 5)) * 0.7
+    got = enc.quantize(torch.from_numpy(x)).numpy()[0]                # [16, 5]
+    W = {k: np.asarray(v, dtype=np.float64) for k, v in w.items()}
+    row = 0
+    for part, n in (("rvq_first", 1), ("rvq_rest", 15)):
+        r = x[0].T @ W[f"encoder.quantizer.{part}.input_proj.weight"][:, 0, :].T       # [5, cb]
+        for i in range(n):
+            b = f"encoder.quantizer.{part}.vq.layers.{i}.codebook"
+            E = W[f"{b}.embeddingSum"] / np.maximum(W[f"{b}.clusterUsage"], 1e-5)[:, None]
+            for t in range(5):
+                d2 = ((E - r[t]) ** 2).sum(-1)
+                order = np.argsort(d2)
+                if d2[order[1]] - d2[order[0]] > 1e-4:                 # (the oracle searches in float32: skip genuine near-ties)
+                    assert got[row, t] == order[0], (part, i, t)
+                r[t] = r[t] - E[got[row, t]]
+            row += 1
